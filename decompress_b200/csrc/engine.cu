@@ -1,0 +1,227 @@
+// decompress_b200/csrc/engine.cu — the C ABI (include/dcmp.h) over the CUDA kernels.
+//
+// Host-side plumbing only: device/stream ownership, scratch buffers, host<->device
+// staging for the *_batch entry points, kernel dispatch.  No codec logic lives here
+// and nothing here can run a stream on the CPU: without a device every compute call
+// fails with DCMP_API_NO_DEVICE.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+#include <algorithm>
+#include <vector>
+#include "../../include/dcmp.h"
+
+namespace dcmp {
+void launch_inflate_serial(int fmt, int64_t n, const uint8_t *src_base, const int64_t *src_off, const int64_t *src_len,
+                           uint8_t *dst_base, const int64_t *dst_off, const int64_t *dst_cap, int64_t *consumed,
+                           int64_t *produced, int32_t *status, const int32_t *todo, cudaStream_t stream);
+}
+
+static thread_local char g_err[512] = "";
+static void set_err(const char *what, cudaError_t e) {
+  snprintf(g_err, sizeof g_err, "%s: %s (%s)", what, cudaGetErrorName(e), cudaGetErrorString(e));
+}
+#define CU(call)                                         \
+  do {                                                   \
+    cudaError_t e_ = (call);                             \
+    if (e_ != cudaSuccess) {                             \
+      set_err(#call, e_);                                \
+      return e_ == cudaErrorMemoryAllocation ? DCMP_API_OUT_OF_MEMORY : DCMP_API_CUDA_ERROR; \
+    }                                                    \
+  } while (0)
+
+struct dcmp_engine {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  uint8_t *d_buf = nullptr; // one growable device arena: [src | dst | tables]
+  size_t d_cap = 0;
+  int64_t launches = 0;
+  int reserve(size_t bytes) {
+    if (bytes <= d_cap) return DCMP_API_OK;
+    if (d_buf) { CU(cudaFree(d_buf)); d_buf = nullptr; d_cap = 0; }
+    size_t want = bytes + (bytes >> 3) + (1 << 20);
+    CU(cudaMalloc(&d_buf, want));
+    d_cap = want;
+    return DCMP_API_OK;
+  }
+};
+
+extern "C" {
+
+int dcmp_abi_version(void) { return DCMP_ABI_VERSION; }
+
+int dcmp_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+const char *dcmp_last_error(void) { return g_err; }
+
+const char *dcmp_status_string(int s) {
+  switch (s) {
+  case DCMP_OK: return "Ok";
+  case DCMP_UNEXPECTED_END_OF_INPUT: return "Unexpected end of input";
+  case DCMP_UNEXPECTED_END_OF_OUTPUT: return "Unexpected end of output";
+  case DCMP_INVALID_KIND_OF_BLOCK: return "Invalid kind of block";
+  case DCMP_INVALID_DICTIONARY: return "Invalid dictionary";
+  case DCMP_INVALID_COMPLEMENT_OF_LENGTH: return "Invalid complement of length";
+  case DCMP_INVALID_DISTANCE: return "Invalid distance";
+  case DCMP_INVALID_DISTANCE_CODE: return "Invalid distance code";
+  case DCMP_REF_EXCEPTION: return "Reference raises an exception (index out of bounds)";
+  case DCMP_INVALID_HEADER: return "Invalid header";
+  case DCMP_INVALID_CHECKSUM: return "Invalid checksum";
+  case DCMP_INVALID_GZIP_HEADER: return "Invalid GZip header";
+  case DCMP_INVALID_GZIP_HEADER_CHECKSUM: return "Invalid GZip header checksum";
+  case DCMP_INVALID_INPUT_SIZE: return "Invalid input size";
+  case DCMP_LZO_MALFORMED: return "Malformed";
+  case DCMP_LZO_INVALID_ARGUMENT: return "Input is malformed or output is not large enough";
+  case DCMP_LZO_INVALID_DICTIONARY: return "Invalid dictionary";
+  case DCMP_INVALID_COMPRESSION_LEVEL: return "Invalid compression level";
+  default: return "?";
+  }
+}
+
+int dcmp_engine_create(int device, dcmp_engine **out) {
+  if (!out) return DCMP_API_INVALID_ARGUMENT;
+  *out = nullptr;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    cudaGetLastError();
+    snprintf(g_err, sizeof g_err, "no CUDA device (%s); libdcmp_b200 has no CPU fallback", cudaGetErrorName(e));
+    return DCMP_API_NO_DEVICE;
+  }
+  if (device < 0 || device >= n) return DCMP_API_INVALID_ARGUMENT;
+  CU(cudaSetDevice(device));
+  dcmp_engine *eng = new dcmp_engine();
+  eng->device = device;
+  cudaError_t se = cudaStreamCreateWithFlags(&eng->stream, cudaStreamNonBlocking);
+  if (se != cudaSuccess) { set_err("cudaStreamCreate", se); delete eng; return DCMP_API_CUDA_ERROR; }
+  *out = eng;
+  return DCMP_API_OK;
+}
+
+void dcmp_engine_destroy(dcmp_engine *e) {
+  if (!e) return;
+  cudaSetDevice(e->device);
+  if (e->d_buf) cudaFree(e->d_buf);
+  if (e->stream) cudaStreamDestroy(e->stream);
+  delete e;
+}
+
+int64_t dcmp_engine_launch_count(const dcmp_engine *e) { return e ? e->launches : 0; }
+
+int dcmp_inflate_batch_device(dcmp_engine *e, int fmt, int64_t n, const uint8_t *d_src_base, const int64_t *d_src_off,
+                              const int64_t *d_src_len, uint8_t *d_dst_base, const int64_t *d_dst_off,
+                              const int64_t *d_dst_cap, int64_t *d_consumed, int64_t *d_produced, int32_t *d_status,
+                              void *cuda_stream) {
+  if (!e) return DCMP_API_INVALID_ARGUMENT;
+  if (fmt != DCMP_FMT_RAW && fmt != DCMP_FMT_ZLIB) return DCMP_API_INVALID_ARGUMENT;
+  if (n < 0) return DCMP_API_INVALID_ARGUMENT;
+  if (n == 0) return DCMP_API_OK;
+  CU(cudaSetDevice(e->device));
+  cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : e->stream;
+  dcmp::launch_inflate_serial(fmt, n, d_src_base, d_src_off, d_src_len, d_dst_base, d_dst_off, d_dst_cap, d_consumed,
+                              d_produced, d_status, nullptr, st);
+  e->launches += 1;
+  CU(cudaGetLastError());
+  return DCMP_API_OK;
+}
+
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+int dcmp_inflate_batch(dcmp_engine *e, int fmt, int64_t n, const uint8_t *src_base, const int64_t *src_off,
+                       const int64_t *src_len, uint8_t *dst_base, const int64_t *dst_off, const int64_t *dst_cap,
+                       int64_t *consumed, int64_t *produced, int32_t *status) {
+  if (!e) return DCMP_API_INVALID_ARGUMENT;
+  if (n < 0) return DCMP_API_INVALID_ARGUMENT;
+  if (n == 0) return DCMP_API_OK;
+  if (!src_off || !src_len || !dst_off || !dst_cap || !consumed || !produced || !status)
+    return DCMP_API_INVALID_ARGUMENT;
+  CU(cudaSetDevice(e->device));
+  // Spans of the host slabs actually referenced.
+  int64_t s_lo = INT64_MAX, s_hi = 0, d_lo = INT64_MAX, d_hi = 0;
+  for (int64_t k = 0; k < n; k++) {
+    if (src_len[k] < 0 || dst_cap[k] < 0 || src_off[k] < 0 || dst_off[k] < 0) return DCMP_API_INVALID_ARGUMENT;
+    s_lo = std::min(s_lo, src_off[k]); s_hi = std::max(s_hi, src_off[k] + src_len[k]);
+    d_lo = std::min(d_lo, dst_off[k]); d_hi = std::max(d_hi, dst_off[k] + dst_cap[k]);
+  }
+  size_t s_bytes = (size_t)(s_hi - s_lo), d_bytes = (size_t)(d_hi - d_lo);
+  if ((s_bytes && !src_base) || (d_bytes && !dst_base)) return DCMP_API_INVALID_ARGUMENT;
+  size_t o_src = 0;
+  size_t o_dst = align_up(o_src + s_bytes + 16, 256);
+  size_t o_tab = align_up(o_dst + d_bytes + 16, 256);
+  size_t tab_bytes = (size_t)n * (8 * 6 + 4);
+  int rc = e->reserve(o_tab + tab_bytes + 256);
+  if (rc != DCMP_API_OK) return rc;
+  // Offset tables rebased to the spans, packed into one upload.
+  std::vector<int64_t> tab((size_t)n * 4);
+  for (int64_t k = 0; k < n; k++) {
+    tab[k] = src_off[k] - s_lo;
+    tab[n + k] = src_len[k];
+    tab[2 * n + k] = dst_off[k] - d_lo;
+    tab[3 * n + k] = dst_cap[k];
+  }
+  uint8_t *d_src = e->d_buf + o_src, *d_dst = e->d_buf + o_dst;
+  int64_t *d_tab = (int64_t *)(e->d_buf + o_tab);
+  int64_t *d_cons = d_tab + 4 * n, *d_prod = d_tab + 5 * n;
+  int32_t *d_stat = (int32_t *)(d_tab + 6 * n);
+  cudaStream_t st = e->stream;
+  CU(cudaMemcpyAsync(d_tab, tab.data(), (size_t)n * 32, cudaMemcpyHostToDevice, st));
+  if (s_bytes) CU(cudaMemcpyAsync(d_src, src_base + s_lo, s_bytes, cudaMemcpyHostToDevice, st));
+  rc = dcmp_inflate_batch_device(e, fmt, n, d_src, d_tab, d_tab + n, d_dst, d_tab + 2 * n, d_tab + 3 * n, d_cons,
+                                 d_prod, d_stat, st);
+  if (rc != DCMP_API_OK) return rc;
+  CU(cudaMemcpyAsync(consumed, d_cons, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(produced, d_prod, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(status, d_stat, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+  if (d_bytes) CU(cudaMemcpyAsync(dst_base + d_lo, d_dst, d_bytes, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  return DCMP_API_OK;
+}
+
+int dcmp_inf_ns_inflate(dcmp_engine *e, const uint8_t *src, int64_t src_len, uint8_t *dst, int64_t dst_len,
+                        int64_t *consumed, int64_t *produced) {
+  int64_t zero = 0;
+  int32_t status = 0;
+  int rc = dcmp_inflate_batch(e, DCMP_FMT_RAW, 1, src, &zero, &src_len, dst, &zero, &dst_len, consumed, produced, &status);
+  return rc != DCMP_API_OK ? rc : status;
+}
+
+int dcmp_zl_inf_ns_inflate(dcmp_engine *e, const uint8_t *src, int64_t src_len, uint8_t *dst, int64_t dst_len,
+                           int64_t *consumed, int64_t *produced) {
+  int64_t zero = 0;
+  int32_t status = 0;
+  int rc = dcmp_inflate_batch(e, DCMP_FMT_ZLIB, 1, src, &zero, &src_len, dst, &zero, &dst_len, consumed, produced, &status);
+  return rc != DCMP_API_OK ? rc : status;
+}
+
+uint32_t dcmp_adler32(uint32_t adler, const uint8_t *p, int64_t n) {
+  uint32_t a = adler & 0xffff, b = (adler >> 16) & 0xffff;
+  while (n > 0) {
+    int64_t k = n < 5552 ? n : 5552;
+    n -= k;
+    while (k--) { a += *p++; b += a; }
+    a %= 65521; b %= 65521;
+  }
+  return (b << 16) | a;
+}
+
+uint32_t dcmp_crc32(uint32_t crc, const uint8_t *p, int64_t n) {
+  static uint32_t table[256];
+  static bool ready = false;
+  if (!ready) {
+    for (uint32_t i = 0; i < 256; i++) {
+      uint32_t c = i;
+      for (int k = 0; k < 8; k++) c = (c & 1) ? 0xedb88320u ^ (c >> 1) : c >> 1;
+      table[i] = c;
+    }
+    ready = true;
+  }
+  uint32_t c = crc ^ 0xffffffffu;
+  while (n--) c = table[(c ^ *p++) & 0xff] ^ (c >> 8);
+  return c ^ 0xffffffffu;
+}
+
+} // extern "C"

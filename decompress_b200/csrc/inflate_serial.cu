@@ -1,0 +1,362 @@
+// decompress_b200/csrc/inflate_serial.cu — general-purpose inflate kernel, one warp per stream.
+//
+// Replaces De.Inf.Ns.inflate (lib/de.ml:1534-1823) for n independent streams.  This is
+// the *general* path: any block mix (stored / fixed / dynamic), any output size,
+// every reference error class.  The warp executes the bit decode uniformly (all lanes
+// hold the same bit cursor; table reads are shared-memory broadcasts) and spreads the
+// byte work — stored-block copies, LZ77 back-references — over its 32 lanes.  The
+// sub-chunk-parallel kernel for the C2 workload lives in inflate_parallel.cu; it falls
+// back to this one for streams it cannot take.
+//
+// Input-exhaustion semantics.  The reference's observable behaviour depends only on the
+// bit cursor c (bits consumed) and the input length n, not on its 16-bit refill
+// schedule (proof sketch in DESIGN.md §"Bit cursor"):
+//   * header-side reads (`_fill_bits`, de.ml:1629-1641) of k bits fail with
+//     Unexpected_end_of_input iff 8n - c < k (k = 3, 14, 3 per HCLEN code, the CODES
+//     table's max length per code-length symbol, 2/3/7 for the repeats);
+//   * reads inside a compressed block (`__fill_bits`, de.ml:1643-1654) never fail; past
+//     the end they see zero bits;
+//   * after the final block consumed = ceil(c/8), or, when c ran past the input,
+//     n - ((8n - c) lsr 3) in 63-bit OCaml arithmetic (de.ml:1805).
+#include "inflate_tables.cuh"
+
+namespace dcmp {
+
+constexpr int SERIAL_WARPS = 4;
+
+struct WarpScratch {
+  uint32_t lit[LIT_TABLE_SIZE];
+  uint32_t dist[DIST_TABLE_SIZE];
+  uint32_t codes[CODES_TABLE_SIZE];
+  uint16_t work[MAX_LENS];
+  uint8_t lens[MAX_LENS];
+};
+
+struct BitCursor {
+  const uint8_t *p;
+  int64_t n;    // input length in bytes
+  int64_t pos;  // next byte to load (may run past n: virtual zeros)
+  uint64_t hold;
+  int bits;     // loaded bits in hold
+  __device__ __forceinline__ void init(const uint8_t *p_, int64_t n_) { p = p_; n = n_; pos = 0; hold = 0; bits = 0; }
+  __device__ __forceinline__ void refill() { // afterwards bits >= 33
+    if (bits <= 32) {
+      uint32_t w;
+      if (pos + 4 <= n) {
+        w = (uint32_t)p[pos] | ((uint32_t)p[pos + 1] << 8) | ((uint32_t)p[pos + 2] << 16) | ((uint32_t)p[pos + 3] << 24);
+      } else {
+        w = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+          if (pos + k < n) w |= (uint32_t)p[pos + k] << (8 * k);
+      }
+      hold |= (uint64_t)w << bits;
+      bits += 32;
+      pos += 4;
+    }
+  }
+  __device__ __forceinline__ int64_t consumed_bits() const { return 8 * pos - bits; }
+  __device__ __forceinline__ int64_t real_bits_left() const { return 8 * n - consumed_bits(); }
+  __device__ __forceinline__ uint32_t peek(int k) const { return (uint32_t)hold & ((1u << k) - 1u); }
+  __device__ __forceinline__ void drop(int k) { hold >>= k; bits -= k; }
+  __device__ __forceinline__ uint32_t pop(int k) { uint32_t v = peek(k); drop(k); return v; }
+  __device__ __forceinline__ void seek_byte(int64_t byte_pos) { pos = byte_pos; hold = 0; bits = 0; }
+};
+
+__device__ __forceinline__ uint32_t lookup(const uint32_t *tbl, int root, uint64_t hold) {
+  uint32_t e = tbl[(uint32_t)hold & ((1u << root) - 1u)];
+  if (e_kind(e) == K_LINK) e = tbl[e_base(e) + (((uint32_t)(hold >> root)) & ((1u << e_extra(e)) - 1u))];
+  return e;
+}
+
+struct StreamOut {
+  uint8_t *o;
+  int64_t cap;
+  int64_t pos;
+};
+
+// literal/length/distance loop, de.ml:1667-1712.  Returns a DCMP_* status (DCMP_OK = EOB seen).
+__device__ int inflate_block(BitCursor &br, StreamOut &out, const uint32_t *lit, int lit_root,
+                             const uint32_t *dist, int dist_root, int lane) {
+  for (;;) {
+    br.refill();
+    uint32_t e = lookup(lit, lit_root, br.hold);
+    uint32_t kind = e_kind(e);
+    if (kind == K_INVALID) return DCMP_REF_EXCEPTION;
+    br.drop(e_len(e));
+    if (kind == K_LIT) {
+      if (out.pos >= out.cap) return DCMP_UNEXPECTED_END_OF_OUTPUT;
+      if (lane == 0) out.o[out.pos] = (uint8_t)e_base(e);
+      out.pos++;
+      continue;
+    }
+    if (kind == K_EOB) return DCMP_OK;
+    int ext = e_extra(e);
+    int len = (int)e_base(e) + (int)br.pop(ext);
+    br.refill();
+    uint32_t d = lookup(dist, dist_root, br.hold);
+    if (e_kind(d) == K_INVALID) return DCMP_REF_EXCEPTION;
+    br.drop(e_len(d));
+    int dext = e_extra(d);
+    int64_t dd = (int64_t)e_base(d) + (int64_t)br.pop(dext);
+    if (e_base(d) == 0) return DCMP_INVALID_DISTANCE_CODE; // _base_dist = -1, de.ml:1698-1699
+    if (dd > (out.pos < 32768 ? out.pos : 32768)) return DCMP_INVALID_DISTANCE;
+    if (len > out.cap - out.pos) return DCMP_UNEXPECTED_END_OF_OUTPUT;
+    __syncwarp(); // earlier stores of every lane are visible to the loads below
+    {
+      const uint8_t *s = out.o + out.pos - dd;
+      uint8_t *t = out.o + out.pos;
+      // byte k of the match is source byte (k mod dd): all sources precede out.pos
+      for (int k = lane; k < len; k += 32) {
+        int sk = dd >= len ? k : (int)(k % dd);
+        t[k] = s[sk];
+      }
+    }
+    out.pos += len;
+  }
+}
+
+__device__ int decode_dynamic_header(BitCursor &br, WarpScratch &ws, int lane, TableInfo &li, TableInfo &di) {
+  // de.ml:1788-1793
+  br.refill();
+  if (br.real_bits_left() < 14) return DCMP_UNEXPECTED_END_OF_INPUT;
+  int hlit = (int)br.pop(5) + 257;
+  int hdist = (int)br.pop(5) + 1;
+  int hclen = (int)br.pop(4) + 4;
+  // de.ml:1771-1786
+  __syncwarp();
+  if (lane < 19) ws.lens[lane] = 0;
+  __syncwarp();
+  for (int i = 0; i < hclen; i++) {
+    br.refill();
+    if (br.real_bits_left() < 3) return DCMP_UNEXPECTED_END_OF_INPUT;
+    uint32_t v = br.pop(3);
+    if (lane == 0) ws.lens[c_zigzag[i]] = (uint8_t)v;
+  }
+  __syncwarp();
+  int rc = 0;
+  TableInfo ci;
+  if (lane == 0) rc = build_decode_table(KIND_CODES, ws.lens, 19, ws.codes, CODES_TABLE_SIZE, ws.work, &ci);
+  rc = __shfl_sync(0xffffffffu, rc, 0);
+  ci.root = __shfl_sync(0xffffffffu, ci.root, 0);
+  ci.maxl = __shfl_sync(0xffffffffu, ci.maxl, 0);
+  if (rc == TBL_INVALID) return DCMP_INVALID_DICTIONARY;
+  if (rc == TBL_EXCEPTION) return DCMP_REF_EXCEPTION;
+  __syncwarp();
+  // de.ml:1733-1769
+  const int max_res = hlit + hdist;
+  int i = 0;
+  int prev = 0;
+  while (i < max_res) {
+    br.refill();
+    if (br.real_bits_left() < ci.maxl) return DCMP_UNEXPECTED_END_OF_INPUT;
+    uint32_t e = ws.codes[br.peek(ci.maxl)];
+    if (e_kind(e) == K_INVALID) return DCMP_REF_EXCEPTION;
+    br.drop(e_len(e));
+    int v = (int)e_base(e);
+    int copy, fillv;
+    if (v < 16) {
+      if (lane == 0) ws.lens[i] = (uint8_t)v;
+      prev = v;
+      i++;
+      continue;
+    } else if (v == 16) {
+      if (i == 0) return DCMP_INVALID_DICTIONARY;
+      if (br.real_bits_left() < 2) return DCMP_UNEXPECTED_END_OF_INPUT;
+      copy = (int)br.pop(2) + 3; fillv = prev;
+    } else if (v == 17) {
+      if (br.real_bits_left() < 3) return DCMP_UNEXPECTED_END_OF_INPUT;
+      copy = (int)br.pop(3) + 3; fillv = 0;
+    } else {
+      if (br.real_bits_left() < 7) return DCMP_UNEXPECTED_END_OF_INPUT;
+      copy = (int)br.pop(7) + 11; fillv = 0;
+    }
+    if (i + copy > max_res) return DCMP_INVALID_DICTIONARY;
+    for (int x = lane; x < copy; x += 32) ws.lens[i + x] = (uint8_t)fillv;
+    prev = fillv;
+    i += copy;
+  }
+  __syncwarp();
+  // de.ml:1718-1731
+  if (ws.lens[256] == 0) return DCMP_INVALID_DICTIONARY;
+  int rl = 0, rd = 0;
+  if (lane == 0) {
+    rl = build_decode_table(KIND_LENS, ws.lens, hlit, ws.lit, LIT_TABLE_SIZE, ws.work, &li);
+    if (rl == TBL_OK) rd = build_decode_table(KIND_DISTS, ws.lens + hlit, hdist, ws.dist, DIST_TABLE_SIZE, ws.work, &di);
+  }
+  rl = __shfl_sync(0xffffffffu, rl, 0);
+  rd = __shfl_sync(0xffffffffu, rd, 0);
+  li.root = __shfl_sync(0xffffffffu, li.root, 0);
+  li.maxl = __shfl_sync(0xffffffffu, li.maxl, 0);
+  di.root = __shfl_sync(0xffffffffu, di.root, 0);
+  di.maxl = __shfl_sync(0xffffffffu, di.maxl, 0);
+  if (rl == TBL_INVALID || rd == TBL_INVALID) return (rl == TBL_EXCEPTION) ? DCMP_REF_EXCEPTION : DCMP_INVALID_DICTIONARY;
+  if (rl == TBL_EXCEPTION || rd == TBL_EXCEPTION) return DCMP_REF_EXCEPTION;
+  __syncwarp();
+  return DCMP_OK;
+}
+
+__device__ void build_fixed_tables(WarpScratch &ws, int lane, TableInfo &li, TableInfo &di) {
+  // de.ml:821-833
+  __syncwarp();
+  for (int n = lane; n < 288; n += 32) ws.lens[n] = n < 144 ? 8 : n < 256 ? 9 : n < 280 ? 7 : 8;
+  if (lane < 32) ws.lens[288 + lane] = 5;
+  __syncwarp();
+  if (lane == 0) {
+    build_decode_table(KIND_LENS, ws.lens, 288, ws.lit, LIT_TABLE_SIZE, ws.work, &li);
+    build_decode_table(KIND_DISTS, ws.lens + 288, 32, ws.dist, DIST_TABLE_SIZE, ws.work, &di);
+  }
+  li.root = __shfl_sync(0xffffffffu, li.root, 0);
+  li.maxl = __shfl_sync(0xffffffffu, li.maxl, 0);
+  di.root = __shfl_sync(0xffffffffu, di.root, 0);
+  di.maxl = __shfl_sync(0xffffffffu, di.maxl, 0);
+  __syncwarp();
+}
+
+// De.Inf.Ns.inflate for one stream, executed by one warp.
+__device__ int inflate_stream_warp(const uint8_t *src, int64_t n, uint8_t *dst, int64_t cap, WarpScratch &ws,
+                                   int lane, int64_t *consumed, int64_t *produced) {
+  BitCursor br;
+  br.init(src, n);
+  StreamOut out{dst, cap, 0};
+  int status = DCMP_OK;
+  TableInfo li{0, 0}, di{0, 0};
+  bool fixed_ready = false; // consecutive fixed blocks reuse the tables
+  for (;;) {
+    // de.ml:1795-1805
+    br.refill();
+    if (br.real_bits_left() < 3) { status = DCMP_UNEXPECTED_END_OF_INPUT; break; }
+    bool last = br.pop(1) == 1;
+    uint32_t type = br.pop(2);
+    if (type == 0) {
+      // de.ml:1613-1627
+      int64_t ip = (br.consumed_bits() + 7) >> 3;
+      if (n - ip < 4) { status = DCMP_UNEXPECTED_END_OF_INPUT; break; }
+      int len = src[ip] | (src[ip + 1] << 8);
+      int nlen = src[ip + 2] | (src[ip + 3] << 8);
+      ip += 4;
+      if (nlen != 0xffff - len) { status = DCMP_INVALID_COMPLEMENT_OF_LENGTH; break; }
+      if (len > n - ip) { status = DCMP_UNEXPECTED_END_OF_INPUT; break; }
+      if (len > out.cap - out.pos) { status = DCMP_UNEXPECTED_END_OF_OUTPUT; break; }
+      for (int k = lane; k < len; k += 32) out.o[out.pos + k] = src[ip + k];
+      out.pos += len;
+      br.seek_byte(ip + len);
+    } else if (type == 3) {
+      status = DCMP_INVALID_KIND_OF_BLOCK;
+      break;
+    } else {
+      if (type == 1) {
+        if (!fixed_ready) build_fixed_tables(ws, lane, li, di);
+        fixed_ready = true;
+      } else {
+        fixed_ready = false;
+        status = decode_dynamic_header(br, ws, lane, li, di);
+        if (status != DCMP_OK) break;
+      }
+      status = inflate_block(br, out, ws.lit, li.root, ws.dist, di.root, lane);
+      if (status != DCMP_OK) break;
+    }
+    if (last) break;
+  }
+  __syncwarp();
+  int64_t c = br.consumed_bits();
+  int64_t r = 8 * n - c;
+  int64_t cons;
+  if (status != DCMP_OK) cons = (c + 7) >> 3 > n ? n : (c + 7) >> 3;
+  else if (r >= 0) cons = (c + 7) >> 3;
+  else cons = n - (int64_t)(((uint64_t)r & 0x7fffffffffffffffULL) >> 3); // de.ml:1805 on a negative 63-bit int
+  *consumed = cons;
+  *produced = out.pos;
+  return status;
+}
+
+__device__ uint32_t warp_adler32(const uint8_t *p, int64_t n, int lane) {
+  // RFC1950 Adler-32 of p[0..n): lanes take contiguous slices, then combine
+  // (A,B) pairs: B_total = sum_i (B_i + A_i * bytes_after_i) + n (for the initial 1).
+  const uint32_t MOD = 65521u;
+  int64_t per = (n + 31) / 32;
+  int64_t lo = per * lane, hi = lo + per;
+  if (lo > n) lo = n;
+  if (hi > n) hi = n;
+  uint64_t a = 0, b = 0;
+  int64_t i = lo;
+  while (i < hi) {
+    int64_t stop = i + 2048 < hi ? i + 2048 : hi; // a,b < 2^64 trivially; reduce per chunk
+    uint64_t a0 = a;
+    uint64_t sa = 0, sb = 0;
+    for (int64_t k = i; k < stop; k++) { sa += p[k]; sb += sa; }
+    b = (b + a0 * (uint64_t)(stop - i) + sb) % MOD;
+    a = (a + sa) % MOD;
+    i = stop;
+  }
+  uint64_t after = (uint64_t)(n - hi);
+  uint64_t bc = (b + (a * (after % MOD)) % MOD) % MOD;
+  for (int o = 16; o > 0; o >>= 1) {
+    a += __shfl_xor_sync(0xffffffffu, a, o);
+    bc += __shfl_xor_sync(0xffffffffu, bc, o);
+  }
+  uint32_t A = (uint32_t)((1 + a) % MOD);
+  uint32_t B = (uint32_t)((bc + (uint64_t)(n % MOD)) % MOD);
+  return (B << 16) | A;
+}
+
+__global__ void __launch_bounds__(SERIAL_WARPS * 32)
+inflate_serial_kernel(int fmt, int64_t nstreams, const uint8_t *src_base, const int64_t *src_off, const int64_t *src_len,
+                      uint8_t *dst_base, const int64_t *dst_off, const int64_t *dst_cap, int64_t *consumed,
+                      int64_t *produced, int32_t *status, const int32_t *todo) {
+  __shared__ WarpScratch scratch[SERIAL_WARPS];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  int64_t slot = (int64_t)blockIdx.x * SERIAL_WARPS + warp;
+  if (slot >= nstreams) return;
+  int64_t k = todo ? (int64_t)todo[slot] : slot;
+  const uint8_t *src = src_base + src_off[k];
+  int64_t n = src_len[k];
+  uint8_t *dst = dst_base + dst_off[k];
+  int64_t cap = dst_cap[k];
+  int64_t cons = 0, prod = 0;
+  int st;
+  if (fmt == DCMP_FMT_RAW) {
+    st = inflate_stream_warp(src, n, dst, cap, scratch[warp], lane, &cons, &prod);
+  } else {
+    // Zl.Inf.Ns.inflate, lib/zl.ml:391-417
+    if (n < 2) st = DCMP_UNEXPECTED_END_OF_INPUT;
+    else {
+      uint32_t cmf = src[0], flg = src[1];
+      if (((cmf << 8) + flg) % 31 != 0 || (cmf & 15) != 8) st = DCMP_INVALID_HEADER;
+      else if (n < 6) st = DCMP_REF_EXCEPTION; // bigstring_sub src 2 (len - 6) raises
+      else {
+        int64_t i = 0;
+        st = inflate_stream_warp(src + 2, n - 6, dst, cap, scratch[warp], lane, &i, &prod);
+        if (st == DCMP_OK) {
+          if (n < i + 6) st = DCMP_UNEXPECTED_END_OF_INPUT;
+          else if (i < -2) st = DCMP_REF_EXCEPTION;
+          else {
+            uint32_t want = ((uint32_t)src[i + 2] << 24) | ((uint32_t)src[i + 3] << 16) |
+                            ((uint32_t)src[i + 4] << 8) | (uint32_t)src[i + 5];
+            __syncwarp();
+            uint32_t got = warp_adler32(dst, prod, lane);
+            if (want != got) st = DCMP_INVALID_CHECKSUM;
+            else cons = i + 6;
+          }
+        }
+      }
+    }
+  }
+  if (lane == 0) {
+    consumed[k] = cons;
+    produced[k] = prod;
+    status[k] = st;
+  }
+}
+
+void launch_inflate_serial(int fmt, int64_t n, const uint8_t *src_base, const int64_t *src_off, const int64_t *src_len,
+                           uint8_t *dst_base, const int64_t *dst_off, const int64_t *dst_cap, int64_t *consumed,
+                           int64_t *produced, int32_t *status, const int32_t *todo, cudaStream_t stream) {
+  if (n <= 0) return;
+  int64_t blocks = (n + SERIAL_WARPS - 1) / SERIAL_WARPS;
+  inflate_serial_kernel<<<(unsigned)blocks, SERIAL_WARPS * 32, 0, stream>>>(
+      fmt, n, src_base, src_off, src_len, dst_base, dst_off, dst_cap, consumed, produced, status, todo);
+}
+
+} // namespace dcmp

@@ -1,0 +1,26 @@
+"""Mirror of lib/zl.mli for the GPU-backed path: Zl.Inf.Ns.inflate (zl.ml:400-417)."""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from .de import _as_u8
+from .result import Error, Ok
+
+
+class Inf:
+    class Ns:
+        @staticmethod
+        def inflate(src, dst, engine=None):
+            eng = engine or _lib.default_engine()
+            s = np.ascontiguousarray(_as_u8(src))
+            d = _as_u8(dst, writable=True)
+            cons, prod = C.c_int64(0), C.c_int64(0)
+            st = _lib.lib().dcmp_zl_inf_ns_inflate(eng.handle, C.c_void_p(s.ctypes.data if s.size else 0), s.size,
+                                                   C.c_void_p(d.ctypes.data if d.size else 0), d.size,
+                                                   C.byref(cons), C.byref(prod))
+            if st < 0:
+                _lib.check(st, "dcmp_zl_inf_ns_inflate")
+            if st == 0:
+                return Ok((cons.value, prod.value))
+            return Error(_lib.STATUS_TAG.get(st, st))

@@ -69,7 +69,7 @@ int orc_huffman(int kind, const int *table, int off, int codes, int32_t *tbl,
   if (root < min) root = min;
   int size = (max <= root) ? (1 << max)
              : kind == K_LENS ? 852 : kind == K_DISTS ? 592 : (1 << max);
-  memset(tbl, 0, sizeof(int32_t) * ORC_TBL_CAP);
+  memset(tbl, 0, sizeof(int32_t) * (size_t)size);
   {
     int huff = 0, len = min, next = 0, curr = root, drop = 0, low = -1;
     int mask = (1 << root) - 1, fill_size = 0, finished = 0;
@@ -266,7 +266,7 @@ static uint8_t reverse8(uint8_t b) { /* de.ml:792-819 */
 }
 
 /* de.ml:821-833 */
-static void init_fixed(void) {
+__attribute__((constructor)) static void init_fixed(void) {
   int lens[288], n, size, root, max;
   if (g_fixed_ready) return;
   for (n = 0; n < 288; n++) lens[n] = n < 144 ? 8 : n < 256 ? 9 : n < 280 ? 7 : 8;

@@ -7,7 +7,7 @@
  *
  * Parity pin: the reference is OCaml and cannot be built in this image (no
  * ocaml/dune/opam).  The restatement is pinned against every golden vector
- * the reference's own tests hold for this path (tests/golden/*.json, made by
+ * the reference's own tests hold for this path (the JSON files under tests/golden/, made by
  * tests/golden/make_golden.py from test/test.ml, test/test_ns.ml,
  * test/test_lzo.ml) and against the reference's own differential oracles:
  * system zlib (fuzz/fuzz.ml:82-88) and vendored minilzo (fuzz/fuzz_lzo.ml),

@@ -1,0 +1,72 @@
+"""Seeded DEFLATE test inputs shared by the CPU (oracle) and GPU (C-ABI) parity tests."""
+import random
+import zlib
+
+import numpy as np
+
+import workloads
+
+
+def deflate_raw(data, level=6, mem=8, strategy=zlib.Z_DEFAULT_STRATEGY, wbits=-15):
+    co = zlib.compressobj(level, zlib.DEFLATED, wbits, mem, strategy)
+    return co.compress(data) + co.flush()
+
+
+def valid_streams():
+    """(name, raw deflate stream, plaintext) covering stored / fixed / dynamic, multi-block, long runs, windows."""
+    rng = np.random.default_rng(42)
+    out = []
+    txt = workloads.text(300000, 3)
+    out.append(("empty", deflate_raw(b""), b""))
+    out.append(("one_byte", deflate_raw(b"a"), b"a"))
+    out.append(("text_64k_l6_m9", deflate_raw(txt[:65536], 6, 9), txt[:65536]))
+    out.append(("text_300k_l6", deflate_raw(txt, 6, 8), txt))  # several dynamic blocks, 32 KiB window in use
+    out.append(("text_300k_l1", deflate_raw(txt, 1, 8), txt))
+    out.append(("text_300k_l9", deflate_raw(txt, 9, 9), txt))
+    out.append(("text_fixed", deflate_raw(txt[:20000], 6, 8, zlib.Z_FIXED), txt[:20000]))
+    out.append(("text_huffman_only", deflate_raw(txt[:50000], 6, 8, zlib.Z_HUFFMAN_ONLY), txt[:50000]))
+    rnd = rng.integers(0, 256, 100000, dtype=np.uint8).tobytes()
+    out.append(("random_100k_stored", deflate_raw(rnd, 6), rnd))  # incompressible -> stored blocks
+    out.append(("level0_stored_200k", deflate_raw(txt[:200000], 0), txt[:200000]))
+    zeros = bytes(200000)
+    out.append(("zeros_200k", deflate_raw(zeros, 9), zeros))  # dist=1 len=258 runs
+    per = (b"abcdefghij" * 7 + b"\n") * 3000
+    out.append(("periodic_71", deflate_raw(per, 6), per))
+    rle = bytes(rng.integers(0, 4, 120000, dtype=np.uint8))
+    out.append(("low_entropy", deflate_raw(rle, 6), rle))
+    mixed = txt[:40000] + rnd[:40000] + zeros[:40000] + txt[40000:80000]
+    out.append(("mixed_blocks", deflate_raw(mixed, 6), mixed))
+    # sync-flush pieces: empty stored blocks between compressed blocks (de.ml flat + dynamic sequencing)
+    co = zlib.compressobj(6, zlib.DEFLATED, -15, 8)
+    parts = b""
+    for k in range(0, 90000, 7000):
+        parts += co.compress(txt[k:k + 7000]) + co.flush(zlib.Z_SYNC_FLUSH)
+    parts += co.flush()
+    out.append(("sync_flush_pieces", parts, txt[:91000][:len(range(0, 90000, 7000)) * 7000]))
+    far = txt[:1000] + bytes(rng.integers(0, 256, 31700, dtype=np.uint8)) + txt[:1000]
+    out.append(("far_match_32k", deflate_raw(far, 9, 9), far))
+    return out
+
+
+def mutated_streams(count=300, seed=7):
+    """Corrupted / truncated variants of valid streams: every reference error class shows up."""
+    rnd = random.Random(seed)
+    base = [s for _, s, _ in valid_streams() if len(s) < 60000]
+    out = []
+    for k in range(count):
+        s = bytearray(rnd.choice(base))
+        mode = rnd.randrange(5)
+        if mode == 0 and len(s) > 2:      # truncate
+            s = s[:rnd.randrange(1, len(s))]
+        elif mode == 1:                    # flip a bit near the front (headers / tables)
+            i = rnd.randrange(min(len(s), 80))
+            s[i] ^= 1 << rnd.randrange(8)
+        elif mode == 2:                    # flip a bit anywhere
+            i = rnd.randrange(len(s))
+            s[i] ^= 1 << rnd.randrange(8)
+        elif mode == 3:                    # random garbage
+            s = bytearray(rnd.randrange(256) for _ in range(rnd.randrange(1, 200)))
+        else:                              # append garbage after a valid stream
+            s += bytes(rnd.randrange(256) for _ in range(rnd.randrange(1, 16)))
+        out.append(("mut%03d_m%d" % (k, mode), bytes(s)))
+    return out

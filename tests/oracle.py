@@ -59,3 +59,20 @@ def adler32(data, start=1):
 
 def crc32(data, start=0):
     return lib().orc_crc32(start, bytes(data), len(data))
+
+
+def bench_batch(fmt, src, src_off, src_len, dst, dst_off, dst_cap, threads):
+    """One timed pass of the CPU restatement over a batch (numpy arrays); returns (seconds, status, produced)."""
+    import numpy as np
+
+    L = lib()
+    L.orc_bench_batch.restype = C.c_double
+    L.orc_bench_batch.argtypes = [C.c_int, C.c_int64] + [C.c_void_p] * 9 + [C.c_int]
+    n = len(src_off)
+    cons = np.zeros(n, dtype=np.int64)
+    prod = np.zeros(n, dtype=np.int64)
+    status = np.zeros(n, dtype=np.int32)
+    p = lambda a: C.c_void_p(a.ctypes.data)
+    secs = L.orc_bench_batch(fmt, n, p(src), p(src_off), p(src_len), p(dst), p(dst_off), p(dst_cap), p(cons), p(prod),
+                             p(status), int(threads))
+    return secs, status, prod
