@@ -121,7 +121,7 @@ int dcmp_inflate_batch_device(dcmp_engine *e, int fmt, int64_t n, const uint8_t 
   if (n < 0) return DCMP_API_INVALID_ARGUMENT;
   if (n == 0) return DCMP_API_OK;
   CU(cudaSetDevice(e->device));
-  cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : e->stream;
+  cudaStream_t st = (cudaStream_t)cuda_stream; // NULL = the legacy default stream, as everywhere in CUDA
   dcmp::launch_inflate_serial(fmt, n, d_src_base, d_src_off, d_src_len, d_dst_base, d_dst_off, d_dst_cap, d_consumed,
                               d_produced, d_status, nullptr, st);
   e->launches += 1;
@@ -171,12 +171,29 @@ int dcmp_inflate_batch(dcmp_engine *e, int fmt, int64_t n, const uint8_t *src_ba
   CU(cudaMemcpyAsync(d_tab, tab.data(), (size_t)n * 32, cudaMemcpyHostToDevice, st));
   if (s_bytes) CU(cudaMemcpyAsync(d_src, src_base + s_lo, s_bytes, cudaMemcpyHostToDevice, st));
   rc = dcmp_inflate_batch_device(e, fmt, n, d_src, d_tab, d_tab + n, d_dst, d_tab + 2 * n, d_tab + 3 * n, d_cons,
-                                 d_prod, d_stat, st);
+                                 d_prod, d_stat, (void *)st);
   if (rc != DCMP_API_OK) return rc;
   CU(cudaMemcpyAsync(consumed, d_cons, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
   CU(cudaMemcpyAsync(produced, d_prod, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
   CU(cudaMemcpyAsync(status, d_stat, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
-  if (d_bytes) CU(cudaMemcpyAsync(dst_base + d_lo, d_dst, d_bytes, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  // Copy back exactly what each stream produced and nothing else (the reference never
+  // touches dst beyond o_pos).  Adjacent, completely filled windows are merged into one
+  // transfer, so the common layout (C2: dense slab of full windows) is a single copy.
+  int64_t run_lo = -1, run_hi = -1;
+  for (int64_t k = 0; k <= n; k++) {
+    int64_t lo = 0, hi = 0;
+    if (k < n) {
+      int64_t p = std::min(std::max<int64_t>(produced[k], 0), dst_cap[k]);
+      lo = dst_off[k];
+      hi = lo + p;
+      if (hi == lo) continue;
+    }
+    if (k < n && run_hi == lo) { run_hi = hi; continue; }
+    if (run_hi > run_lo)
+      CU(cudaMemcpyAsync(dst_base + run_lo, d_dst + (run_lo - d_lo), (size_t)(run_hi - run_lo), cudaMemcpyDeviceToHost, st));
+    run_lo = lo; run_hi = hi;
+  }
   CU(cudaStreamSynchronize(st));
   return DCMP_API_OK;
 }

@@ -102,8 +102,8 @@ int dcmp_inflate_batch(dcmp_engine *e, int fmt, int64_t n,
                        int64_t *consumed, int64_t *produced, int32_t *status);
 
 /* Same, all pointers are device pointers (offset tables included); enqueued on
- * `cuda_stream` (a cudaStream_t, 0 = the engine's stream); returns without
- * synchronising. */
+ * `cuda_stream` (a cudaStream_t; NULL = the legacy default stream, as in CUDA);
+ * returns without synchronising. */
 int dcmp_inflate_batch_device(dcmp_engine *e, int fmt, int64_t n,
                               const uint8_t *d_src_base, const int64_t *d_src_off, const int64_t *d_src_len,
                               uint8_t *d_dst_base, const int64_t *d_dst_off, const int64_t *d_dst_cap,
