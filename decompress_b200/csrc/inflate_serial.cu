@@ -19,6 +19,7 @@
 //   * after the final block consumed = ceil(c/8), or, when c ran past the input,
 //     n - ((8n - c) lsr 3) in 63-bit OCaml arithmetic (de.ml:1805).
 #include "inflate_tables.cuh"
+#include "simt.cuh"
 
 namespace dcmp {
 
@@ -350,6 +351,7 @@ inflate_serial_kernel(int fmt, int64_t nstreams, const uint8_t *src_base, const 
   }
 }
 
+#ifndef DCMP_EMU
 void launch_inflate_serial(int fmt, int64_t n, const uint8_t *src_base, const int64_t *src_off, const int64_t *src_len,
                            uint8_t *dst_base, const int64_t *dst_off, const int64_t *dst_cap, int64_t *consumed,
                            int64_t *produced, int32_t *status, const int32_t *todo, cudaStream_t stream) {
@@ -358,5 +360,6 @@ void launch_inflate_serial(int fmt, int64_t n, const uint8_t *src_base, const in
   inflate_serial_kernel<<<(unsigned)blocks, SERIAL_WARPS * 32, 0, stream>>>(
       fmt, n, src_base, src_off, src_len, dst_base, dst_off, dst_cap, consumed, produced, status, todo);
 }
+#endif
 
 } // namespace dcmp

@@ -1,0 +1,41 @@
+// tests/simt_emu/emu_inflate.cc — runs the REAL kernel sources (decompress_b200/csrc/*.cu,
+// compiled as C++ with -DDCMP_EMU) on the CPU SIMT emulator so their logic can be debugged
+// without a GPU.  TEST INFRASTRUCTURE ONLY: built into tests/_build/, never part of the product.
+#include "simt_emu.h"
+#include "../../decompress_b200/csrc/inflate_serial.cu"
+#include "../../decompress_b200/csrc/inflate_parallel.cu"
+
+extern "C" {
+
+// mode 0: parallel kernel, then the general kernel on the streams it gave up (like engine.cu)
+// mode 1: parallel kernel only (status 0x7f marks given-up streams)
+// mode 2: general kernel only
+int emu_inflate_batch(int mode, int fmt, int64_t n, const uint8_t *src, const int64_t *soff, const int64_t *slen,
+                      uint8_t *dst, const int64_t *doff, const int64_t *dcap, int64_t *cons, int64_t *prod,
+                      int32_t *status, int ctas) {
+  using namespace dcmp;
+  if (mode != 2) {
+    unsigned long long counter = 0;
+    if (ctas < 1) ctas = 1;
+    std::vector<uint32_t> scratch(inflate_parallel_scratch_bytes_per_cta() / 4 * (size_t)ctas);
+    uint32_t *tok_scratch = scratch.data();
+    simt::launch(simt::dim3((unsigned)ctas), simt::dim3(PT), inflate_parallel_smem_bytes(), [&]() {
+      inflate_parallel_kernel(fmt, n, src, soff, slen, dst, doff, dcap, cons, prod, status, &counter, tok_scratch);
+    });
+  }
+  if (mode == 1) return 0;
+  std::vector<int32_t> todo;
+  for (int64_t k = 0; k < n; k++)
+    if (mode == 2 || status[k] == DCMP_INTERNAL_RETRY) todo.push_back((int32_t)k);
+  if (!todo.empty()) {
+    int64_t m = (int64_t)todo.size();
+    simt::launch(simt::dim3((unsigned)((m + SERIAL_WARPS - 1) / SERIAL_WARPS)), simt::dim3(SERIAL_WARPS * 32), 0, [&]() {
+      inflate_serial_kernel(fmt, m, src, soff, slen, dst, doff, dcap, cons, prod, status, todo.data());
+    });
+  }
+  return (int)todo.size();
+}
+
+long emu_switches() { return simt::g_switches; }
+void emu_stats(long *out) { memcpy(out, &dcmp::g_stats, sizeof(dcmp::g_stats)); memset(&dcmp::g_stats, 0, sizeof(dcmp::g_stats)); }
+}
