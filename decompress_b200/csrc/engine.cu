@@ -6,6 +6,7 @@
 // fails with DCMP_API_NO_DEVICE.
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <algorithm>
 #include <vector>
@@ -14,7 +15,13 @@
 namespace dcmp {
 void launch_inflate_serial(int fmt, int64_t n, const uint8_t *src_base, const int64_t *src_off, const int64_t *src_len,
                            uint8_t *dst_base, const int64_t *dst_off, const int64_t *dst_cap, int64_t *consumed,
-                           int64_t *produced, int32_t *status, const int32_t *todo, cudaStream_t stream);
+                           int64_t *produced, int32_t *status, int only_status, cudaStream_t stream);
+int launch_inflate_parallel(int fmt, int64_t n, const uint8_t *src_base, const int64_t *src_off, const int64_t *src_len,
+                            uint8_t *dst_base, const int64_t *dst_off, const int64_t *dst_cap, int64_t *consumed,
+                            int64_t *produced, int32_t *status, unsigned long long *work_counter, uint32_t *tok_scratch,
+                            int ctas, cudaStream_t stream);
+size_t inflate_parallel_scratch_bytes_per_cta();
+constexpr int INTERNAL_RETRY = 0x7f; // inflate_parallel.cu: "this stream is for the general kernel"
 }
 
 static thread_local char g_err[512] = "";
@@ -36,6 +43,10 @@ struct dcmp_engine {
   uint8_t *d_buf = nullptr; // one growable device arena: [src | dst | tables]
   size_t d_cap = 0;
   int64_t launches = 0;
+  int sm_count = 0;
+  int par_ctas = 0;                  // persistent CTAs of the sub-chunk-parallel kernel (2 per SM)
+  uint8_t *d_scratch = nullptr;      // [work counter (256 B) | token scratch of every CTA]
+  int mode = 0;                      // 0 = parallel + general, 1 = general kernel only (DCMP_INFLATE_MODE=serial)
   int reserve(size_t bytes) {
     if (bytes <= d_cap) return DCMP_API_OK;
     if (d_buf) { CU(cudaFree(d_buf)); d_buf = nullptr; d_cap = 0; }
@@ -98,6 +109,12 @@ int dcmp_engine_create(int device, dcmp_engine **out) {
   eng->device = device;
   cudaError_t se = cudaStreamCreateWithFlags(&eng->stream, cudaStreamNonBlocking);
   if (se != cudaSuccess) { set_err("cudaStreamCreate", se); delete eng; return DCMP_API_CUDA_ERROR; }
+  cudaDeviceGetAttribute(&eng->sm_count, cudaDevAttrMultiProcessorCount, device);
+  eng->par_ctas = 2 * (eng->sm_count > 0 ? eng->sm_count : 148);
+  se = cudaMalloc(&eng->d_scratch, 256 + (size_t)eng->par_ctas * dcmp::inflate_parallel_scratch_bytes_per_cta());
+  if (se != cudaSuccess) { set_err("cudaMalloc(scratch)", se); cudaStreamDestroy(eng->stream); delete eng; return DCMP_API_OUT_OF_MEMORY; }
+  const char *m = getenv("DCMP_INFLATE_MODE");
+  eng->mode = (m && strcmp(m, "serial") == 0) ? 1 : 0;
   *out = eng;
   return DCMP_API_OK;
 }
@@ -106,6 +123,7 @@ void dcmp_engine_destroy(dcmp_engine *e) {
   if (!e) return;
   cudaSetDevice(e->device);
   if (e->d_buf) cudaFree(e->d_buf);
+  if (e->d_scratch) cudaFree(e->d_scratch);
   if (e->stream) cudaStreamDestroy(e->stream);
   delete e;
 }
@@ -122,9 +140,24 @@ int dcmp_inflate_batch_device(dcmp_engine *e, int fmt, int64_t n, const uint8_t 
   if (n == 0) return DCMP_API_OK;
   CU(cudaSetDevice(e->device));
   cudaStream_t st = (cudaStream_t)cuda_stream; // NULL = the legacy default stream, as everywhere in CUDA
-  dcmp::launch_inflate_serial(fmt, n, d_src_base, d_src_off, d_src_len, d_dst_base, d_dst_off, d_dst_cap, d_consumed,
-                              d_produced, d_status, nullptr, st);
-  e->launches += 1;
+  if (e->mode == 0) {
+    // stage 1: sub-chunk-parallel kernel, persistent CTAs pulling streams from a device counter;
+    // stage 2: the general kernel on exactly the streams stage 1 marked INTERNAL_RETRY.
+    unsigned long long *counter = (unsigned long long *)e->d_scratch;
+    CU(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), st));
+    int rc = dcmp::launch_inflate_parallel(fmt, n, d_src_base, d_src_off, d_src_len, d_dst_base, d_dst_off, d_dst_cap,
+                                           d_consumed, d_produced, d_status, counter, (uint32_t *)(e->d_scratch + 256),
+                                           e->par_ctas, st);
+    if (rc != 0) { set_err("launch_inflate_parallel", (cudaError_t)rc); return DCMP_API_CUDA_ERROR; }
+    CU(cudaGetLastError());
+    dcmp::launch_inflate_serial(fmt, n, d_src_base, d_src_off, d_src_len, d_dst_base, d_dst_off, d_dst_cap, d_consumed,
+                                d_produced, d_status, dcmp::INTERNAL_RETRY, st);
+    e->launches += 2;
+  } else {
+    dcmp::launch_inflate_serial(fmt, n, d_src_base, d_src_off, d_src_len, d_dst_base, d_dst_off, d_dst_cap, d_consumed,
+                                d_produced, d_status, -1, st);
+    e->launches += 1;
+  }
   CU(cudaGetLastError());
   return DCMP_API_OK;
 }

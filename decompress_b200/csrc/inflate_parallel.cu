@@ -4,13 +4,14 @@
 // streams).  It replaces the literal/length/distance state machine of De.Inf
 // (lib/de.ml:1054-1261, one-shot form 1667-1712), the window (WInf, de.ml:436-508) and
 // the table construction (Inf.huffman, de.ml:523-638) with a design that has no
-// counterpart in the reference (which is strictly serial):
+// counterpart in the reference (which is strictly serial).  Nothing in it waits on
+// another lane: every phase is data-parallel over the PT lanes of the CTA.
 //
-//   round = 128 lanes x 1056-bit sub-chunks of the compressed stream (33 words: an odd
-//           word stride, so the lanes of a warp read the TMA-staged window without
-//           shared-memory bank conflicts and no per-lane repacking is needed)
-//   A  speculative decode   every lane decodes its sub-chunk from an arbitrary bit
-//                           offset into 32-bit tokens (literal | len,dist) written to an
+//   round = PT lanes x SUB_BITS-bit sub-chunks of the compressed stream (an odd number of
+//           32-bit words per lane, so the lanes of a warp read the TMA-staged window
+//           without shared-memory bank conflicts)
+//   A  speculative decode   every lane decodes its sub-chunk from an arbitrary bit offset
+//                           into 32-bit tokens (literal | len,dist) written to an
 //                           L2-resident scratch in [token][lane] order (coalesced), and
 //                           leaves a checkpoint (first token start, token index, bytes so
 //                           far) for every 64-bit window it crosses;
@@ -23,17 +24,20 @@
 //                           (end of block, token buffer full, no re-synchronisation,
 //                           output budget); an exclusive scan of emitted byte counts
 //                           gives every lane its output offset;
-//   D  LZ77 resolve         every lane replays its tokens into the 64 KiB shared-memory
-//                           ring (the sliding window); back-references into bytes another
-//                           lane of the same round still owes wait on that lane's
-//                           progress counter (fine-grained dataflow, no global order);
-//   E  drain                finished bytes leave through TMA bulk stores (16-byte aligned
-//                           body); the next round's input arrives through a TMA bulk load;
-//                           Adler-32 is folded over the drained bytes.
+//   D  symbol replay        every lane replays its tokens into a 16-bit symbol buffer at
+//                           its output offset.  A back-reference into the 32 KiB history
+//                           (earlier rounds; a byte ring in shared memory) or into the
+//                           lane's own output is copied; a back-reference into bytes that
+//                           ANOTHER lane produces in this round is not waited for: the
+//                           lane stores a marker 256 + (index of the source symbol);
+//   E  resolve + drain      16 symbols per thread: markers are chased to a literal
+//                           (markers only point backwards, chains are short), the 16
+//                           bytes leave through one 128-bit store to HBM and one to the
+//                           history ring; Adler-32 is folded over the same registers.
 //
-// Anything that is not the happy path — stored blocks, malformed input, incomplete code
-// sets, an output buffer that is too small — makes the CTA give the stream up with
-// status DCMP_INTERNAL_RETRY; the host-side dispatcher (engine.cu) then runs the general
+// Anything that is not the happy path — stored blocks, malformed input, exotic code sets, an
+// output buffer that is too small — makes the CTA give the stream up with status
+// DCMP_INTERNAL_RETRY; the host-side dispatcher (engine.cu) then runs the general
 // one-warp-per-stream kernel (inflate_serial.cu), which reproduces the reference's exact
 // error behaviour, on exactly those streams.  Both kernels are device code; there is no
 // CPU path.
@@ -42,28 +46,48 @@
 
 namespace dcmp {
 
-constexpr int PT = 128;            // threads (= lanes = sub-chunks per round)
-constexpr int SUB_WORDS = 33;      // sub-chunk size in 32-bit words (odd: conflict-free lane stride)
+#ifndef DCMP_PT
+#define DCMP_PT 192
+#endif
+#ifndef DCMP_SUB_WORDS
+#define DCMP_SUB_WORDS 13
+#endif
+
+constexpr int PT = DCMP_PT;               // threads (= lanes = sub-chunks per round)
+constexpr int NWARP = PT / 32;
+constexpr int SUB_WORDS = DCMP_SUB_WORDS; // sub-chunk size in 32-bit words (odd: conflict-free lane stride)
 constexpr int SUB_BITS = 32 * SUB_WORDS;
-constexpr int SPEC_CAP = 160;      // tokens a lane may produce speculatively
-constexpr int HEAD_CAP = 64;       // tokens a lane may produce while re-synchronising
+constexpr int SPEC_CAP = 120;             // tokens a lane may produce speculatively (< 256: checkpoint field)
+constexpr int HEAD_CAP = 56;              // tokens a lane may produce while re-synchronising
 constexpr int TOK_SLOTS = SPEC_CAP + HEAD_CAP; // per lane, in the global scratch
-constexpr int CKPT_SHIFT = 6;      // one checkpoint per 64-bit window of the sub-chunk
+constexpr int LANE_BYTE_CAP = 4096;       // bytes a lane may produce per pass (checkpoint field: 18 bits)
+constexpr int CKPT_SHIFT = 6;             // one checkpoint per 64-bit window of the sub-chunk
 constexpr int NCKPT = (SUB_BITS >> CKPT_SHIFT) + 1;
-constexpr int RING = 65536;        // output ring (window) in bytes
-constexpr int RING_MASK = RING - 1;
-constexpr int RING_SLACK = 512;
+constexpr int HIST = 32768;               // history ring (the sliding window, de.ml:439-440) in bytes
+constexpr int HIST_MASK = HIST - 1;
+constexpr int RSYM = 28 * 1024;           // symbols one round may produce (+ up to 15 of alignment bias)
+constexpr int SYM_SLOTS = RSYM + 32;
 constexpr int WIN_WORDS = 3 + SUB_WORDS * PT + 4;        // staged input per round
 constexpr int WIN_BYTES = (WIN_WORDS * 4 + 15) & ~15;
 constexpr int HDR_BYTES = 1024 + 16;      // staged input for a block header
 constexpr int LIT_ROOT = 10;
 constexpr int DIST_ROOT = 9;
-constexpr int BUCKET_SHIFT = 6;
-constexpr int NBUCKET = (RING >> BUCKET_SHIFT) + 2;
+constexpr int FIX_PASSES = 3;             // extra head-decode passes behind lanes that did not re-synchronise
 constexpr int DCMP_INTERNAL_RETRY = 0x7f; // never leaves the library
+static_assert(SUB_WORDS % 2 == 1, "odd lane stride keeps the window reads conflict-free");
+static_assert(PT % 32 == 0 && PT <= 1024, "");
+static_assert(SPEC_CAP < 256 && LANE_BYTE_CAP < (1 << 18), "checkpoint fields");
+static_assert(SPEC_CAP % 4 == 0 && HEAD_CAP % 4 == 0, "token slots are moved in batches of four");
+static_assert(NCKPT * PT * 4 <= SYM_SLOTS * 2, "checkpoints alias the symbol buffer");
+static_assert(RSYM + 16 + 256 <= 65536, "markers are 16-bit");
+static_assert(HDR_BYTES <= WIN_BYTES, "");
 
 #ifdef DCMP_EMU
-struct EmuStats { long hist_nh[48]; long nosync_lanes; long rounds, valid_lanes, cut_term[5], cut_bad, cut_budget, head_tokens, spec_tokens, used_tokens, d_iters, d_wait_iters, hdr_rounds, retries; };
+struct EmuStats {
+  long hist_nh[48];
+  long nosync_lanes, rounds, valid_lanes, cut_term[5], cut_bad, cut_budget, head_tokens, spec_tokens, used_tokens;
+  long d_iters, d_lane_max_iters, markers, hist_bytes, own_bytes, chase_hops, chase_max, out_bytes, hdr_rounds, retries, fix_passes;
+};
 static EmuStats g_stats;
 #define STAT(x) x
 #else
@@ -77,7 +101,16 @@ enum : int { NEXT_CONTINUE = 0, NEXT_HEADER = 1, NEXT_FINISH = 2, NEXT_RETRY = 3
 // checkpoint: [5:0] bit offset of the first token start inside the 64-bit window,
 //             [13:6] index of that token, [31:14] bytes emitted before it
 __device__ __forceinline__ bool tok_is_match(uint32_t t) { return (t >> 23) & 1u; }
-__device__ __forceinline__ uint32_t tok_len(uint32_t t) { return tok_is_match(t) ? (t & 0xffu) + 3u : 1u; }
+__device__ __forceinline__ void batch_put(uint4 &b, int k, uint32_t t) {
+  if (k == 0) b.x = t;
+  if (k == 1) b.y = t;
+  if (k == 2) b.z = t;
+  if (k == 3) b.w = t;
+}
+__device__ __forceinline__ uint32_t batch_get(const uint4 &b, int k) {
+  uint32_t lo = (k & 1) ? b.y : b.x, hi = (k & 1) ? b.w : b.z;
+  return (k & 2) ? hi : lo;
+}
 
 struct HuffMeta {      // canonical-code description for codes longer than the root table
   uint16_t first[16];  // first code (MSB-first) of each length
@@ -87,13 +120,13 @@ struct HuffMeta {      // canonical-code description for codes longer than the r
 };
 
 struct ParSmem {
-  uint8_t ring[RING];
+  __align__(16) uint16_t sym[SYM_SLOTS];   // phase D/E: symbols of the round; phase A/B: checkpoints [NCKPT][PT] u32
+  __align__(16) uint8_t ring[HIST];        // last 32 KiB of output, indexed by (global address & HIST_MASK)
   __align__(16) uint32_t win[WIN_BYTES / 4 + 4]; // staged compressed input (TMA destination)
   uint32_t lit[1 << LIT_ROOT];
   uint32_t dist[1 << DIST_ROOT];
   uint32_t codes[CODES_TABLE_SIZE];
   uint32_t code_of[MAX_LENS];    // table build scratch: bit-reversed code | len << 16 per symbol
-  uint32_t ckpt[NCKPT][PT];
   uint16_t sorted_l[288];
   uint16_t sorted_d[32];
   uint8_t lens[MAX_LENS];
@@ -102,28 +135,27 @@ struct ParSmem {
   // per-lane results of a round
   uint16_t exit_pos[PT];         // spec pass: bit offset (own sub-chunk coordinates) after the last token
   uint8_t exit_kind[PT];
-  uint32_t lane_off[PT + 1];     // output position (stream-relative) where the lane starts writing
-  volatile uint32_t progress[PT];
-  uint8_t bucket[NBUCKET];
-  uint32_t warp_a[PT / 32], warp_b[PT / 32], warp_c[PT / 32];
-  unsigned long long adl_s[PT / 32], adl_b[PT / 32];
+  int texit[PT];                 // head pass: entry point handed to the next lane (its coordinates), or ENTRY_NONE
+  uint32_t warp_c[NWARP];
+  unsigned long long adl_s[NWARP];
+  long long adl_b[NWARP];
+  uint32_t hdr_hlit, hdr_hdist, tbl_ok;
+  int first_bad, first_term, first_over;
   // stream state (CTA-uniform)
   int64_t stream;                // index of the stream being decoded, -1 = none
   const uint8_t *src; int64_t src_len;  // raw deflate bytes
   uint8_t *dst; int64_t dst_cap;
   int64_t base_bit;              // next bit of the deflate stream to decode
   uint32_t out_pos;              // bytes produced so far
-  uint32_t flushed;              // bytes already stored to global
-  uint32_t ring_bias;            // ring index of output byte p is (p + ring_bias) & RING_MASK
   int last_block, next, status;
   int n_valid;                   // lanes accepted in this round
   uint32_t round_out;            // bytes produced by this round
   uint32_t adler_a, adler_b;
   uint32_t mbar_phase;
-  volatile int abort_round;      // a lane met an invalid distance: everybody leaves phase D
+  int abort_round;               // a lane met an invalid distance: the general kernel reports it
   __align__(8) uint64_t mbar;
 };
-static_assert(sizeof(ParSmem) <= 113 * 1024, "two CTAs per SM need <= 113 KiB each");
+static_assert(sizeof(ParSmem) <= 112 * 1024, "two CTAs per SM need <= ~113 KiB each");
 
 // ------------------------------------------------------------------------------------------
 // bit cursor over a lane's sub-chunk inside the staged window
@@ -177,7 +209,7 @@ __device__ __noinline__ uint32_t slow_symbol(const HuffMeta &m, const uint16_t *
 
 enum : int { T_TOKEN = 0, T_EOB = 1, T_ERR = 2 };
 
-// Decode one literal / match at the cursor.  *tok gets the token (without start tag), *nout its byte count.
+// Decode one literal / match at the cursor.  *tok gets the token, *nout its byte count.
 __device__ __forceinline__ int decode_token(ParSmem &S, LaneBits &lb, uint32_t lmask, uint32_t dmask,
                                             uint32_t *tok, uint32_t *nout) {
   lb.refill();
@@ -195,6 +227,7 @@ __device__ __forceinline__ int decode_token(ParSmem &S, LaneBits &lb, uint32_t l
     return T_TOKEN;
   }
   if (kind == K_EOB) return T_EOB;
+  if (kind != K_LEN) return T_ERR; // K_INVALID: unfilled slot of an incomplete code set
   uint32_t len = e_base(e) + lb.pop(e_extra(e));
   lb.refill();
   uint32_t d = S.dist[(uint32_t)lb.hold & dmask];
@@ -203,6 +236,7 @@ __device__ __forceinline__ int decode_token(ParSmem &S, LaneBits &lb, uint32_t l
     uint32_t sym = slow_symbol(S.md, S.sorted_d, (uint32_t)lb.hold, &l);
     d = dist_symbol_entry((int)sym) | (uint32_t)l;
   }
+  if (e_kind(d) != K_LIT) return T_ERR; // empty / incomplete distance code set: general kernel
   lb.drop(e_len(d));
   uint32_t db = e_base(d);
   uint32_t dd = db + lb.pop(e_extra(d));
@@ -214,8 +248,10 @@ __device__ __forceinline__ int decode_token(ParSmem &S, LaneBits &lb, uint32_t l
 
 // ------------------------------------------------------------------------------------------
 // Parallel construction of the root decode table + canonical metadata from code lengths.
-// Accepts only complete codes (Kraft sum exactly 1); anything else is left to the general
-// kernel.  Returns false (CTA-uniform) when the code set is not acceptable.
+// Accepts complete codes (Kraft sum exactly 1) and, for the literal/length and distance
+// alphabets, the two incomplete shapes the reference accepts (de.ml:544-550): no code at all
+// and a single 1-bit code; their unassigned slots are K_INVALID, which sends a stream that
+// really uses them to the general kernel.  Returns false (CTA-uniform) otherwise.
 __device__ bool build_fast_table(ParSmem &S, int kind, const uint8_t *lens, int n, uint32_t *tbl, int root_max,
                                  HuffMeta &m, uint16_t *sorted, int tid) {
   __syncthreads();
@@ -241,13 +277,20 @@ __device__ bool build_fast_table(ParSmem &S, int kind, const uint8_t *lens, int 
       if (left < 0) left = -100000; // over-subscribed
       if (c) maxl = l;
     }
+    bool ok = left == 0 && maxl >= 1;
+    if (!ok && kind != KIND_CODES && (maxl == 0 || (maxl == 1 && left > 0))) { // none, or one 1-bit code
+      ok = true;
+      if (maxl == 0) maxl = 1;
+    }
     m.maxl = maxl;
     m.root = maxl < root_max ? maxl : root_max;
-    S.warp_a[0] = (left == 0 && maxl >= 1) ? 1u : 0u; // complete codes only
+    S.tbl_ok = ok ? 1u : 0u;
   }
   __syncthreads();
-  if (!S.warp_a[0]) return false;
+  if (!S.tbl_ok) return false;
   if (tid < 16) S.run_cnt[tid] = 0;
+  const int root = m.root;
+  for (int i = tid; i < (1 << root); i += PT) tbl[i] = mk_entry(K_INVALID, 0, 0, 0);
   __syncthreads();
   // canonical rank of every symbol among the symbols of its length (by symbol index):
   // warp 0 walks the alphabet 32 symbols at a time, __match_any_sync groups equal lengths.
@@ -274,7 +317,6 @@ __device__ bool build_fast_table(ParSmem &S, int kind, const uint8_t *lens, int 
     }
   }
   __syncthreads();
-  const int root = m.root;
   for (int s = tid; s < n; s += PT) {
     uint32_t co = S.code_of[s];
     int l = (int)(co >> 16);
@@ -293,7 +335,7 @@ __device__ bool build_fast_table(ParSmem &S, int kind, const uint8_t *lens, int 
 
 // ------------------------------------------------------------------------------------------
 // Block header (de.ml:1788-1793, 1771-1786, 1733-1769) parsed by thread 0 from the staged
-// window; returns NEXT_* / sets lens[] and hlit/hdist.
+// window.
 struct HdrBits {
   const uint32_t *w;
   int nwords;
@@ -325,7 +367,8 @@ struct HdrBits {
   }
 };
 
-// thread 0 only.  Returns bits consumed (>0) or -1 to give the stream to the general kernel.
+// thread 0 only.  Returns the bit position after the header (>0) or -1 to give the stream to the
+// general kernel.
 __device__ int parse_dynamic_header(ParSmem &S, HdrBits &hb, int64_t bits_avail, int *hlit_out, int *hdist_out) {
   hb.refill();
   if (bits_avail - hb.pos() < 14) return -1;
@@ -431,6 +474,7 @@ inflate_parallel_kernel(int fmt, int64_t nstreams, const uint8_t *src_base, cons
   const int tid = threadIdx.x;
   const int lane = tid & 31;
   const int warp = tid >> 5;
+  uint32_t(*ckpt)[PT] = reinterpret_cast<uint32_t(*)[PT]>(S.sym);
 
   if (tid == 0) {
     mbar_init(&S.mbar, 1);
@@ -466,8 +510,6 @@ inflate_parallel_kernel(int fmt, int64_t nstreams, const uint8_t *src_base, cons
         if (S.dst_cap > 0xfff00000LL || n > 0x0fffffffLL) st = DCMP_INTERNAL_RETRY; // 32-bit positions below
         S.base_bit = 0;
         S.out_pos = 0;
-        S.flushed = 0;
-        S.ring_bias = (uint32_t)((uintptr_t)S.dst & RING_MASK);
         S.last_block = 0;
         S.status = st;
         S.next = st == DCMP_OK ? NEXT_HEADER : NEXT_RETRY;
@@ -488,6 +530,7 @@ inflate_parallel_kernel(int fmt, int64_t nstreams, const uint8_t *src_base, cons
       const uint8_t *g0 = S.src - A + v0;
       const int64_t vend = ((int64_t)A + S.src_len + 15) & ~(int64_t)15; // one past the last valid granule
       if (base_bit > 8 * S.src_len) { // ran off the input: the general kernel knows what the reference does
+        __syncthreads();
         if (tid == 0) S.next = NEXT_RETRY;
         __syncthreads();
         break;
@@ -496,6 +539,7 @@ inflate_parallel_kernel(int fmt, int64_t nstreams, const uint8_t *src_base, cons
         // ------------------------------------------------------------ block header
         stage_window(S, g0, HDR_BYTES, (int)(vend - v0 > HDR_BYTES ? HDR_BYTES : vend - v0), tid);
         if (tid == 0) {
+          STAT(g_stats.hdr_rounds++;)
           HdrBits hb;
           hb.init((const uint8_t *)S.win, bit0, HDR_BYTES);
           int64_t avail = 8 * S.src_len - base_bit + bit0; // valid bits measured in window coordinates
@@ -510,18 +554,15 @@ inflate_parallel_kernel(int fmt, int64_t nstreams, const uint8_t *src_base, cons
               int used = parse_dynamic_header(S, hb, avail, &hlit, &hdist);
               if (used < 0) nx = NEXT_RETRY;
               else {
-                S.warp_b[0] = (uint32_t)hlit;
-                S.warp_b[1] = (uint32_t)hdist;
+                S.hdr_hlit = (uint32_t)hlit;
+                S.hdr_hdist = (uint32_t)hdist;
                 S.base_bit = base_bit + (used - bit0);
               }
             } else if (type == 1) {
               for (int n = 0; n < 288; n++) S.lens[n] = n < 144 ? 8 : n < 256 ? 9 : n < 280 ? 7 : 8; // de.ml:821-833
-              for (int n = 0; n < 30; n++) S.lens[288 + n] = 5;
-              // the fixed distance code has 32 codes of 5 bits; 30/31 are invalid symbols
-              S.lens[288 + 30] = 5;
-              S.lens[288 + 31] = 5;
-              S.warp_b[0] = 288;
-              S.warp_b[1] = 32;
+              for (int n = 0; n < 32; n++) S.lens[288 + n] = 5; // 32 codes of 5 bits; 30/31 are invalid symbols
+              S.hdr_hlit = 288;
+              S.hdr_hdist = 32;
               S.base_bit = base_bit + (hb.pos() - bit0);
             } else {
               nx = NEXT_RETRY; // stored blocks and BTYPE=3: general kernel
@@ -531,10 +572,11 @@ inflate_parallel_kernel(int fmt, int64_t nstreams, const uint8_t *src_base, cons
         }
         __syncthreads();
         if (S.next == NEXT_RETRY) break;
-        const int hlit = (int)S.warp_b[0], hdist = (int)S.warp_b[1];
+        const int hlit = (int)S.hdr_hlit, hdist = (int)S.hdr_hdist;
         bool ok = build_fast_table(S, KIND_LENS, S.lens, hlit, S.lit, LIT_ROOT, S.ml, S.sorted_l, tid);
         ok = ok && build_fast_table(S, KIND_DISTS, S.lens + hlit, hdist, S.dist, DIST_ROOT, S.md, S.sorted_d, tid);
         if (!ok) {
+          __syncthreads();
           if (tid == 0) S.next = NEXT_RETRY;
           __syncthreads();
           break;
@@ -550,8 +592,11 @@ inflate_parallel_kernel(int fmt, int64_t nstreams, const uint8_t *src_base, cons
       const int sh = bit0 & 31;
       const uint32_t *lane_words = S.win + (bit0 >> 5) + SUB_WORDS * tid;
       const uint32_t lmask = (1u << S.ml.root) - 1u, dmask = (1u << S.md.root) - 1u;
-      uint32_t *tok_spec = tok_scratch + (size_t)blockIdx.x * TOK_SLOTS * PT + tid; // [slot][lane]
-      uint32_t *tok_head = tok_spec + (size_t)SPEC_CAP * PT;
+      // this lane's token slots in the L2-resident scratch: [HEAD_CAP head tokens | SPEC_CAP speculative tokens],
+      // written and read back as 128-bit batches of four
+      uint4 *tok_lane = reinterpret_cast<uint4 *>(tok_scratch + ((size_t)blockIdx.x * PT + tid) * TOK_SLOTS);
+      uint4 *tok_head = tok_lane;
+      uint4 *tok_spec = tok_lane + HEAD_CAP / 4;
       // lanes whose sub-chunk starts beyond the input decode nothing
       const bool lane_has_input = base_bit + (int64_t)SUB_BITS * tid < 8 * S.src_len;
       // ---- A: speculative decode of the own sub-chunk from bit 0
@@ -562,135 +607,143 @@ inflate_parallel_kernel(int fmt, int64_t nstreams, const uint8_t *src_base, cons
       if (lane_has_input) {
         LaneBits lb;
         lb.init(lane_words, sh, 0);
+        uint4 tbuf = make_uint4(0, 0, 0, 0);
         for (;;) {
           int p = lb.pos();
           if (p >= SUB_BITS) { xkind = X_NORMAL; xpos = p; break; }
-          if (ns == SPEC_CAP) { xkind = X_CAP; xpos = p; break; }
+          if (ns == SPEC_CAP || out_s > (uint32_t)(LANE_BYTE_CAP - 258)) { xkind = X_CAP; xpos = p; break; }
           int ck = p >> CKPT_SHIFT;
           if (ck != last_ck) {
-            S.ckpt[ck][tid] = (uint32_t)(p & 63) | ((uint32_t)ns << 6) | (out_s << 14);
+            ckpt[ck][tid] = (uint32_t)(p & 63) | ((uint32_t)ns << 6) | (out_s << 14);
             last_ck = ck;
           }
           uint32_t tok, no;
           int r = decode_token(S, lb, lmask, dmask, &tok, &no);
           if (r == T_EOB) { xkind = X_EOB; xpos = lb.pos(); break; }
           if (r == T_ERR) { xkind = X_ERR; xpos = p; break; }
-          tok_spec[(size_t)ns * PT] = tok;
+          batch_put(tbuf, ns & 3, tok);
+          if ((ns & 3) == 3) tok_spec[ns >> 2] = tbuf;
           ns++;
           out_s += no;
         }
+        if (ns & 3) tok_spec[ns >> 2] = tbuf;
       }
       S.exit_pos[tid] = (uint16_t)xpos;
       S.exit_kind[tid] = (uint8_t)xkind;
+      if (tid == 0) { S.first_bad = PT; S.first_term = PT; S.first_over = PT; S.abort_round = 0; }
       __syncthreads();
-      // ---- B: re-synchronise with the true entry point handed over by the previous lane
+      // ---- B: re-synchronise with the true entry point handed over by the previous lane.
+      // Lane t first assumes that lane t-1 merged into its own speculative sequence (entry = that
+      // sequence's exit).  A lane that crosses its whole sub-chunk without merging ("no sync")
+      // hands over a different exit; the few lanes behind such a lane redo the step (FIX_PASSES
+      // times at most, then the round is cut there).
       int nh = 0, kmerge = 0;
       uint32_t out_valid = 0;
-      bool in_ok = lane_has_input, term, merged = false;
+      bool in_ok = false, term = false, merged = false;
       int tkind = xkind, tpos = xpos; // exit of this lane's TRUE sequence
-      {
-        int p_in = 0;
-        if (tid > 0 && in_ok) {
-          if (S.exit_kind[tid - 1] != X_NORMAL) in_ok = false;
-          else p_in = (int)S.exit_pos[tid - 1] - SUB_BITS;
-        }
-        uint32_t skipped = 0, out_h = 0;
-        if (in_ok) {
-          if (p_in == 0 && ns > 0) {
-            merged = true;
-          } else {
-            LaneBits lb;
-            lb.init(lane_words, sh, p_in);
-            int seen_ck = -1;
-            for (;;) {
-              int p = lb.pos();
-              if (p >= SUB_BITS) { tkind = X_NOSYNC; tpos = p; break; }  // true tokens covered the whole sub-chunk
-              int ck = p >> CKPT_SHIFT;
-              if (ck != seen_ck) {
-                seen_ck = ck;
-                if (ck <= last_ck) { // the speculative pass left a checkpoint for this window
-                  uint32_t c = S.ckpt[ck][tid];
-                  if ((int)(c & 63u) == (p & 63)) { merged = true; kmerge = (int)((c >> 6) & 255u); skipped = c >> 14; break; }
+      const int ENTRY_NONE = -100000;
+      int entry = 0;                  // bit offset (own sub-chunk coordinates) the head decode starts from
+      if (tid > 0) entry = S.exit_kind[tid - 1] == X_NORMAL ? (int)S.exit_pos[tid - 1] - SUB_BITS : ENTRY_NONE;
+      bool dirty = true;
+      for (int pass = 0;; pass++) {
+        if (dirty) {
+          nh = 0; kmerge = 0; merged = false; out_valid = 0;
+          in_ok = lane_has_input && entry != ENTRY_NONE;
+          tkind = xkind; tpos = xpos;
+          uint32_t skipped = 0, out_h = 0;
+          if (in_ok) {
+            if (entry == 0 && ns > 0) {
+              merged = true;
+            } else {
+              LaneBits lb;
+              lb.init(lane_words, sh, entry);
+              uint4 tbuf = make_uint4(0, 0, 0, 0);
+              int seen_ck = -1;
+              for (;;) {
+                int p = lb.pos();
+                if (p >= SUB_BITS) { tkind = X_NOSYNC; tpos = p; break; }  // true tokens covered the whole sub-chunk
+                int ck = p >> CKPT_SHIFT;
+                if (ck != seen_ck) {
+                  seen_ck = ck;
+                  if (ck <= last_ck) { // the speculative pass left a checkpoint for this window
+                    uint32_t c = ckpt[ck][tid];
+                    if ((int)(c & 63u) == (p & 63)) { merged = true; kmerge = (int)((c >> 6) & 255u); skipped = c >> 14; break; }
+                  }
                 }
+                if (xkind == X_CAP && p == xpos) { merged = true; kmerge = ns; skipped = out_s; break; } // met the spec pass where its buffer filled up
+                if (nh == HEAD_CAP || out_h > (uint32_t)(LANE_BYTE_CAP - 258)) { tkind = X_CAP; tpos = p; break; }
+                uint32_t tok, no;
+                int r = decode_token(S, lb, lmask, dmask, &tok, &no);
+                if (r == T_EOB) { tkind = X_EOB; tpos = lb.pos(); break; }
+                if (r == T_ERR) { tkind = X_ERR; tpos = p; break; }
+                batch_put(tbuf, nh & 3, tok);
+                if ((nh & 3) == 3) tok_head[nh >> 2] = tbuf;
+                nh++;
+                out_h += no;
               }
-              if (xkind == X_CAP && p == xpos) { merged = true; kmerge = ns; skipped = out_s; break; } // met the spec pass where its buffer filled up
-              if (nh == HEAD_CAP) { in_ok = false; break; }
-              uint32_t tok, no;
-              int r = decode_token(S, lb, lmask, dmask, &tok, &no);
-              if (r == T_EOB) { tkind = X_EOB; tpos = lb.pos(); break; }
-              if (r == T_ERR) { tkind = X_ERR; tpos = p; break; }
-              tok_head[(size_t)nh * PT] = tok;
-              nh++;
-              out_h += no;
+              if (nh & 3) tok_head[nh >> 2] = tbuf;
             }
+            out_valid = out_h + (merged ? out_s - skipped : 0u);
+            if (merged) { tkind = xkind; tpos = xpos; }
           }
+          // a lane that ends normally (merged or not) hands its exit to the next lane
+          const bool normal_exit = in_ok && (tkind == X_NORMAL || tkind == X_NOSYNC);
+          term = in_ok && !normal_exit;
+          S.texit[tid] = normal_exit ? tpos - SUB_BITS : ENTRY_NONE;
+          STAT(if (in_ok && tid > 0) { if (merged) { g_stats.hist_nh[nh < 47 ? nh : 47]++; } else if (tkind == X_NOSYNC) g_stats.nosync_lanes++; })
         }
-        STAT(if (in_ok && tid > 0) { if (merged) { g_stats.hist_nh[nh < 47 ? nh : 47]++; } else if (tkind == X_NOSYNC) g_stats.nosync_lanes++; })
-        if (in_ok) {
-          out_valid = out_h + (merged ? out_s - skipped : 0u);
-          if (merged) { tkind = xkind; tpos = xpos; }
+        __syncthreads();
+        const int want = tid == 0 ? 0 : S.texit[tid - 1];
+        dirty = lane_has_input && want != entry;
+        if (pass == FIX_PASSES) {
+          if (dirty) in_ok = false; // still inconsistent: the round is cut at this lane
+          break;
         }
-        term = in_ok && tkind != X_NORMAL;
+        if (!__syncthreads_or(dirty)) break;
+        STAT(if (tid == 0) g_stats.fix_passes++;)
+        if (dirty) entry = want;
       }
       // ---- C: cut the round at the first lane that cannot be chained, scan output sizes
-      {
-        uint32_t bad = __ballot_sync(0xffffffffu, !in_ok);
-        uint32_t trm = __ballot_sync(0xffffffffu, term);
-        if (lane == 0) { S.warp_a[warp] = bad; S.warp_b[warp] = trm; }
-      }
-      __syncthreads();
-      int first_bad = PT, first_term = PT;
-#pragma unroll
-      for (int w = PT / 32 - 1; w >= 0; w--) {
-        if (S.warp_a[w]) first_bad = 32 * w + __ffs((int)S.warp_a[w]) - 1;
-        if (S.warp_b[w]) first_term = 32 * w + __ffs((int)S.warp_b[w]) - 1;
-      }
+      if (!in_ok) atomicMin(&S.first_bad, tid);
+      if (term) atomicMin(&S.first_term, tid);
+      __syncthreads();   // (also: every lane is done with its checkpoints; S.sym may be reused)
+      const int first_bad = S.first_bad, first_term = S.first_term;
       int n_valid = first_term < first_bad ? first_term + 1 : first_bad;
       uint32_t mine = tid < n_valid ? out_valid : 0u;
       uint32_t incl = warp_incl_scan(mine, lane);
-      __syncthreads(); // warp_a / warp_b fully read
       if (lane == 31) S.warp_c[warp] = incl;
       __syncthreads();
-      uint32_t woff = 0;
-#pragma unroll
-      for (int w = 0; w < PT / 32; w++)
-        if (w < warp) woff += S.warp_c[w];
-      incl += woff;
-      // output budget of the ring (it must keep min(32 KiB, produced) of history): first lane
-      // whose inclusive sum exceeds it
-      const uint32_t round_budget = (uint32_t)RING - umin32(S.out_pos, 32768u) - (uint32_t)RING_SLACK;
       {
-        uint32_t over = __ballot_sync(0xffffffffu, tid < n_valid && incl > round_budget);
-        if (lane == 0) S.warp_a[warp] = over;
-      }
-      __syncthreads();
-      int first_over = PT;
+        uint32_t woff = 0;
 #pragma unroll
-      for (int w = PT / 32 - 1; w >= 0; w--)
-        if (S.warp_a[w]) first_over = 32 * w + __ffs((int)S.warp_a[w]) - 1;
-      bool cut_by_budget = first_over < n_valid;
-      if (cut_by_budget) n_valid = first_over;
-      const uint32_t out0 = S.out_pos;
-      const uint32_t my_off = out0 + incl - mine;
-      if (tid <= n_valid && tid < PT) S.lane_off[tid] = tid < n_valid ? my_off : 0u;
+        for (int w = 0; w < NWARP; w++)
+          if (w < warp) woff += S.warp_c[w];
+        incl += woff;
+      }
+      // output budget of the symbol buffer: first lane whose inclusive sum exceeds it
+      if (tid < n_valid && incl > (uint32_t)RSYM) atomicMin(&S.first_over, tid);
       __syncthreads();
-      if (tid == n_valid - 1) {
+      const bool cut_by_budget = S.first_over < n_valid;
+      if (cut_by_budget) n_valid = S.first_over;
+      const uint32_t out0 = S.out_pos;
+      if (tid < n_valid) mine = out_valid; else mine = 0;
+      const uint32_t my_off = out0 + incl - out_valid; // only meaningful for tid < n_valid
+      if (n_valid == 0) {
+        if (tid == 0) S.next = NEXT_RETRY; // truncated input: the general kernel reports what the reference does
+      } else if (tid == n_valid - 1) {
         // this lane closes the round
-        uint32_t round_out = incl - 0u; // inclusive sum up to the last valid lane
+        const uint32_t round_out = incl; // inclusive sum up to the last valid lane
         S.round_out = round_out;
-        S.lane_off[n_valid] = out0 + round_out;
         int nx;
-        int64_t nb;
+        const int64_t nb = base_bit + (int64_t)SUB_BITS * tid + tpos;
         if (!cut_by_budget && first_term < first_bad) {
           // closed by this lane's own exit
-          nb = base_bit + (int64_t)SUB_BITS * tid + tpos;
           if (tkind == X_EOB) nx = S.last_block ? NEXT_FINISH : NEXT_HEADER;
           else if (tkind == X_ERR) nx = NEXT_RETRY;
-          else nx = NEXT_CONTINUE; // X_CAP / X_NOSYNC: resume right after the last token
+          else nx = NEXT_CONTINUE; // X_CAP: resume right after the last token
         } else {
           // the next lane could not be chained (or did not fit the budget): it opens the next round
           // at this lane's (normal) exit
-          nb = base_bit + (int64_t)SUB_BITS * tid + tpos;
           nx = NEXT_CONTINUE;
         }
         if ((int64_t)out0 + round_out > S.dst_cap) nx = NEXT_RETRY; // Unexpected_end_of_output: exact point needed
@@ -703,127 +756,196 @@ inflate_parallel_kernel(int fmt, int64_t nstreams, const uint8_t *src_base, cons
       __syncthreads();
       if (S.next == NEXT_RETRY) break;
       const uint32_t round_out = S.round_out;
-      // ---- D: replay tokens into the ring
-      // make sure earlier bulk stores finished reading the ring region this round overwrites
-      if (tid == 0) { tma_store_wait_read(); S.abort_round = 0; }
-      // bucket map: lane owning the first byte of every 64-byte bucket of this round's output
-      if (tid < n_valid) {
-        uint32_t a = my_off - out0, b = a + mine;
-        for (uint32_t q = (a + (1u << BUCKET_SHIFT) - 1u) >> BUCKET_SHIFT; (q << BUCKET_SHIFT) < b; q++) S.bucket[q] = (uint8_t)tid;
-        S.progress[tid] = my_off;
+      // Symbol-buffer coordinates: index i <-> stream position out0 + (i - bias) <-> global address G0 + i,
+      // G0 = (dst + out0) rounded down to 16 bytes, so that 16-symbol chunks are aligned 16-byte stores.
+      const uint32_t bias = (uint32_t)((uintptr_t)(S.dst + out0) & 15);
+      uint8_t *const G0 = S.dst + out0 - bias;
+      const uint32_t g0_low = (uint32_t)((uintptr_t)G0 & HIST_MASK);
+      const uint32_t E = bias + round_out; // one past the last symbol of the round
+      // ---- D: replay tokens into symbols
+      if (tid < 16) {
+        if ((uint32_t)tid < bias) S.sym[tid] = 0;
+        S.sym[E + tid] = 0;
       }
-      __syncthreads();
       {
-        const uint32_t bias = S.ring_bias;
-        bool active = tid < n_valid;
-        const int total_tok = active ? nh + (merged ? ns - kmerge : 0) : 0;
-        STAT(if (active) { g_stats.head_tokens += nh; g_stats.used_tokens += total_tok; } g_stats.spec_tokens += ns;)
-        int ti = 0;                     // token index over head ++ spec[kmerge..]
-        uint32_t pos = my_off;          // stream-relative output position
-        uint32_t rem = 0, src = 0;      // pending match copy
-        bool waiting = false;           // the pending match still has to see its source bytes
-        uint32_t need_hi = 0;
+        // Every lane walks its own token list: head tokens [0, nh), then the speculative tokens from
+        // the merge point on.  One step of the (warp-uniform) loop emits a literal or up to four
+        // symbols of a match; the source of a match decides how:
+        //   MARK  entirely inside this round, before this lane's first symbol: markers, no load
+        //   HISTV entirely in earlier rounds: bytes of the history ring
+        //   SLOW  anything else (overlaps the lane's own output, or straddles a boundary): per symbol
+        enum : int { C_MARK = 0, C_HISTV = 1, C_SLOW = 2 };
+        const int total_tok = tid < n_valid ? nh + (merged ? ns - kmerge : 0) : 0;
+        const int delta = HEAD_CAP + kmerge - nh; // token index -> slot for the speculative part
+        STAT(if (tid < n_valid) { g_stats.head_tokens += nh; g_stats.used_tokens += total_tok; } long iters = 0;)
+        const int32_t my_i0 = (int32_t)(my_off - out0 + bias);
+        const uint32_t *ring32 = reinterpret_cast<const uint32_t *>(S.ring);
+        int ti = 0;
+        int32_t i = my_i0;            // next symbol to write
+        int32_t s = 0;                // next source symbol of the pending match
+        uint32_t rem = 0;             // symbols the pending match still owes
+        int cls = C_MARK;
+        uint4 cur = make_uint4(0, 0, 0, 0), nxt = make_uint4(0, 0, 0, 0);
+        int cur_b = -1;
+        bool active = total_tok > 0;
+        if (active) nxt = tok_lane[(nh > 0 ? 0 : delta) >> 2];
         while (__any_sync(0xffffffffu, active)) {
-          if (active) {
-            STAT(g_stats.d_iters++; if (rem && waiting) g_stats.d_wait_iters++;)
-            if (S.abort_round) { active = false; continue; }
-            if (rem == 0) {
-              if (ti == total_tok) {
-                __threadfence_block();
-                S.progress[tid] = pos;
-                active = false;
+          STAT(if (active) iters++;)
+          if (active && rem == 0) {
+            if (ti == total_tok) {
+              active = false;
+            } else {
+              const int slot = ti < nh ? ti : ti + delta;
+              if ((slot >> 2) != cur_b) {
+                cur = nxt;
+                cur_b = slot >> 2;
+                int t2 = ti + 4 - (slot & 3);          // first token of the batch after this one
+                if (ti < nh && t2 > nh) t2 = nh;
+                if (t2 < total_tok) nxt = tok_lane[(t2 < nh ? t2 : t2 + delta) >> 2];
+              }
+              const uint32_t t = batch_get(cur, slot & 3);
+              ti++;
+              if (!tok_is_match(t)) {
+                S.sym[i] = (uint16_t)(t & 0xffu);
+                i++;
               } else {
-                uint32_t t = ti < nh ? tok_head[(size_t)ti * PT] : tok_spec[(size_t)(kmerge + (ti - nh)) * PT];
-                ti++;
-                if (!tok_is_match(t)) {
-                  S.ring[(pos + bias) & RING_MASK] = (uint8_t)(t & 0xffu);
-                  pos++;
-                } else {
-                  uint32_t d = ((t >> 8) & 0x7fffu) + 1u;
-                  if (d > pos) { // Invalid distance (de.ml:1700): the general kernel reports it
-                    S.abort_round = 1;
-                    active = false;
-                  } else {
-                    rem = (t & 0xffu) + 3u;
-                    src = pos - d;
-                    // source bytes this match needs from outside itself: [src, min(src+rem, pos))
-                    need_hi = umin32(src + rem, pos);
-                    waiting = need_hi > out0 && src < my_off; // touches bytes other lanes write this round
-                    __threadfence_block();
-                    S.progress[tid] = pos; // everything before this match is in the ring
-                  }
+                const uint32_t d = ((t >> 8) & 0x7fffu) + 1u;
+                rem = (t & 0xffu) + 3u;
+                s = i - (int32_t)d;
+                if (d > out0 + (uint32_t)(i - (int32_t)bias)) { // Invalid distance (de.ml:1700): the general kernel reports it
+                  S.abort_round = 1;
+                  active = false;
+                  rem = 0;
                 }
-              }
-            }
-            if (rem) {
-              bool ready = true;
-              if (waiting) {
-                uint32_t q_hi = umin32(need_hi, my_off);
-                uint32_t q_lo = umax32(src, out0);
-                if (q_lo < q_hi) {
-                  int v = S.bucket[(q_hi - 1u - out0) >> BUCKET_SHIFT];
-                  // bucket[] names the owner of the bucket's first byte; walk up to the owner of q_hi-1
-                  while (S.lane_off[v + 1] <= q_hi - 1u) v++;
-                  ready = S.progress[v] >= q_hi;
-                  while (ready && S.lane_off[v] > q_lo) {
-                    v--;
-                    ready = S.progress[v] >= S.lane_off[v + 1];
-                  }
-                }
-                if (ready) { waiting = false; __threadfence_block(); }
-              }
-              if (ready) {
-                uint32_t n = umin32(rem, 8u);
-                for (uint32_t i = 0; i < n; i++) S.ring[(pos + i + bias) & RING_MASK] = S.ring[(src + i + bias) & RING_MASK];
-                pos += n;
-                src += n;
-                rem -= n;
+                const int32_t s_end = s + (int32_t)rem;
+                cls = (s >= (int32_t)bias && s_end <= my_i0) ? C_MARK : (s_end <= (int32_t)bias) ? C_HISTV : C_SLOW;
               }
             }
           }
+          if (rem > 0) {
+            const uint32_t n = rem < 4u ? rem : 4u;
+            if (cls == C_SLOW) {
+              for (uint32_t k = 0; k < n; k++) {
+                const int32_t sk = s + (int32_t)k;
+                uint32_t v;
+                if (sk >= my_i0) { v = S.sym[sk]; STAT(g_stats.own_bytes++;) }                        // produced by this lane
+                else if (sk >= (int32_t)bias) { v = 256u + (uint32_t)sk; STAT(g_stats.markers++;) }   // another lane of this round
+                else { v = S.ring[(g0_low + (uint32_t)sk) & HIST_MASK]; STAT(g_stats.hist_bytes++;) } // history
+                S.sym[i + (int32_t)k] = (uint16_t)v;
+              }
+            } else {
+              uint32_t lo, hi; // four symbols, two per word
+              if (cls == C_MARK) {
+                lo = (256u + (uint32_t)s) * 0x00010001u + 0x00010000u;
+                hi = lo + 0x00020002u;
+                STAT(g_stats.markers += n;)
+              } else {
+                const uint32_t r = g0_low + (uint32_t)s; // ring byte address (mod HIST) of the first source byte
+                const uint32_t w0 = ring32[(r >> 2) & (HIST / 4 - 1)], w1 = ring32[((r >> 2) + 1u) & (HIST / 4 - 1)];
+                const uint32_t w = __funnelshift_r(w0, w1, 8u * (r & 3u));
+                lo = __byte_perm(w, 0u, 0x4140);
+                hi = __byte_perm(w, 0u, 0x4342);
+                STAT(g_stats.hist_bytes += n;)
+              }
+              if (n == 4u && (i & 3) == 0) {
+                *reinterpret_cast<uint2 *>(S.sym + i) = make_uint2(lo, hi);
+              } else {
+                S.sym[i] = (uint16_t)lo;
+                if (n > 1u) S.sym[i + 1] = (uint16_t)(lo >> 16);
+                if (n > 2u) S.sym[i + 2] = (uint16_t)hi;
+                if (n > 3u) S.sym[i + 3] = (uint16_t)(hi >> 16);
+              }
+            }
+            i += (int32_t)n;
+            s += (int32_t)n;
+            rem -= n;
+          }
         }
-        __syncthreads();
-        if (S.abort_round) {
-          if (tid == 0) S.next = NEXT_RETRY;
-          __syncthreads();
-          break;
-        }
+        STAT(g_stats.d_iters += iters; if (iters > g_stats.d_lane_max_iters) g_stats.d_lane_max_iters = iters;)
       }
-      // ---- E: drain finished bytes, fold Adler-32
+      STAT(if (tid == 0) g_stats.spec_tokens += 0;)
+      STAT(g_stats.spec_tokens += ns;)
+      __syncthreads();
+      if (S.abort_round) {
+        __syncthreads();
+        if (tid == 0) S.next = NEXT_RETRY;
+        __syncthreads();
+        break;
+      }
+      // ---- E: resolve markers, drain to HBM and to the history ring, fold Adler-32
       {
-        const uint32_t new_pos = out0 + round_out;
-        const uint32_t bias = S.ring_bias;
-        if (fmt == DCMP_FMT_ZLIB && round_out) {
-          // granules of 16 ring bytes covering [out0, new_pos); bytes outside are masked to zero
-          uint32_t g_lo = (out0 + bias) & ~15u, g_hi = (new_pos + bias + 15u) & ~15u; // biased coordinates
-          unsigned long long s_sum = 0, b_sum = 0;
-          for (uint32_t g = g_lo + 16u * tid; g < g_hi; g += 16u * PT) {
-            uint4 q = *(const uint4 *)(S.ring + (g & RING_MASK));
-            uint32_t wv[4] = {q.x, q.y, q.z, q.w};
-            uint32_t s = 0, b = 0;
+        const uint32_t nchunks = (E + 15u) >> 4;
+        unsigned long long s_sum = 0;
+        long long b_sum = 0;
+        for (uint32_t c = (uint32_t)tid; c < nchunks; c += PT) {
+          const uint32_t i0 = c << 4;
+          uint4 qa = *(const uint4 *)(S.sym + i0);
+          uint4 qb = *(const uint4 *)(S.sym + i0 + 8);
+          uint32_t pr[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
+          uint32_t wv[4];
+          const bool any_marker = ((qa.x | qa.y | qa.z | qa.w | qb.x | qb.y | qb.z | qb.w) & 0xff00ff00u) != 0u;
+#pragma unroll
+          for (int k = 0; k < 4; k++) {
+            uint32_t w = 0;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+              uint32_t v = (pr[2 * k + (j >> 1)] >> (16 * (j & 1))) & 0xffffu;
+              STAT(long hops = 0;)
+              while (v >= 256u) { v = S.sym[v - 256u]; STAT(hops++;) }
+              STAT(g_stats.chase_hops += hops; if (hops > g_stats.chase_max) g_stats.chase_max = hops;)
+              w |= v << (8 * j);
+            }
+            wv[k] = w;
+          }
+          // path compression: later chases that land here stop after one hop (a racing reader sees
+          // either the old marker or the final literal — both lead to the same byte)
+          if (any_marker) {
+            uint4 ra, rb;
+            ra.x = __byte_perm(wv[0], 0u, 0x4140); ra.y = __byte_perm(wv[0], 0u, 0x4342);
+            ra.z = __byte_perm(wv[1], 0u, 0x4140); ra.w = __byte_perm(wv[1], 0u, 0x4342);
+            rb.x = __byte_perm(wv[2], 0u, 0x4140); rb.y = __byte_perm(wv[2], 0u, 0x4342);
+            rb.z = __byte_perm(wv[3], 0u, 0x4140); rb.w = __byte_perm(wv[3], 0u, 0x4342);
+            *(uint4 *)(S.sym + i0) = ra;
+            *(uint4 *)(S.sym + i0 + 8) = rb;
+          }
+          const bool full = i0 >= bias && i0 + 16u <= E;
+          if (full) {
+            uint4 q = make_uint4(wv[0], wv[1], wv[2], wv[3]);
+            *(uint4 *)(G0 + i0) = q;
+            *(uint4 *)(S.ring + ((g0_low + i0) & HIST_MASK)) = q;
+          } else {
 #pragma unroll
             for (int k = 0; k < 4; k++) {
-              uint32_t w = wv[k];
-              // mask bytes outside [out0+bias, new_pos+bias)
-              uint32_t byte0 = g + 4u * k;
               uint32_t m = 0;
 #pragma unroll
               for (int j = 0; j < 4; j++) {
-                uint32_t bp = byte0 + j;
-                if (bp >= out0 + bias && bp < new_pos + bias) m |= 0xffu << (8 * j);
+                uint32_t idx = i0 + 4u * k + j;
+                if (idx >= bias && idx < E) {
+                  uint8_t b = (uint8_t)(wv[k] >> (8 * j));
+                  G0[idx] = b;
+                  S.ring[(g0_low + idx) & HIST_MASK] = b;
+                  m |= 0xffu << (8 * j);
+                }
               }
-              w &= m;
-              s += __dp4a(w, 0x01010101u, 0u);
-              // weight of byte j of word k: distance to the granule end = 16 - (4k + j)
-              b += __dp4a(w, (uint32_t)(((16 - 4 * k) & 0xff) | (((15 - 4 * k) & 0xff) << 8) | (((14 - 4 * k) & 0xff) << 16) |
-                                        (((13 - 4 * k) & 0xff) << 24)),
-                          0u);
+              wv[k] &= m;
             }
-            // bytes after this granule's end inside the round (may be negative by < 16 for the last granule)
-            long long after = (long long)(new_pos + bias) - (long long)(g + 16u);
-            s_sum += s;
-            b_sum += (unsigned long long)((long long)b + (long long)s * after);
           }
+          if (fmt == DCMP_FMT_ZLIB) {
+            uint32_t sb = 0, bb = 0;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+              sb = __dp4a(wv[k], 0x01010101u, sb);
+              // weight of byte j of word k: distance to the chunk end = 16 - (4k + j)
+              bb = __dp4a(wv[k], (uint32_t)(((16 - 4 * k) & 0xff) | (((15 - 4 * k) & 0xff) << 8) |
+                                            (((14 - 4 * k) & 0xff) << 16) | (((13 - 4 * k) & 0xff) << 24)), bb);
+            }
+            // bytes of the round after this chunk's end (negative by < 16 for a ragged last chunk)
+            long long after = (long long)E - (long long)(i0 + 16u);
+            s_sum += sb;
+            b_sum += (long long)bb + (long long)sb * after;
+          }
+        }
+        if (fmt == DCMP_FMT_ZLIB) {
           for (int o = 16; o > 0; o >>= 1) {
             s_sum += __shfl_xor_sync(0xffffffffu, s_sum, o);
             b_sum += __shfl_xor_sync(0xffffffffu, b_sum, o);
@@ -833,40 +955,20 @@ inflate_parallel_kernel(int fmt, int64_t nstreams, const uint8_t *src_base, cons
         __syncthreads();
         if (tid == 0) {
           if (fmt == DCMP_FMT_ZLIB && round_out) {
-            unsigned long long s_sum = 0, b_sum = 0;
-            for (int w = 0; w < PT / 32; w++) { s_sum += S.adl_s[w]; b_sum += S.adl_b[w]; }
+            unsigned long long ts = 0;
+            long long tb = 0;
+            for (int w = 0; w < NWARP; w++) { ts += S.adl_s[w]; tb += S.adl_b[w]; }
             const unsigned long long M = 65521ull;
-            // (A,B) after appending a segment with byte sum s and suffix-weighted sum b of length n:
+            // (A,B) after appending a segment of n bytes with byte sum s and suffix-weighted sum b:
             // B' = B + n*A + b ; A' = A + s
             unsigned long long a = S.adler_a, b = S.adler_b;
-            b = (b + (round_out % M) * a + b_sum % M) % M;
-            a = (a + s_sum % M) % M;
+            b = (b + (round_out % M) * a + (unsigned long long)tb % M) % M;
+            a = (a + ts % M) % M;
             S.adler_a = (uint32_t)a;
             S.adler_b = (uint32_t)b;
           }
-          // bulk-store the 16-byte aligned body of [flushed, new_pos); ragged ends wait for later / the finish
-          fence_proxy_async();
-          uint32_t lo = S.flushed, hi = new_pos;
-          uintptr_t ga = (uintptr_t)S.dst;
-          uint32_t lo_al = (uint32_t)((((ga + lo) + 15) & ~(uintptr_t)15) - ga);
-          uint32_t hi_al = (uint32_t)(((ga + hi) & ~(uintptr_t)15) - ga);
-          if (S.next == NEXT_FINISH) hi_al = hi_al; // tail bytes handled below by all threads
-          if (hi_al > lo_al && lo_al >= lo) {
-            // head bytes [lo, lo_al) are stored by the finish path or were stored already
-            if (lo == 0 && lo_al > 0) {
-              for (uint32_t i = 0; i < lo_al && i < hi; i++) S.dst[i] = S.ring[(i + bias) & RING_MASK];
-            }
-            uint32_t a = lo_al;
-            while (a < hi_al) {
-              uint32_t ri = (a + bias) & RING_MASK;
-              uint32_t n = umin32(hi_al - a, (uint32_t)RING - ri); // do not cross the ring end
-              tma_store_1d(S.dst + a, S.ring + ri, n);
-              a += n;
-            }
-            tma_store_commit();
-            S.flushed = hi_al;
-          }
-          S.out_pos = new_pos;
+          S.out_pos = out0 + round_out;
+          STAT(g_stats.out_bytes += round_out;)
         }
         __syncthreads();
       }
@@ -874,46 +976,36 @@ inflate_parallel_kernel(int fmt, int64_t nstreams, const uint8_t *src_base, cons
 
     // ---------------------------------------------------------------- finish the stream
     __syncthreads();
-    {
+    if (tid == 0) {
       const int64_t k = S.stream;
+      int st = DCMP_INTERNAL_RETRY;
+      int64_t cons = 0, prod = 0;
       if (S.next == NEXT_FINISH) {
-        // ragged tail (and a head shorter than one granule) by plain stores
-        const uint32_t bias = S.ring_bias;
-        for (uint32_t i = S.flushed + tid; i < S.out_pos; i += PT) S.dst[i] = S.ring[(i + bias) & RING_MASK];
-        if (tid == 0) {
-          tma_store_wait_all();
-          int st = DCMP_OK;
-          int64_t c = S.base_bit;
-          int64_t cons = (c + 7) >> 3;
-          if (c > 8 * S.src_len) st = DCMP_INTERNAL_RETRY; // decoded past the end: reference quirk, general kernel
-          if (fmt == DCMP_FMT_ZLIB && st == DCMP_OK) {
-            const uint8_t *tr = S.src + cons; // lib/zl.ml:409-415: big-endian Adler-32 right after the deflate data
-            uint32_t want = ((uint32_t)tr[0] << 24) | ((uint32_t)tr[1] << 16) | ((uint32_t)tr[2] << 8) | (uint32_t)tr[3];
-            uint32_t got = (S.adler_b << 16) | S.adler_a;
-            if (want != got) st = DCMP_INVALID_CHECKSUM;
-            else cons += 6;
-            if (st != DCMP_OK) cons = 0;
-          }
-          consumed[k] = cons;
-          produced[k] = S.out_pos;
-          status[k] = st;
+        st = DCMP_OK;
+        int64_t c = S.base_bit;
+        cons = (c + 7) >> 3;
+        prod = S.out_pos;
+        if (c > 8 * S.src_len) st = DCMP_INTERNAL_RETRY; // decoded past the end: reference quirk, general kernel
+        if (fmt == DCMP_FMT_ZLIB && st == DCMP_OK) {
+          const uint8_t *tr = S.src + cons; // lib/zl.ml:409-415: big-endian Adler-32 right after the deflate data
+          uint32_t want = ((uint32_t)tr[0] << 24) | ((uint32_t)tr[1] << 16) | ((uint32_t)tr[2] << 8) | (uint32_t)tr[3];
+          uint32_t got = (S.adler_b << 16) | S.adler_a;
+          if (want != got) { st = DCMP_INVALID_CHECKSUM; cons = 0; }
+          else cons += 6;
         }
-      } else {
-        if (tid == 0) {
-          tma_store_wait_all();
-          consumed[k] = 0;
-          produced[k] = 0;
-          status[k] = DCMP_INTERNAL_RETRY;
-        }
+        if (st == DCMP_INTERNAL_RETRY) { cons = 0; prod = 0; }
       }
+      STAT(if (st == DCMP_INTERNAL_RETRY) g_stats.retries++;)
+      consumed[k] = cons;
+      produced[k] = prod;
+      status[k] = st;
     }
   }
-  if (tid == 0) tma_store_wait_all();
 }
 
 size_t inflate_parallel_smem_bytes() { return sizeof(ParSmem) + 128; }
 // bytes of token scratch one CTA needs (global memory, stays L2-resident)
-size_t inflate_parallel_scratch_bytes_per_cta() { return (size_t)TOK_SLOTS * PT * sizeof(uint32_t); }
+size_t inflate_parallel_scratch_bytes_per_cta() { return (size_t)TOK_SLOTS * PT * sizeof(uint32_t) + 64; }
 
 #ifndef DCMP_EMU
 int launch_inflate_parallel(int fmt, int64_t n, const uint8_t *src_base, const int64_t *src_off, const int64_t *src_len,

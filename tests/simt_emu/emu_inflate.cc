@@ -24,16 +24,15 @@ int emu_inflate_batch(int mode, int fmt, int64_t n, const uint8_t *src, const in
     });
   }
   if (mode == 1) return 0;
-  std::vector<int32_t> todo;
+  int retried = 0;
   for (int64_t k = 0; k < n; k++)
-    if (mode == 2 || status[k] == DCMP_INTERNAL_RETRY) todo.push_back((int32_t)k);
-  if (!todo.empty()) {
-    int64_t m = (int64_t)todo.size();
-    simt::launch(simt::dim3((unsigned)((m + SERIAL_WARPS - 1) / SERIAL_WARPS)), simt::dim3(SERIAL_WARPS * 32), 0, [&]() {
-      inflate_serial_kernel(fmt, m, src, soff, slen, dst, doff, dcap, cons, prod, status, todo.data());
+    if (mode == 2 || status[k] == DCMP_INTERNAL_RETRY) retried++;
+  if (retried) {
+    simt::launch(simt::dim3((unsigned)((n + SERIAL_WARPS - 1) / SERIAL_WARPS)), simt::dim3(SERIAL_WARPS * 32), 0, [&]() {
+      inflate_serial_kernel(fmt, n, src, soff, slen, dst, doff, dcap, cons, prod, status, mode == 2 ? -1 : DCMP_INTERNAL_RETRY);
     });
   }
-  return (int)todo.size();
+  return retried;
 }
 
 long emu_switches() { return simt::g_switches; }

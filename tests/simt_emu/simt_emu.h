@@ -247,4 +247,6 @@ template <class T> inline T max(T a, T b) { return a > b ? a : b; }
   simt::launch(simt::dim3(grid), simt::dim3(block), (smem), [&]() { kernel(__VA_ARGS__); })
 
 struct uint4 { unsigned x, y, z, w; };
+struct uint2 { unsigned x, y; };
+inline uint2 make_uint2(unsigned a, unsigned b) { return uint2{a, b}; }
 inline uint4 make_uint4(unsigned a, unsigned b, unsigned c, unsigned d) { return uint4{a, b, c, d}; }
