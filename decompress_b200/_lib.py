@@ -9,7 +9,7 @@ import os
 import re
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdcmp_b200.so")
+LIB_PATH = os.environ.get("DCMP_LIB_PATH") or os.path.join(_HERE, "libdcmp_b200.so")  # override: tuning builds only
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "dcmp.h")
 
 API_OK, API_NO_DEVICE, API_CUDA_ERROR, API_INVALID_ARGUMENT, API_OUT_OF_MEMORY = 0, -1, -2, -3, -4

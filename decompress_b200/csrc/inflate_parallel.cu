@@ -47,10 +47,10 @@
 namespace dcmp {
 
 #ifndef DCMP_PT
-#define DCMP_PT 192
+#define DCMP_PT 256
 #endif
 #ifndef DCMP_SUB_WORDS
-#define DCMP_SUB_WORDS 13
+#define DCMP_SUB_WORDS 9
 #endif
 
 constexpr int PT = DCMP_PT;               // threads (= lanes = sub-chunks per round)
@@ -769,97 +769,110 @@ inflate_parallel_kernel(int fmt, int64_t nstreams, const uint8_t *src_base, cons
       }
       {
         // Every lane walks its own token list: head tokens [0, nh), then the speculative tokens from
-        // the merge point on.  One step of the (warp-uniform) loop emits a literal or up to four
+        // the merge point on.  One step of the (warp-uniform) loop emits a literal or up to eight
         // symbols of a match; the source of a match decides how:
-        //   MARK  entirely inside this round, before this lane's first symbol: markers, no load
-        //   HISTV entirely in earlier rounds: bytes of the history ring
-        //   SLOW  anything else (overlaps the lane's own output, or straddles a boundary): per symbol
-        enum : int { C_MARK = 0, C_HISTV = 1, C_SLOW = 2 };
+        //   inside this round (any lane, this one included): markers 256 + source index, no load at all
+        //   entirely in earlier rounds: bytes of the history ring
+        //   straddling the start of the round, or overlapping itself inside the group: per symbol
         const int total_tok = tid < n_valid ? nh + (merged ? ns - kmerge : 0) : 0;
         const int delta = HEAD_CAP + kmerge - nh; // token index -> slot for the speculative part
         STAT(if (tid < n_valid) { g_stats.head_tokens += nh; g_stats.used_tokens += total_tok; } long iters = 0;)
-        const int32_t my_i0 = (int32_t)(my_off - out0 + bias);
         const uint32_t *ring32 = reinterpret_cast<const uint32_t *>(S.ring);
         int ti = 0;
-        int32_t i = my_i0;            // next symbol to write
+        int32_t i = (int32_t)(my_off - out0 + bias); // next symbol to write
         int32_t s = 0;                // next source symbol of the pending match
         uint32_t rem = 0;             // symbols the pending match still owes
-        int cls = C_MARK;
+        uint32_t dist = 0;
         uint4 cur = make_uint4(0, 0, 0, 0), nxt = make_uint4(0, 0, 0, 0);
         int cur_b = -1;
         bool active = total_tok > 0;
         if (active) nxt = tok_lane[(nh > 0 ? 0 : delta) >> 2];
         while (__any_sync(0xffffffffu, active)) {
           STAT(if (active) iters++;)
-          if (active && rem == 0) {
-            if (ti == total_tok) {
-              active = false;
-            } else {
-              const int slot = ti < nh ? ti : ti + delta;
-              if ((slot >> 2) != cur_b) {
-                cur = nxt;
-                cur_b = slot >> 2;
-                int t2 = ti + 4 - (slot & 3);          // first token of the batch after this one
-                if (ti < nh && t2 > nh) t2 = nh;
-                if (t2 < total_tok) nxt = tok_lane[(t2 < nh ? t2 : t2 + delta) >> 2];
-              }
-              const uint32_t t = batch_get(cur, slot & 3);
-              ti++;
-              if (!tok_is_match(t)) {
-                S.sym[i] = (uint16_t)(t & 0xffu);
-                i++;
+          uint32_t n = 0;               // symbols emitted by this step
+          uint32_t p0 = 0, p1 = 0, p2 = 0, p3 = 0; // up to eight symbols, two per word
+          bool slow = false;
+          if (active) {
+            if (rem == 0) {
+              if (ti == total_tok) {
+                active = false;
               } else {
-                const uint32_t d = ((t >> 8) & 0x7fffu) + 1u;
-                rem = (t & 0xffu) + 3u;
-                s = i - (int32_t)d;
-                if (d > out0 + (uint32_t)(i - (int32_t)bias)) { // Invalid distance (de.ml:1700): the general kernel reports it
-                  S.abort_round = 1;
-                  active = false;
-                  rem = 0;
+                const int slot = ti < nh ? ti : ti + delta;
+                if ((slot >> 2) != cur_b) {
+                  cur = nxt;
+                  cur_b = slot >> 2;
+                  int t2 = ti + 4 - (slot & 3);          // first token of the batch after this one
+                  if (ti < nh && t2 > nh) t2 = nh;
+                  if (t2 < total_tok) nxt = tok_lane[(t2 < nh ? t2 : t2 + delta) >> 2];
                 }
-                const int32_t s_end = s + (int32_t)rem;
-                cls = (s >= (int32_t)bias && s_end <= my_i0) ? C_MARK : (s_end <= (int32_t)bias) ? C_HISTV : C_SLOW;
+                const uint32_t t = batch_get(cur, slot & 3);
+                ti++;
+                if (!tok_is_match(t)) {
+                  p0 = t & 0xffu;
+                  n = 1;
+                } else {
+                  dist = ((t >> 8) & 0x7fffu) + 1u;
+                  rem = (t & 0xffu) + 3u;
+                  s = i - (int32_t)dist;
+                  if (dist > out0 + (uint32_t)(i - (int32_t)bias)) { // Invalid distance (de.ml:1700): the general kernel reports it
+                    S.abort_round = 1;
+                    active = false;
+                    rem = 0;
+                  }
+                }
               }
             }
-          }
-          if (rem > 0) {
-            const uint32_t n = rem < 4u ? rem : 4u;
-            if (cls == C_SLOW) {
-              for (uint32_t k = 0; k < n; k++) {
-                const int32_t sk = s + (int32_t)k;
-                uint32_t v;
-                if (sk >= my_i0) { v = S.sym[sk]; STAT(g_stats.own_bytes++;) }                        // produced by this lane
-                else if (sk >= (int32_t)bias) { v = 256u + (uint32_t)sk; STAT(g_stats.markers++;) }   // another lane of this round
-                else { v = S.ring[(g0_low + (uint32_t)sk) & HIST_MASK]; STAT(g_stats.hist_bytes++;) } // history
-                S.sym[i + (int32_t)k] = (uint16_t)v;
-              }
-            } else {
-              uint32_t lo, hi; // four symbols, two per word
-              if (cls == C_MARK) {
-                lo = (256u + (uint32_t)s) * 0x00010001u + 0x00010000u;
-                hi = lo + 0x00020002u;
-                STAT(g_stats.markers += n;)
-              } else {
+            if (rem > 0) {
+              n = rem < 8u ? rem : 8u;
+              if (s >= (int32_t)bias) {
+                // source inside this round (another lane's output or this lane's own): markers
+                if (dist >= n) {
+                  p0 = (256u + (uint32_t)s) * 0x00010001u + 0x00010000u;
+                  p1 = p0 + 0x00020002u;
+                  p2 = p0 + 0x00040004u;
+                  p3 = p0 + 0x00060006u;
+                  STAT(g_stats.markers += n;)
+                } else {
+                  slow = true; // the copy overlaps itself inside this group: point at the first period
+                }
+              } else if (s + (int32_t)n <= (int32_t)bias) {
+                // source entirely in earlier rounds: bytes of the history ring
                 const uint32_t r = g0_low + (uint32_t)s; // ring byte address (mod HIST) of the first source byte
-                const uint32_t w0 = ring32[(r >> 2) & (HIST / 4 - 1)], w1 = ring32[((r >> 2) + 1u) & (HIST / 4 - 1)];
-                const uint32_t w = __funnelshift_r(w0, w1, 8u * (r & 3u));
-                lo = __byte_perm(w, 0u, 0x4140);
-                hi = __byte_perm(w, 0u, 0x4342);
+                const uint32_t wi0 = r >> 2;
+                const uint32_t w0 = ring32[wi0 & (HIST / 4 - 1)], w1 = ring32[(wi0 + 1u) & (HIST / 4 - 1)],
+                               w2 = ring32[(wi0 + 2u) & (HIST / 4 - 1)];
+                const uint32_t sh8 = 8u * (r & 3u);
+                const uint32_t a = __funnelshift_r(w0, w1, sh8), b = __funnelshift_r(w1, w2, sh8);
+                p0 = __byte_perm(a, 0u, 0x4140);
+                p1 = __byte_perm(a, 0u, 0x4342);
+                p2 = __byte_perm(b, 0u, 0x4140);
+                p3 = __byte_perm(b, 0u, 0x4342);
                 STAT(g_stats.hist_bytes += n;)
-              }
-              if (n == 4u && (i & 3) == 0) {
-                *reinterpret_cast<uint2 *>(S.sym + i) = make_uint2(lo, hi);
               } else {
-                S.sym[i] = (uint16_t)lo;
-                if (n > 1u) S.sym[i + 1] = (uint16_t)(lo >> 16);
-                if (n > 2u) S.sym[i + 2] = (uint16_t)hi;
-                if (n > 3u) S.sym[i + 3] = (uint16_t)(hi >> 16);
+                slow = true; // straddles the start of the round
               }
             }
-            i += (int32_t)n;
-            s += (int32_t)n;
-            rem -= n;
           }
+          if (slow) {
+            for (uint32_t k = 0; k < n; k++) {
+              const int32_t sk = s + (int32_t)(dist < n ? k % dist : k);
+              uint32_t v;
+              if (sk >= (int32_t)bias) { v = 256u + (uint32_t)sk; STAT(g_stats.markers++;) }
+              else { v = S.ring[(g0_low + (uint32_t)sk) & HIST_MASK]; STAT(g_stats.hist_bytes++;) }
+              S.sym[i + (int32_t)k] = (uint16_t)v;
+            }
+          } else {
+            if (n > 0u) S.sym[i] = (uint16_t)p0;
+            if (n > 1u) S.sym[i + 1] = (uint16_t)(p0 >> 16);
+            if (n > 2u) S.sym[i + 2] = (uint16_t)p1;
+            if (n > 3u) S.sym[i + 3] = (uint16_t)(p1 >> 16);
+            if (n > 4u) S.sym[i + 4] = (uint16_t)p2;
+            if (n > 5u) S.sym[i + 5] = (uint16_t)(p2 >> 16);
+            if (n > 6u) S.sym[i + 6] = (uint16_t)p3;
+            if (n > 7u) S.sym[i + 7] = (uint16_t)(p3 >> 16);
+          }
+          i += (int32_t)n;
+          if (rem > 0) { s += (int32_t)n; rem -= n; }
         }
         STAT(g_stats.d_iters += iters; if (iters > g_stats.d_lane_max_iters) g_stats.d_lane_max_iters = iters;)
       }
