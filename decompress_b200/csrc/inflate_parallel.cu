@@ -57,11 +57,11 @@ constexpr int PT = DCMP_PT;               // threads (= lanes = sub-chunks per r
 constexpr int NWARP = PT / 32;
 constexpr int SUB_WORDS = DCMP_SUB_WORDS; // sub-chunk size in 32-bit words (odd: conflict-free lane stride)
 constexpr int SUB_BITS = 32 * SUB_WORDS;
-constexpr int SPEC_CAP = 120;             // tokens a lane may produce speculatively (< 256: checkpoint field)
-constexpr int HEAD_CAP = 56;              // tokens a lane may produce while re-synchronising
+constexpr int SPEC_CAP = ((SUB_BITS / 3) + 3) & ~3; // tokens a lane may produce speculatively (< 256: checkpoint field)
+constexpr int HEAD_CAP = 96;              // tokens a lane may produce while re-synchronising (p99 of the distance is ~55 on text)
 constexpr int TOK_SLOTS = SPEC_CAP + HEAD_CAP; // per lane, in the global scratch
-constexpr int LANE_BYTE_CAP = 4096;       // bytes a lane may produce per pass (checkpoint field: 18 bits)
-constexpr int CKPT_SHIFT = 6;             // one checkpoint per 64-bit window of the sub-chunk
+constexpr int LANE_BYTE_CAP = 4096;       // bytes a lane may produce per pass (checkpoint field: 19 bits)
+constexpr int CKPT_SHIFT = 5;             // one checkpoint per 32-bit window of the sub-chunk
 constexpr int NCKPT = (SUB_BITS >> CKPT_SHIFT) + 1;
 constexpr int HIST = 32768;               // history ring (the sliding window, de.ml:439-440) in bytes
 constexpr int HIST_MASK = HIST - 1;
@@ -72,13 +72,31 @@ constexpr int WIN_BYTES = (WIN_WORDS * 4 + 15) & ~15;
 constexpr int HDR_BYTES = 1024 + 16;      // staged input for a block header
 constexpr int LIT_ROOT = 10;
 constexpr int DIST_ROOT = 9;
-constexpr int FIX_PASSES = 3;             // extra head-decode passes behind lanes that did not re-synchronise
 constexpr int DCMP_INTERNAL_RETRY = 0x7f; // never leaves the library
 static_assert(SUB_WORDS % 2 == 1, "odd lane stride keeps the window reads conflict-free");
 static_assert(PT % 32 == 0 && PT <= 1024, "");
-static_assert(SPEC_CAP < 256 && LANE_BYTE_CAP < (1 << 18), "checkpoint fields");
+static_assert(SPEC_CAP < 256 && LANE_BYTE_CAP + 258 < (1 << 19), "checkpoint fields");
 static_assert(SPEC_CAP % 4 == 0 && HEAD_CAP % 4 == 0, "token slots are moved in batches of four");
-static_assert(NCKPT * PT * 4 <= SYM_SLOTS * 2, "checkpoints alias the symbol buffer");
+constexpr int MAX_CROSS = 6;              // sub-chunk boundaries one head decode may cross
+// Per-round metadata that is dead before phase D writes symbols; it overlays the symbol buffer.
+struct LaneDesc {          // what a lane replays in phase D, written by the lane that owns the head
+  uint16_t owner;          // lane whose head slots hold the tokens
+  uint8_t h0, h1;          // head tokens [h0, h1)
+  uint16_t out_head;       // bytes they produce
+  uint8_t spec_k;          // speculative tokens from spec_k on (if has_spec)
+  uint8_t flags;           // bit0 has_spec, bit1 terminal here (head ended: kind in bits 4..6)
+  uint16_t spec_skip;      // bytes the speculative pass produced before spec_k
+  uint16_t term_pos;       // terminal position in the OWNER's sub-chunk coordinates
+};
+struct RoundMeta {
+  uint32_t ckpt[NCKPT][PT];
+  uint16_t cross_nh[PT][MAX_CROSS];   // head pass: tokens / bytes produced before entering the j-th next sub-chunk
+  uint16_t cross_out[PT][MAX_CROSS];
+  uint16_t jump[2][PT];
+  uint8_t mark[PT];
+  LaneDesc desc[PT];
+};
+static_assert(sizeof(RoundMeta) <= SYM_SLOTS * 2, "round metadata overlays the symbol buffer");
 static_assert(RSYM + 16 + 256 <= 65536, "markers are 16-bit");
 static_assert(HDR_BYTES <= WIN_BYTES, "");
 
@@ -98,8 +116,8 @@ enum : int { X_NORMAL = 0, X_EOB = 1, X_CAP = 2, X_ERR = 3, X_NOSYNC = 4 };
 enum : int { NEXT_CONTINUE = 0, NEXT_HEADER = 1, NEXT_FINISH = 2, NEXT_RETRY = 3 };
 
 // token: [23] match flag; match: [22:8] distance-1, [7:0] length-3;  literal: [7:0] byte
-// checkpoint: [5:0] bit offset of the first token start inside the 64-bit window,
-//             [13:6] index of that token, [31:14] bytes emitted before it
+// checkpoint: [4:0] bit offset of the first token start inside the 32-bit window,
+//             [12:5] index of that token, [31:13] bytes emitted before it
 __device__ __forceinline__ bool tok_is_match(uint32_t t) { return (t >> 23) & 1u; }
 __device__ __forceinline__ void batch_put(uint4 &b, int k, uint32_t t) {
   if (k == 0) b.x = t;
@@ -135,7 +153,13 @@ struct ParSmem {
   // per-lane results of a round
   uint16_t exit_pos[PT];         // spec pass: bit offset (own sub-chunk coordinates) after the last token
   uint8_t exit_kind[PT];
-  int texit[PT];                 // head pass: entry point handed to the next lane (its coordinates), or ENTRY_NONE
+  int8_t last_ck[PT];            // spec pass: last checkpoint window written
+  uint8_t spec_ns[PT];           // spec pass: tokens produced
+  uint16_t spec_out[PT];         // spec pass: bytes produced
+  uint32_t m_owner[NWARP];       // lanes whose own head decode counts (not covered by an earlier lane's head)
+  int pass_owner;                // lane whose head ran past the end of the window (-1: none)
+  int pass_pos;                  // its exit (own sub-chunk coordinates)
+  int last_clean;
   uint32_t warp_c[NWARP];
   unsigned long long adl_s[NWARP];
   long long adl_b[NWARP];
@@ -474,7 +498,8 @@ inflate_parallel_kernel(int fmt, int64_t nstreams, const uint8_t *src_base, cons
   const int tid = threadIdx.x;
   const int lane = tid & 31;
   const int warp = tid >> 5;
-  uint32_t(*ckpt)[PT] = reinterpret_cast<uint32_t(*)[PT]>(S.sym);
+  RoundMeta &M = *reinterpret_cast<RoundMeta *>(S.sym);
+  uint32_t(*ckpt)[PT] = M.ckpt;
 
   if (tid == 0) {
     mbar_init(&S.mbar, 1);
@@ -614,7 +639,7 @@ inflate_parallel_kernel(int fmt, int64_t nstreams, const uint8_t *src_base, cons
           if (ns == SPEC_CAP || out_s > (uint32_t)(LANE_BYTE_CAP - 258)) { xkind = X_CAP; xpos = p; break; }
           int ck = p >> CKPT_SHIFT;
           if (ck != last_ck) {
-            ckpt[ck][tid] = (uint32_t)(p & 63) | ((uint32_t)ns << 6) | (out_s << 14);
+            ckpt[ck][tid] = (uint32_t)(p & 31) | ((uint32_t)ns << 5) | (out_s << 13);
             last_ck = ck;
           }
           uint32_t tok, no;
@@ -630,83 +655,158 @@ inflate_parallel_kernel(int fmt, int64_t nstreams, const uint8_t *src_base, cons
       }
       S.exit_pos[tid] = (uint16_t)xpos;
       S.exit_kind[tid] = (uint8_t)xkind;
-      if (tid == 0) { S.first_bad = PT; S.first_term = PT; S.first_over = PT; S.abort_round = 0; }
+      S.last_ck[tid] = (int8_t)last_ck;
+      S.spec_ns[tid] = (uint8_t)ns;
+      S.spec_out[tid] = (uint16_t)out_s;
+      if (tid == 0) { S.first_bad = PT; S.first_term = PT; S.first_over = PT; S.abort_round = 0; S.pass_owner = -1; S.last_clean = -1; }
       __syncthreads();
       // ---- B: re-synchronise with the true entry point handed over by the previous lane.
-      // Lane t first assumes that lane t-1 merged into its own speculative sequence (entry = that
-      // sequence's exit).  A lane that crosses its whole sub-chunk without merging ("no sync")
-      // hands over a different exit; the few lanes behind such a lane redo the step (FIX_PASSES
-      // times at most, then the round is cut there).
-      int nh = 0, kmerge = 0;
-      uint32_t out_valid = 0;
-      bool in_ok = false, term = false, merged = false;
-      int tkind = xkind, tpos = xpos; // exit of this lane's TRUE sequence
+      // Lane t assumes that lane t-1's true sequence ends in that lane's speculative sequence
+      // (entry = its exit) and decodes from there until the start of one of its tokens coincides
+      // with a checkpoint of the speculative sequence of the sub-chunk it is in — its own, or,
+      // when it crosses its whole sub-chunk without meeting it, a later lane's.  Lanes covered by
+      // such a long head are "absorbed": their own head is discarded; each replays the part of the
+      // covering head that starts in its sub-chunk, and the one in which that head merged adds its
+      // speculative tokens from the merge point on.
+      enum : int { H_BAD = 0, H_MERGE = 1, H_PASS = 2, H_TERM = 3 };
       const int ENTRY_NONE = -100000;
-      int entry = 0;                  // bit offset (own sub-chunk coordinates) the head decode starts from
-      if (tid > 0) entry = S.exit_kind[tid - 1] == X_NORMAL ? (int)S.exit_pos[tid - 1] - SUB_BITS : ENTRY_NONE;
-      bool dirty = true;
-      for (int pass = 0;; pass++) {
-        if (dirty) {
-          nh = 0; kmerge = 0; merged = false; out_valid = 0;
-          in_ok = lane_has_input && entry != ENTRY_NONE;
-          tkind = xkind; tpos = xpos;
-          uint32_t skipped = 0, out_h = 0;
-          if (in_ok) {
-            if (entry == 0 && ns > 0) {
-              merged = true;
-            } else {
-              LaneBits lb;
-              lb.init(lane_words, sh, entry);
-              uint4 tbuf = make_uint4(0, 0, 0, 0);
-              int seen_ck = -1;
-              for (;;) {
-                int p = lb.pos();
-                if (p >= SUB_BITS) { tkind = X_NOSYNC; tpos = p; break; }  // true tokens covered the whole sub-chunk
-                int ck = p >> CKPT_SHIFT;
-                if (ck != seen_ck) {
-                  seen_ck = ck;
-                  if (ck <= last_ck) { // the speculative pass left a checkpoint for this window
-                    uint32_t c = ckpt[ck][tid];
-                    if ((int)(c & 63u) == (p & 63)) { merged = true; kmerge = (int)((c >> 6) & 255u); skipped = c >> 14; break; }
-                  }
-                }
-                if (xkind == X_CAP && p == xpos) { merged = true; kmerge = ns; skipped = out_s; break; } // met the spec pass where its buffer filled up
-                if (nh == HEAD_CAP || out_h > (uint32_t)(LANE_BYTE_CAP - 258)) { tkind = X_CAP; tpos = p; break; }
-                uint32_t tok, no;
-                int r = decode_token(S, lb, lmask, dmask, &tok, &no);
-                if (r == T_EOB) { tkind = X_EOB; tpos = lb.pos(); break; }
-                if (r == T_ERR) { tkind = X_ERR; tpos = p; break; }
-                batch_put(tbuf, nh & 3, tok);
-                if ((nh & 3) == 3) tok_head[nh >> 2] = tbuf;
-                nh++;
-                out_h += no;
+      int nh = 0, mk = 0, hcat = H_BAD, hkind = X_NORMAL, hpos = 0, ncross = 0;
+      uint32_t out_h = 0, mskip = 0;
+      {
+        int entry = 0;
+        if (tid > 0) entry = S.exit_kind[tid - 1] == X_NORMAL ? (int)S.exit_pos[tid - 1] - SUB_BITS : ENTRY_NONE;
+        if (lane_has_input && entry != ENTRY_NONE) {
+          if (entry == 0 && ns > 0) {
+            hcat = H_MERGE; // the speculative pass started at the true position
+          } else {
+            LaneBits lb;
+            lb.init(lane_words, sh, entry);
+            uint4 tbuf = make_uint4(0, 0, 0, 0);
+            int u = tid, ubase = 0, lck = last_ck, seen_ck = -1, xk_u = xkind, xp_u = xpos;
+            for (;;) {
+              const int p = lb.pos();
+              if (p - ubase >= SUB_BITS) { // crossed into the next sub-chunk (rare)
+                if (ncross == MAX_CROSS) { hcat = H_TERM; hkind = X_CAP; hpos = p; break; }
+                M.cross_nh[tid][ncross] = (uint16_t)nh;
+                M.cross_out[tid][ncross] = (uint16_t)out_h;
+                ncross++;
+                u++;
+                ubase += SUB_BITS;
+                seen_ck = -1;
+                if (u >= PT) { hcat = H_PASS; hpos = p; break; } // past the window: the next round starts here
+                lck = S.last_ck[u];
+                xk_u = S.exit_kind[u];
+                xp_u = S.exit_pos[u];
               }
-              if (nh & 3) tok_head[nh >> 2] = tbuf;
+              const int pl = p - ubase;
+              const int ck = pl >> CKPT_SHIFT;
+              if (ck != seen_ck) {
+                seen_ck = ck;
+                if (ck <= lck) { // the speculative pass of lane u left a checkpoint for this window
+                  const uint32_t c = ckpt[ck][u];
+                  if ((int)(c & 31u) == (pl & 31)) { mk = (int)((c >> 5) & 255u); mskip = c >> 13; hcat = H_MERGE; break; }
+                }
+              }
+              if (xk_u == X_CAP && pl == xp_u) { // met that pass where its token buffer filled up
+                mk = S.spec_ns[u]; mskip = S.spec_out[u]; hcat = H_MERGE; break;
+              }
+              if (nh == HEAD_CAP || out_h > (uint32_t)(LANE_BYTE_CAP - 258)) { hcat = H_TERM; hkind = X_CAP; hpos = p; break; }
+              uint32_t tok, no;
+              const int r = decode_token(S, lb, lmask, dmask, &tok, &no);
+              if (r == T_EOB) { hcat = H_TERM; hkind = X_EOB; hpos = lb.pos(); break; }
+              if (r == T_ERR) { hcat = H_TERM; hkind = X_ERR; hpos = p; break; }
+              batch_put(tbuf, nh & 3, tok);
+              if ((nh & 3) == 3) tok_head[nh >> 2] = tbuf;
+              nh++;
+              out_h += no;
             }
-            out_valid = out_h + (merged ? out_s - skipped : 0u);
-            if (merged) { tkind = xkind; tpos = xpos; }
+            if (nh & 3) tok_head[nh >> 2] = tbuf;
           }
-          // a lane that ends normally (merged or not) hands its exit to the next lane
-          const bool normal_exit = in_ok && (tkind == X_NORMAL || tkind == X_NOSYNC);
-          term = in_ok && !normal_exit;
-          S.texit[tid] = normal_exit ? tpos - SUB_BITS : ENTRY_NONE;
-          STAT(if (in_ok && tid > 0) { if (merged) { g_stats.hist_nh[nh < 47 ? nh : 47]++; } else if (tkind == X_NOSYNC) g_stats.nosync_lanes++; })
         }
-        __syncthreads();
-        const int want = tid == 0 ? 0 : S.texit[tid - 1];
-        dirty = lane_has_input && want != entry;
-        if (pass == FIX_PASSES) {
-          if (dirty) in_ok = false; // still inconsistent: the round is cut at this lane
-          break;
-        }
-        if (!__syncthreads_or(dirty)) break;
-        STAT(if (tid == 0) g_stats.fix_passes++;)
-        if (dirty) entry = want;
+        STAT(if (hcat != H_BAD && tid > 0) { if (hcat == H_MERGE && ncross == 0) g_stats.hist_nh[nh < 47 ? nh : 47]++; else if (hcat != H_TERM) g_stats.nosync_lanes++; })
+        // the lane after the ones this head covers is the next one whose own head counts
+        int last = tid + ncross;           // lane in which the head ended
+        if (last > PT - 1) last = PT - 1;  // (H_PASS)
+        M.jump[0][tid] = (uint16_t)(last + 1);
+        M.mark[tid] = tid == 0 ? 1 : 0;
       }
-      // ---- C: cut the round at the first lane that cannot be chained, scan output sizes
+      __syncthreads();
+      // ---- C: find the lanes whose head counts (the orbit of lane 0 under `jump`, by pointer doubling),
+      // describe every lane's part, cut the round at the first lane that ends it, scan output sizes
+      {
+        int cur = 0;
+#pragma unroll 1
+        for (int span = 1; span < PT; span <<= 1) {
+          const int j = M.jump[cur][tid];
+          if (j < PT) {
+            if (M.mark[tid]) M.mark[j] = 1;
+            M.jump[cur ^ 1][tid] = M.jump[cur][j];
+          } else {
+            M.jump[cur ^ 1][tid] = (uint16_t)PT;
+          }
+          cur ^= 1;
+          __syncthreads();
+        }
+      }
+      const bool owner = M.mark[tid] != 0;
+      {
+        const uint32_t ow = __ballot_sync(0xffffffffu, owner);
+        if (lane == 0) S.m_owner[warp] = ow;
+      }
+      if (owner) {
+        // describe this lane's part and the parts of the lanes its head covers
+        const bool has_head_end = hcat == H_TERM;
+        for (int j = 0; j <= ncross; j++) {
+          const int y = tid + j;
+          if (y >= PT) break; // H_PASS: the last crossing left the window
+          LaneDesc d;
+          d.owner = (uint16_t)tid;
+          d.h0 = (uint8_t)(j == 0 ? 0 : M.cross_nh[tid][j - 1]);
+          d.h1 = (uint8_t)(j < ncross ? M.cross_nh[tid][j] : nh);
+          const uint32_t o0 = j == 0 ? 0u : M.cross_out[tid][j - 1], o1 = j < ncross ? M.cross_out[tid][j] : out_h;
+          d.out_head = (uint16_t)(o1 - o0);
+          d.spec_k = (uint8_t)mk;
+          d.spec_skip = (uint16_t)mskip;
+          d.term_pos = (uint16_t)hpos;
+          const bool lastlane = j == ncross;
+          d.flags = (uint8_t)((lastlane && hcat == H_MERGE ? 1 : 0) | (lastlane && has_head_end ? 2 | (hkind << 4) : 0));
+          M.desc[y] = d;
+        }
+        if (hcat == H_PASS) { S.pass_owner = tid; S.pass_pos = hpos; }
+      }
+      __syncthreads();
+      // every lane's final contribution: head tokens [d_h0, d_h0 + d_nh) of lane d_owner, then (d_spec) its own
+      // speculative tokens from d_k on
+      int d_owner = tid, d_h0 = 0, d_nh = 0, d_k = 0, tkind = X_NORMAL;
+      int64_t t_next = 0; // where the stream continues if this lane closes the round
+      bool d_spec = false, in_ok = true, term = false, clean = false;
+      uint32_t out_valid = 0;
+      {
+        in_ok = owner ? hcat != H_BAD : true;
+        if (in_ok) {
+          const LaneDesc d = M.desc[tid];
+          d_owner = d.owner;
+          d_h0 = d.h0;
+          d_nh = (int)d.h1 - (int)d.h0;
+          out_valid = d.out_head;
+          if (d.flags & 1) { // the true sequence leaves this sub-chunk the way the speculative one does
+            d_spec = true;
+            d_k = d.spec_k;
+            out_valid += out_s - d.spec_skip;
+            clean = true;
+            tkind = xkind;
+            term = xkind != X_NORMAL;
+            t_next = base_bit + (int64_t)SUB_BITS * tid + xpos;
+          } else if (d.flags & 2) {
+            term = true;
+            tkind = (d.flags >> 4) & 7;
+            t_next = base_bit + (int64_t)SUB_BITS * d_owner + d.term_pos;
+          }
+        }
+      }
       if (!in_ok) atomicMin(&S.first_bad, tid);
       if (term) atomicMin(&S.first_term, tid);
-      __syncthreads();   // (also: every lane is done with its checkpoints; S.sym may be reused)
+      __syncthreads();
       const int first_bad = S.first_bad, first_term = S.first_term;
       int n_valid = first_term < first_bad ? first_term + 1 : first_bad;
       uint32_t mine = tid < n_valid ? out_valid : 0u;
@@ -724,9 +824,12 @@ inflate_parallel_kernel(int fmt, int64_t nstreams, const uint8_t *src_base, cons
       if (tid < n_valid && incl > (uint32_t)RSYM) atomicMin(&S.first_over, tid);
       __syncthreads();
       const bool cut_by_budget = S.first_over < n_valid;
-      if (cut_by_budget) n_valid = S.first_over;
+      // a round can only be cut where the position of the true sequence is known: behind a lane that
+      // ends in its own speculative sequence
+      if (cut_by_budget && clean && tid < S.first_over) atomicMax(&S.last_clean, tid);
+      __syncthreads();
+      if (cut_by_budget) n_valid = S.last_clean + 1;
       const uint32_t out0 = S.out_pos;
-      if (tid < n_valid) mine = out_valid; else mine = 0;
       const uint32_t my_off = out0 + incl - out_valid; // only meaningful for tid < n_valid
       if (n_valid == 0) {
         if (tid == 0) S.next = NEXT_RETRY; // truncated input: the general kernel reports what the reference does
@@ -734,18 +837,21 @@ inflate_parallel_kernel(int fmt, int64_t nstreams, const uint8_t *src_base, cons
         // this lane closes the round
         const uint32_t round_out = incl; // inclusive sum up to the last valid lane
         S.round_out = round_out;
-        int nx;
-        const int64_t nb = base_bit + (int64_t)SUB_BITS * tid + tpos;
+        int nx = NEXT_CONTINUE;
+        int64_t nb = t_next;
         if (!cut_by_budget && first_term < first_bad) {
           // closed by this lane's own exit
           if (tkind == X_EOB) nx = S.last_block ? NEXT_FINISH : NEXT_HEADER;
           else if (tkind == X_ERR) nx = NEXT_RETRY;
-          else nx = NEXT_CONTINUE; // X_CAP: resume right after the last token
-        } else {
-          // the next lane could not be chained (or did not fit the budget): it opens the next round
-          // at this lane's (normal) exit
-          nx = NEXT_CONTINUE;
+          // X_CAP: resume right after the last token
+        } else if (!clean) {
+          // every lane was used and the last ones are covered by a head that ran past the window
+          const int x = S.pass_owner;
+          if (x < 0) nx = NEXT_RETRY; // cannot happen
+          else nb = base_bit + (int64_t)SUB_BITS * x + S.pass_pos;
         }
+        // otherwise the next lane could not be chained (or did not fit the budget): it opens the next
+        // round at this lane's (normal) exit
         if ((int64_t)out0 + round_out > S.dst_cap) nx = NEXT_RETRY; // Unexpected_end_of_output: exact point needed
         S.base_bit = nb;
         S.next = nx;
@@ -774,9 +880,10 @@ inflate_parallel_kernel(int fmt, int64_t nstreams, const uint8_t *src_base, cons
         //   inside this round (any lane, this one included): markers 256 + source index, no load at all
         //   entirely in earlier rounds: bytes of the history ring
         //   straddling the start of the round, or overlapping itself inside the group: per symbol
-        const int total_tok = tid < n_valid ? nh + (merged ? ns - kmerge : 0) : 0;
-        const int delta = HEAD_CAP + kmerge - nh; // token index -> slot for the speculative part
-        STAT(if (tid < n_valid) { g_stats.head_tokens += nh; g_stats.used_tokens += total_tok; } long iters = 0;)
+        const int total_tok = tid < n_valid ? d_nh + (d_spec ? ns - d_k : 0) : 0;
+        const int delta = HEAD_CAP + d_k - d_nh; // token index -> slot for the speculative part
+        const uint4 *head_lane = reinterpret_cast<const uint4 *>(tok_scratch + ((size_t)blockIdx.x * PT + d_owner) * TOK_SLOTS);
+        STAT(if (tid < n_valid) { g_stats.head_tokens += d_nh; g_stats.used_tokens += total_tok; } long iters = 0;)
         const uint32_t *ring32 = reinterpret_cast<const uint32_t *>(S.ring);
         int ti = 0;
         int32_t i = (int32_t)(my_off - out0 + bias); // next symbol to write
@@ -786,7 +893,7 @@ inflate_parallel_kernel(int fmt, int64_t nstreams, const uint8_t *src_base, cons
         uint4 cur = make_uint4(0, 0, 0, 0), nxt = make_uint4(0, 0, 0, 0);
         int cur_b = -1;
         bool active = total_tok > 0;
-        if (active) nxt = tok_lane[(nh > 0 ? 0 : delta) >> 2];
+        if (active) nxt = d_nh > 0 ? head_lane[d_h0 >> 2] : tok_lane[delta >> 2];
         while (__any_sync(0xffffffffu, active)) {
           STAT(if (active) iters++;)
           uint32_t n = 0;               // symbols emitted by this step
@@ -797,13 +904,13 @@ inflate_parallel_kernel(int fmt, int64_t nstreams, const uint8_t *src_base, cons
               if (ti == total_tok) {
                 active = false;
               } else {
-                const int slot = ti < nh ? ti : ti + delta;
+                const int slot = ti < d_nh ? ti + d_h0 : ti + delta;
                 if ((slot >> 2) != cur_b) {
                   cur = nxt;
                   cur_b = slot >> 2;
                   int t2 = ti + 4 - (slot & 3);          // first token of the batch after this one
-                  if (ti < nh && t2 > nh) t2 = nh;
-                  if (t2 < total_tok) nxt = tok_lane[(t2 < nh ? t2 : t2 + delta) >> 2];
+                  if (ti < d_nh && t2 > d_nh) t2 = d_nh;
+                  if (t2 < total_tok) nxt = t2 < d_nh ? head_lane[(t2 + d_h0) >> 2] : tok_lane[(t2 + delta) >> 2];
                 }
                 const uint32_t t = batch_get(cur, slot & 3);
                 ti++;
