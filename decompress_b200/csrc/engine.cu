@@ -47,6 +47,23 @@ struct dcmp_engine {
   int par_ctas = 0;                  // persistent CTAs of the sub-chunk-parallel kernel (2 per SM)
   uint8_t *d_scratch = nullptr;      // [work counter (256 B) | token scratch of every CTA]
   int mode = 0;                      // 0 = parallel + general, 1 = general kernel only (DCMP_INFLATE_MODE=serial)
+  // host-facing calls: three-stage pipeline (H2D | kernels | D2H) over slices of the batch
+  static const int MAX_SLICES = 8;
+  cudaStream_t s_kernel = nullptr, s_out = nullptr;
+  cudaEvent_t ev_in[MAX_SLICES] = {}, ev_k[MAX_SLICES] = {}, ev_meta[MAX_SLICES] = {};
+  bool pipeline_ready = false;
+  int ensure_pipeline() {
+    if (pipeline_ready) return DCMP_API_OK;
+    CU(cudaStreamCreateWithFlags(&s_kernel, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking));
+    for (int i = 0; i < MAX_SLICES; i++) {
+      CU(cudaEventCreateWithFlags(&ev_in[i], cudaEventDisableTiming));
+      CU(cudaEventCreateWithFlags(&ev_k[i], cudaEventDisableTiming));
+      CU(cudaEventCreateWithFlags(&ev_meta[i], cudaEventDisableTiming));
+    }
+    pipeline_ready = true;
+    return DCMP_API_OK;
+  }
   int reserve(size_t bytes) {
     if (bytes <= d_cap) return DCMP_API_OK;
     if (d_buf) { CU(cudaFree(d_buf)); d_buf = nullptr; d_cap = 0; }
@@ -124,6 +141,11 @@ void dcmp_engine_destroy(dcmp_engine *e) {
   cudaSetDevice(e->device);
   if (e->d_buf) cudaFree(e->d_buf);
   if (e->d_scratch) cudaFree(e->d_scratch);
+  if (e->pipeline_ready) {
+    for (int i = 0; i < dcmp_engine::MAX_SLICES; i++) { cudaEventDestroy(e->ev_in[i]); cudaEventDestroy(e->ev_k[i]); cudaEventDestroy(e->ev_meta[i]); }
+    cudaStreamDestroy(e->s_kernel);
+    cudaStreamDestroy(e->s_out);
+  }
   if (e->stream) cudaStreamDestroy(e->stream);
   delete e;
 }
@@ -174,11 +196,12 @@ int dcmp_inflate_batch(dcmp_engine *e, int fmt, int64_t n, const uint8_t *src_ba
     return DCMP_API_INVALID_ARGUMENT;
   CU(cudaSetDevice(e->device));
   // Spans of the host slabs actually referenced.
-  int64_t s_lo = INT64_MAX, s_hi = 0, d_lo = INT64_MAX, d_hi = 0;
+  int64_t s_lo = INT64_MAX, s_hi = 0, d_lo = INT64_MAX, d_hi = 0, work = 0;
   for (int64_t k = 0; k < n; k++) {
     if (src_len[k] < 0 || dst_cap[k] < 0 || src_off[k] < 0 || dst_off[k] < 0) return DCMP_API_INVALID_ARGUMENT;
     s_lo = std::min(s_lo, src_off[k]); s_hi = std::max(s_hi, src_off[k] + src_len[k]);
     d_lo = std::min(d_lo, dst_off[k]); d_hi = std::max(d_hi, dst_off[k] + dst_cap[k]);
+    work += src_len[k] + dst_cap[k];
   }
   size_t s_bytes = (size_t)(s_hi - s_lo), d_bytes = (size_t)(d_hi - d_lo);
   if ((s_bytes && !src_base) || (d_bytes && !dst_base)) return DCMP_API_INVALID_ARGUMENT;
@@ -187,6 +210,8 @@ int dcmp_inflate_batch(dcmp_engine *e, int fmt, int64_t n, const uint8_t *src_ba
   size_t o_tab = align_up(o_dst + d_bytes + 16, 256);
   size_t tab_bytes = (size_t)n * (8 * 6 + 4);
   int rc = e->reserve(o_tab + tab_bytes + 256);
+  if (rc != DCMP_API_OK) return rc;
+  rc = e->ensure_pipeline();
   if (rc != DCMP_API_OK) return rc;
   // Offset tables rebased to the spans, packed into one upload.
   std::vector<int64_t> tab((size_t)n * 4);
@@ -200,34 +225,74 @@ int dcmp_inflate_batch(dcmp_engine *e, int fmt, int64_t n, const uint8_t *src_ba
   int64_t *d_tab = (int64_t *)(e->d_buf + o_tab);
   int64_t *d_cons = d_tab + 4 * n, *d_prod = d_tab + 5 * n;
   int32_t *d_stat = (int32_t *)(d_tab + 6 * n);
-  cudaStream_t st = e->stream;
-  CU(cudaMemcpyAsync(d_tab, tab.data(), (size_t)n * 32, cudaMemcpyHostToDevice, st));
-  if (s_bytes) CU(cudaMemcpyAsync(d_src, src_base + s_lo, s_bytes, cudaMemcpyHostToDevice, st));
-  rc = dcmp_inflate_batch_device(e, fmt, n, d_src, d_tab, d_tab + n, d_dst, d_tab + 2 * n, d_tab + 3 * n, d_cons,
-                                 d_prod, d_stat, (void *)st);
-  if (rc != DCMP_API_OK) return rc;
-  CU(cudaMemcpyAsync(consumed, d_cons, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
-  CU(cudaMemcpyAsync(produced, d_prod, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
-  CU(cudaMemcpyAsync(status, d_stat, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
-  CU(cudaStreamSynchronize(st));
+  // The batch moves through three stages on three CUDA streams — host->device copy of the compressed
+  // bytes, the kernels, device->host copy of the inflated bytes — in slices of consecutive streams, so
+  // that PCIe in both directions and the SMs work at the same time.  A slice's input is the byte span
+  // its streams reference; if the caller's layout is not monotonic the batch runs as one slice.
+  int nslice = (int)std::min<int64_t>(dcmp_engine::MAX_SLICES, std::max<int64_t>(1, work / (48ll << 20)));
+  if (n < 4 * nslice) nslice = 1;
+  bool monotonic = true;
+  for (int64_t k = 1; k < n && monotonic; k++)
+    monotonic = src_off[k] >= src_off[k - 1] + src_len[k - 1] && dst_off[k] >= dst_off[k - 1] + dst_cap[k - 1];
+  if (!monotonic) nslice = 1;
+  std::vector<int64_t> cut(nslice + 1, 0);
+  {
+    int64_t acc = 0;
+    int c = 1;
+    for (int64_t k = 0; k < n && c < nslice; k++) {
+      acc += src_len[k] + dst_cap[k];
+      if (acc >= work * c / nslice) cut[c++] = k + 1;
+    }
+    while (c < nslice) cut[c++] = n;
+    cut[nslice] = n;
+  }
+  cudaStream_t s_in = e->stream, s_k = e->s_kernel, s_out = e->s_out;
+  CU(cudaMemcpyAsync(d_tab, tab.data(), (size_t)n * 32, cudaMemcpyHostToDevice, s_in));
+  for (int c = 0; c < nslice; c++) {
+    int64_t k0 = cut[c], k1 = cut[c + 1];
+    if (k1 > k0) {
+      int64_t lo = nslice == 1 ? s_lo : src_off[k0], hi = nslice == 1 ? s_hi : src_off[k1 - 1] + src_len[k1 - 1];
+      if (hi > lo) CU(cudaMemcpyAsync(d_src + (lo - s_lo), src_base + lo, (size_t)(hi - lo), cudaMemcpyHostToDevice, s_in));
+    }
+    CU(cudaEventRecord(e->ev_in[c], s_in));
+    CU(cudaStreamWaitEvent(s_k, e->ev_in[c], 0));
+    if (k1 > k0) {
+      rc = dcmp_inflate_batch_device(e, fmt, k1 - k0, d_src, d_tab + k0, d_tab + n + k0, d_dst, d_tab + 2 * n + k0,
+                                     d_tab + 3 * n + k0, d_cons + k0, d_prod + k0, d_stat + k0, (void *)s_k);
+      if (rc != DCMP_API_OK) return rc;
+    }
+    CU(cudaEventRecord(e->ev_k[c], s_k));
+  }
   // Copy back exactly what each stream produced and nothing else (the reference never
   // touches dst beyond o_pos).  Adjacent, completely filled windows are merged into one
-  // transfer, so the common layout (C2: dense slab of full windows) is a single copy.
-  int64_t run_lo = -1, run_hi = -1;
-  for (int64_t k = 0; k <= n; k++) {
-    int64_t lo = 0, hi = 0;
-    if (k < n) {
-      int64_t p = std::min(std::max<int64_t>(produced[k], 0), dst_cap[k]);
-      lo = dst_off[k];
-      hi = lo + p;
-      if (hi == lo) continue;
+  // transfer, so the common layout (C2: dense slab of full windows) is one copy per slice.
+  for (int c = 0; c < nslice; c++) {
+    int64_t k0 = cut[c], k1 = cut[c + 1], m = k1 - k0;
+    if (m <= 0) continue;
+    CU(cudaStreamWaitEvent(s_out, e->ev_k[c], 0));
+    CU(cudaMemcpyAsync(consumed + k0, d_cons + k0, (size_t)m * 8, cudaMemcpyDeviceToHost, s_out));
+    CU(cudaMemcpyAsync(produced + k0, d_prod + k0, (size_t)m * 8, cudaMemcpyDeviceToHost, s_out));
+    CU(cudaMemcpyAsync(status + k0, d_stat + k0, (size_t)m * 4, cudaMemcpyDeviceToHost, s_out));
+    CU(cudaEventRecord(e->ev_meta[c], s_out));
+    CU(cudaEventSynchronize(e->ev_meta[c]));
+    int64_t run_lo = -1, run_hi = -1;
+    for (int64_t k = k0; k <= k1; k++) {
+      int64_t lo = 0, hi = 0;
+      if (k < k1) {
+        int64_t p = std::min(std::max<int64_t>(produced[k], 0), dst_cap[k]);
+        lo = dst_off[k];
+        hi = lo + p;
+        if (hi == lo) continue;
+      }
+      if (k < k1 && run_hi == lo) { run_hi = hi; continue; }
+      if (run_hi > run_lo)
+        CU(cudaMemcpyAsync(dst_base + run_lo, d_dst + (run_lo - d_lo), (size_t)(run_hi - run_lo), cudaMemcpyDeviceToHost, s_out));
+      run_lo = lo; run_hi = hi;
     }
-    if (k < n && run_hi == lo) { run_hi = hi; continue; }
-    if (run_hi > run_lo)
-      CU(cudaMemcpyAsync(dst_base + run_lo, d_dst + (run_lo - d_lo), (size_t)(run_hi - run_lo), cudaMemcpyDeviceToHost, st));
-    run_lo = lo; run_hi = hi;
   }
-  CU(cudaStreamSynchronize(st));
+  CU(cudaStreamSynchronize(s_out));
+  CU(cudaStreamSynchronize(s_k));
+  CU(cudaStreamSynchronize(s_in));
   return DCMP_API_OK;
 }
 

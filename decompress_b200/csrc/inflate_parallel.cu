@@ -47,10 +47,10 @@
 namespace dcmp {
 
 #ifndef DCMP_PT
-#define DCMP_PT 256
+#define DCMP_PT 352
 #endif
 #ifndef DCMP_SUB_WORDS
-#define DCMP_SUB_WORDS 9
+#define DCMP_SUB_WORDS 7
 #endif
 
 constexpr int PT = DCMP_PT;               // threads (= lanes = sub-chunks per round)
@@ -896,71 +896,60 @@ inflate_parallel_kernel(int fmt, int64_t nstreams, const uint8_t *src_base, cons
         if (active) nxt = d_nh > 0 ? head_lane[d_h0 >> 2] : tok_lane[delta >> 2];
         while (__any_sync(0xffffffffu, active)) {
           STAT(if (active) iters++;)
-          uint32_t n = 0;               // symbols emitted by this step
-          uint32_t p0 = 0, p1 = 0, p2 = 0, p3 = 0; // up to eight symbols, two per word
-          bool slow = false;
-          if (active) {
-            if (rem == 0) {
-              if (ti == total_tok) {
-                active = false;
-              } else {
-                const int slot = ti < d_nh ? ti + d_h0 : ti + delta;
-                if ((slot >> 2) != cur_b) {
-                  cur = nxt;
-                  cur_b = slot >> 2;
-                  int t2 = ti + 4 - (slot & 3);          // first token of the batch after this one
-                  if (ti < d_nh && t2 > d_nh) t2 = d_nh;
-                  if (t2 < total_tok) nxt = t2 < d_nh ? head_lane[(t2 + d_h0) >> 2] : tok_lane[(t2 + delta) >> 2];
-                }
-                const uint32_t t = batch_get(cur, slot & 3);
-                ti++;
-                if (!tok_is_match(t)) {
-                  p0 = t & 0xffu;
-                  n = 1;
-                } else {
-                  dist = ((t >> 8) & 0x7fffu) + 1u;
-                  rem = (t & 0xffu) + 3u;
-                  s = i - (int32_t)dist;
-                  if (dist > out0 + (uint32_t)(i - (int32_t)bias)) { // Invalid distance (de.ml:1700): the general kernel reports it
-                    S.abort_round = 1;
-                    active = false;
-                    rem = 0;
-                  }
-                }
-              }
+          // -- next token, for the lanes that finished the previous one
+          bool fetch = active && rem == 0;
+          if (fetch && ti == total_tok) { active = false; fetch = false; }
+          uint32_t t = 0;
+          if (fetch) {
+            const int slot = ti < d_nh ? ti + d_h0 : ti + delta;
+            if ((slot >> 2) != cur_b) {
+              cur = nxt;
+              cur_b = slot >> 2;
+              int t2 = ti + 4 - (slot & 3);          // first token of the batch after this one
+              if (ti < d_nh && t2 > d_nh) t2 = d_nh;
+              if (t2 < total_tok) nxt = t2 < d_nh ? head_lane[(t2 + d_h0) >> 2] : tok_lane[(t2 + delta) >> 2];
             }
-            if (rem > 0) {
-              n = rem < 8u ? rem : 8u;
-              if (s >= (int32_t)bias) {
-                // source inside this round (another lane's output or this lane's own): markers
-                if (dist >= n) {
-                  p0 = (256u + (uint32_t)s) * 0x00010001u + 0x00010000u;
-                  p1 = p0 + 0x00020002u;
-                  p2 = p0 + 0x00040004u;
-                  p3 = p0 + 0x00060006u;
-                  STAT(g_stats.markers += n;)
-                } else {
-                  slow = true; // the copy overlaps itself inside this group: point at the first period
-                }
-              } else if (s + (int32_t)n <= (int32_t)bias) {
-                // source entirely in earlier rounds: bytes of the history ring
-                const uint32_t r = g0_low + (uint32_t)s; // ring byte address (mod HIST) of the first source byte
-                const uint32_t wi0 = r >> 2;
-                const uint32_t w0 = ring32[wi0 & (HIST / 4 - 1)], w1 = ring32[(wi0 + 1u) & (HIST / 4 - 1)],
-                               w2 = ring32[(wi0 + 2u) & (HIST / 4 - 1)];
-                const uint32_t sh8 = 8u * (r & 3u);
-                const uint32_t a = __funnelshift_r(w0, w1, sh8), b = __funnelshift_r(w1, w2, sh8);
-                p0 = __byte_perm(a, 0u, 0x4140);
-                p1 = __byte_perm(a, 0u, 0x4342);
-                p2 = __byte_perm(b, 0u, 0x4140);
-                p3 = __byte_perm(b, 0u, 0x4342);
-                STAT(g_stats.hist_bytes += n;)
-              } else {
-                slow = true; // straddles the start of the round
-              }
+            t = batch_get(cur, slot & 3);
+            ti++;
+          }
+          const bool new_match = fetch && tok_is_match(t);
+          if (new_match) {
+            dist = ((t >> 8) & 0x7fffu) + 1u;
+            rem = (t & 0xffu) + 3u;
+            s = i - (int32_t)dist;
+            if (dist > out0 + (uint32_t)(i - (int32_t)bias)) { // Invalid distance (de.ml:1700): the general kernel reports it
+              S.abort_round = 1;
+              active = false;
+              rem = 0;
             }
           }
+          // -- this step's symbols (branch-free for the three common cases)
+          const bool lit = fetch && !new_match;
+          const uint32_t n = lit ? 1u : (rem < 8u ? rem : 8u);  // 0 for idle lanes
+          const bool in_round = s >= (int32_t)bias;
+          const bool in_hist = s + (int32_t)n <= (int32_t)bias;
+          const bool slow = rem > 0u && (in_round ? dist < n : !in_hist);
+          // markers: source inside this round (another lane's output or this lane's own)
+          const uint32_t m0 = (256u + (uint32_t)s) * 0x00010001u + 0x00010000u;
+          // history: source entirely in earlier rounds (addresses are masked: the loads are always legal)
+          const uint32_t r = g0_low + (uint32_t)s; // ring byte address (mod HIST) of the first source byte
+          const uint32_t wi0 = r >> 2;
+          uint32_t w0 = 0, w1 = 0, w2 = 0;
+          if (in_hist && rem > 0u) {
+            w0 = ring32[wi0 & (HIST / 4 - 1)];
+            w1 = ring32[(wi0 + 1u) & (HIST / 4 - 1)];
+            w2 = ring32[(wi0 + 2u) & (HIST / 4 - 1)];
+          }
+          const uint32_t sh8 = 8u * (r & 3u);
+          const uint32_t ha = __funnelshift_r(w0, w1, sh8), hb = __funnelshift_r(w1, w2, sh8);
+          uint32_t p0 = in_round ? m0 : __byte_perm(ha, 0u, 0x4140);
+          const uint32_t p1 = in_round ? m0 + 0x00020002u : __byte_perm(ha, 0u, 0x4342);
+          const uint32_t p2 = in_round ? m0 + 0x00040004u : __byte_perm(hb, 0u, 0x4140);
+          const uint32_t p3 = in_round ? m0 + 0x00060006u : __byte_perm(hb, 0u, 0x4342);
+          if (lit) p0 = t & 0xffu;
+          STAT(if (!slow && rem > 0) { if (in_round) g_stats.markers += n; else g_stats.hist_bytes += n; })
           if (slow) {
+            // straddles the start of the round, or overlaps itself inside the group (point at the first period)
             for (uint32_t k = 0; k < n; k++) {
               const int32_t sk = s + (int32_t)(dist < n ? k % dist : k);
               uint32_t v;
@@ -979,7 +968,7 @@ inflate_parallel_kernel(int fmt, int64_t nstreams, const uint8_t *src_base, cons
             if (n > 7u) S.sym[i + 7] = (uint16_t)(p3 >> 16);
           }
           i += (int32_t)n;
-          if (rem > 0) { s += (int32_t)n; rem -= n; }
+          if (rem > 0u) { s += (int32_t)n; rem -= n; }
         }
         STAT(g_stats.d_iters += iters; if (iters > g_stats.d_lane_max_iters) g_stats.d_lane_max_iters = iters;)
       }
