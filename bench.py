@@ -49,6 +49,19 @@ def load_peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def load_traffic(streams):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel, from the committed
+    `ncu --set full` summary (profiles/); only valid for the workload size it was captured on."""
+    p = os.path.join(ROOT, "profiles", "inflate_parallel_ncu_summary.json")
+    try:
+        d = json.load(open(p))
+        if int(d.get("streams", -1)) == int(streams):
+            return float(d["dram_bytes_read"]) + float(d["dram_bytes_write"])
+    except Exception:
+        pass
+    return None
+
+
 def make_workload(n, seed0):
     """Generate (or load from a /tmp cache) n C2 streams; returns packed numpy slabs + plaintext digest."""
     cache = os.path.join(tempfile.gettempdir(), "dcmp_c2_%d_%d.npz" % (n, seed0))
@@ -71,15 +84,55 @@ def make_workload(n, seed0):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """SM clock / throttle reasons sampled DURING the timed region: NVML polled every 2 ms from a
+    thread (the timed region is tens of milliseconds, shorter than one `nvidia-smi -lms` period);
+    falls back to the recipe's nvidia-smi line when pynvml is missing."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu):
-        self.gpu, self.rows, self.proc = gpu, [], None
+        self.gpu, self.rows, self.proc, self.stop_flag, self.thread = gpu, [], None, False, None
+        self.sm, self.reasons, self.max_sm, self.power = [], set(), None, []
+
+    def _nvml_loop(self):
+        import pynvml as N
+        N.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        idx = int(vis.split(",")[self.gpu]) if vis and vis.split(",")[self.gpu].isdigit() else self.gpu
+        h = N.nvmlDeviceGetHandleByIndex(idx)
+        self.max_sm = float(N.nvmlDeviceGetMaxClockInfo(h, N.NVML_CLOCK_SM))
+        bits = {"hw_slowdown": N.nvmlClocksEventReasonHwSlowdown, "hw_thermal_slowdown": N.nvmlClocksEventReasonHwThermalSlowdown,
+                "sw_thermal_slowdown": N.nvmlClocksEventReasonSwThermalSlowdown, "sw_power_cap": N.nvmlClocksEventReasonSwPowerCap}
+        get_reasons = getattr(N, "nvmlDeviceGetCurrentClocksEventReasons", None) or N.nvmlDeviceGetCurrentClocksThrottleReasons
+        self.ready = True
+        while not self.stop_flag:
+            if self.armed:
+                self.sm.append(float(N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM)))
+                r = get_reasons(h)
+                for nm, b in bits.items():
+                    if r & b:
+                        self.reasons.add(nm)
+                try:
+                    self.power.append(N.nvmlDeviceGetPowerUsage(h) / 1000.0)
+                except Exception:
+                    pass
+            time.sleep(0.002)
 
     def start(self):
+        self.ready, self.armed = False, False
+        try:
+            import pynvml  # noqa: F401
+            self.thread = threading.Thread(target=self._nvml_loop, daemon=True)
+            self.thread.start()
+            t0 = time.time()
+            while not self.ready and time.time() - t0 < 5 and self.thread.is_alive():
+                time.sleep(0.005)
+            if self.ready:
+                return
+        except Exception:
+            pass
+        self.thread = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
                                           "--format=csv,noheader,nounits", "-lms", "50"],
@@ -88,11 +141,22 @@ class ClockSampler:
         except OSError:
             self.proc = None
 
+    def arm(self):
+        """Called right before the timed region starts."""
+        self.armed = True
+
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append([x.strip() for x in line.split(",")])
 
     def stop(self):
+        self.armed = False
+        self.stop_flag = True
+        if self.thread is not None:
+            self.thread.join(timeout=1)
+            return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.max_sm,
+                    "reasons": sorted(self.reasons), "samples": len(self.sm),
+                    "power_w_max": round(max(self.power), 1) if self.power else None, "source": "nvml, 2 ms poll"}
         if self.proc:
             self.proc.terminate()
             try:
@@ -109,7 +173,7 @@ class ClockSampler:
                     if v.lower().startswith("active"):
                         reasons.add(nm)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi -lms 50"}
 
 
 def cpu_baseline(src, so, sl, do, dc, budget_s=12.0):
@@ -224,6 +288,7 @@ def main():
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
+    sampler.arm()
     l0 = eng.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
@@ -299,8 +364,10 @@ def main():
                        "parallelism": "streams sharded across GPUs, no data-path collective",
                        "l2": "working set %d MiB per step > 126 MB L2 (no flush needed)" % ((total_src + total_out) >> 20)},
             "roofline": {"bound": "hbm", "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
-                         "frac": round(achieved / peak, 4), "traffic": None,
-                         "kernel": "inflate (compressed bytes read once + inflated bytes written once per launch)",
+                         "frac": round(achieved / peak, 4), "traffic": load_traffic(n),
+                         "algorithmic_bytes_per_launch": int(total_src + total_out),
+                         "kernel": "dcmp::inflate_parallel_kernel (compressed bytes read once + inflated bytes written "
+                                   "once per launch; the general kernel that follows it finds no stream to redo)",
                          "peak_source": peak_src},
             "e2e": {"value": round(job_out / (e2e_s / e2e_steps) / 1e9, 3), "unit": "GB/s",
                     "h2d_bytes_per_step": int(total_src + 4 * 8 * n), "d2h_bytes_per_step": int(total_out + 20 * n),

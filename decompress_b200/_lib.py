@@ -45,6 +45,11 @@ _SIGNATURES = {
                                       C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "dcmp_zl_inf_ns_inflate": (C.c_int, [C.c_void_p, p_u8, C.c_int64, p_u8, C.c_int64,
                                          C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "dcmp_lzo_uncompress_batch": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, p_u8, p_i64, p_i64, p_u8, p_i64, p_i64,
+                                            p_i64, p_i64, p_i32]),
+    "dcmp_lzo_uncompress_batch_device": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, p_u8, p_i64, p_i64, p_u8, p_i64,
+                                                   p_i64, p_i64, p_i64, p_i32, C.c_void_p]),
+    "dcmp_lzo_uncompress": (C.c_int, [C.c_void_p, p_u8, C.c_int64, p_u8, C.c_int64, C.POINTER(C.c_int64)]),
     "dcmp_adler32": (C.c_uint32, [C.c_uint32, p_u8, C.c_int64]),
     "dcmp_crc32": (C.c_uint32, [C.c_uint32, p_u8, C.c_int64]),
 }

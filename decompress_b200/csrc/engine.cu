@@ -21,6 +21,9 @@ int launch_inflate_parallel(int fmt, int64_t n, const uint8_t *src_base, const i
                             int64_t *produced, int32_t *status, unsigned long long *work_counter, uint32_t *tok_scratch,
                             int ctas, cudaStream_t stream);
 size_t inflate_parallel_scratch_bytes_per_cta();
+void launch_lzo_decode(int mode, int64_t n, const uint8_t *src_base, const int64_t *src_off, const int64_t *src_len,
+                       uint8_t *dst_base, const int64_t *dst_off, const int64_t *dst_cap, int64_t *consumed,
+                       int64_t *produced, int32_t *status, cudaStream_t stream);
 constexpr int INTERNAL_RETRY = 0x7f; // inflate_parallel.cu: "this stream is for the general kernel"
 }
 
@@ -186,9 +189,16 @@ int dcmp_inflate_batch_device(dcmp_engine *e, int fmt, int64_t n, const uint8_t 
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
-int dcmp_inflate_batch(dcmp_engine *e, int fmt, int64_t n, const uint8_t *src_base, const int64_t *src_off,
-                       const int64_t *src_len, uint8_t *dst_base, const int64_t *dst_off, const int64_t *dst_cap,
-                       int64_t *consumed, int64_t *produced, int32_t *status) {
+// Host-buffer driver shared by every *_batch entry point: uploads, runs `launch` (one of the *_batch_device
+// functions, bound to its codec arguments) and downloads.
+typedef int (*device_batch_fn)(dcmp_engine *e, int arg, int64_t n, const uint8_t *d_src_base, const int64_t *d_src_off,
+                               const int64_t *d_src_len, uint8_t *d_dst_base, const int64_t *d_dst_off,
+                               const int64_t *d_dst_cap, int64_t *d_consumed, int64_t *d_produced, int32_t *d_status,
+                               void *cuda_stream);
+
+static int host_batch(dcmp_engine *e, device_batch_fn launch, int fmt, int64_t n, const uint8_t *src_base,
+                      const int64_t *src_off, const int64_t *src_len, uint8_t *dst_base, const int64_t *dst_off,
+                      const int64_t *dst_cap, int64_t *consumed, int64_t *produced, int32_t *status) {
   if (!e) return DCMP_API_INVALID_ARGUMENT;
   if (n < 0) return DCMP_API_INVALID_ARGUMENT;
   if (n == 0) return DCMP_API_OK;
@@ -257,8 +267,8 @@ int dcmp_inflate_batch(dcmp_engine *e, int fmt, int64_t n, const uint8_t *src_ba
     CU(cudaEventRecord(e->ev_in[c], s_in));
     CU(cudaStreamWaitEvent(s_k, e->ev_in[c], 0));
     if (k1 > k0) {
-      rc = dcmp_inflate_batch_device(e, fmt, k1 - k0, d_src, d_tab + k0, d_tab + n + k0, d_dst, d_tab + 2 * n + k0,
-                                     d_tab + 3 * n + k0, d_cons + k0, d_prod + k0, d_stat + k0, (void *)s_k);
+      rc = launch(e, fmt, k1 - k0, d_src, d_tab + k0, d_tab + n + k0, d_dst, d_tab + 2 * n + k0,
+                  d_tab + 3 * n + k0, d_cons + k0, d_prod + k0, d_stat + k0, (void *)s_k);
       if (rc != DCMP_API_OK) return rc;
     }
     CU(cudaEventRecord(e->ev_k[c], s_k));
@@ -294,6 +304,44 @@ int dcmp_inflate_batch(dcmp_engine *e, int fmt, int64_t n, const uint8_t *src_ba
   CU(cudaStreamSynchronize(s_k));
   CU(cudaStreamSynchronize(s_in));
   return DCMP_API_OK;
+}
+
+int dcmp_inflate_batch(dcmp_engine *e, int fmt, int64_t n, const uint8_t *src_base, const int64_t *src_off,
+                       const int64_t *src_len, uint8_t *dst_base, const int64_t *dst_off, const int64_t *dst_cap,
+                       int64_t *consumed, int64_t *produced, int32_t *status) {
+  if (fmt != DCMP_FMT_RAW && fmt != DCMP_FMT_ZLIB) return DCMP_API_INVALID_ARGUMENT;
+  return host_batch(e, dcmp_inflate_batch_device, fmt, n, src_base, src_off, src_len, dst_base, dst_off, dst_cap,
+                    consumed, produced, status);
+}
+
+int dcmp_lzo_uncompress_batch_device(dcmp_engine *e, int mode, int64_t n, const uint8_t *d_src_base,
+                                     const int64_t *d_src_off, const int64_t *d_src_len, uint8_t *d_dst_base,
+                                     const int64_t *d_dst_off, const int64_t *d_dst_cap, int64_t *d_consumed,
+                                     int64_t *d_produced, int32_t *d_status, void *cuda_stream) {
+  if (!e || n < 0 || (mode != 0 && mode != 1)) return DCMP_API_INVALID_ARGUMENT;
+  if (n == 0) return DCMP_API_OK;
+  CU(cudaSetDevice(e->device));
+  dcmp::launch_lzo_decode(mode, n, d_src_base, d_src_off, d_src_len, d_dst_base, d_dst_off, d_dst_cap, d_consumed,
+                          d_produced, d_status, (cudaStream_t)cuda_stream);
+  e->launches += 1;
+  CU(cudaGetLastError());
+  return DCMP_API_OK;
+}
+
+int dcmp_lzo_uncompress_batch(dcmp_engine *e, int mode, int64_t n, const uint8_t *src_base, const int64_t *src_off,
+                              const int64_t *src_len, uint8_t *dst_base, const int64_t *dst_off,
+                              const int64_t *dst_cap, int64_t *consumed, int64_t *produced, int32_t *status) {
+  if (mode != 0 && mode != 1) return DCMP_API_INVALID_ARGUMENT;
+  return host_batch(e, dcmp_lzo_uncompress_batch_device, mode, n, src_base, src_off, src_len, dst_base, dst_off,
+                    dst_cap, consumed, produced, status);
+}
+
+int dcmp_lzo_uncompress(dcmp_engine *e, const uint8_t *src, int64_t src_len, uint8_t *dst, int64_t dst_len,
+                        int64_t *produced) {
+  int64_t zero = 0, consumed = 0;
+  int32_t status = 0;
+  int rc = dcmp_lzo_uncompress_batch(e, 0, 1, src, &zero, &src_len, dst, &zero, &dst_len, &consumed, produced, &status);
+  return rc != DCMP_API_OK ? rc : status;
 }
 
 int dcmp_inf_ns_inflate(dcmp_engine *e, const uint8_t *src, int64_t src_len, uint8_t *dst, int64_t dst_len,

@@ -1,6 +1,7 @@
 // decompress_b200/csrc/simt.cuh — the few macros that differ between the real CUDA build and
 // the CPU debugging build of the same kernel sources (tests/simt_emu, -DDCMP_EMU; test-only).
 #pragma once
+#include <stdint.h>
 #ifdef DCMP_EMU
 #include "simt_emu.h"
 #else

@@ -118,6 +118,28 @@ int dcmp_inf_ns_inflate(dcmp_engine *e, const uint8_t *src, int64_t src_len,
 int dcmp_zl_inf_ns_inflate(dcmp_engine *e, const uint8_t *src, int64_t src_len,
                            uint8_t *dst, int64_t dst_len, int64_t *consumed, int64_t *produced);
 
+/* ---- batched LZO1X decode ---------------------------------------------------
+ * Replaces Lzo.uncompress (lib/lzo.mli:15-27, lib/lzo.ml:395-403; mode 0) and
+ * Lzo.uncompress_with_buffer (lib/lzo.mli:29-33, lib/lzo.ml:405-414; mode 1) applied to n independent
+ * blocks.  Same slab/offset-table layout as dcmp_inflate_batch.  status[k] is DCMP_OK or one of
+ * DCMP_LZO_MALFORMED / DCMP_LZO_INVALID_ARGUMENT / DCMP_LZO_INVALID_DICTIONARY; the two modes differ
+ * only in how an out-of-bounds access is reported (lib/lzo.ml:399-401 vs 409-412); in mode 1 a full
+ * dst is DCMP_UNEXPECTED_END_OF_OUTPUT (the reference's Buffer.t grows: enlarge dst and call again).  Back-references
+ * replicate bytes (what uncompress_with_buffer, minilzo and every reference test pin). */
+int dcmp_lzo_uncompress_batch(dcmp_engine *e, int mode, int64_t n,
+                              const uint8_t *src_base, const int64_t *src_off, const int64_t *src_len,
+                              uint8_t *dst_base, const int64_t *dst_off, const int64_t *dst_cap,
+                              int64_t *consumed, int64_t *produced, int32_t *status);
+int dcmp_lzo_uncompress_batch_device(dcmp_engine *e, int mode, int64_t n,
+                                     const uint8_t *d_src_base, const int64_t *d_src_off, const int64_t *d_src_len,
+                                     uint8_t *d_dst_base, const int64_t *d_dst_off, const int64_t *d_dst_cap,
+                                     int64_t *d_consumed, int64_t *d_produced, int32_t *d_status,
+                                     void *cuda_stream);
+/* Single-call mirror of Lzo.uncompress (lib/lzo.ml:395-403): returns the status, *produced = length of
+ * the output prefix written. */
+int dcmp_lzo_uncompress(dcmp_engine *e, const uint8_t *src, int64_t src_len, uint8_t *dst, int64_t dst_len,
+                        int64_t *produced);
+
 /* ---- checksums (host; checkseum's Adler32 / Crc32 as used at lib/zl.ml:231-245,
  * lib/gz.ml:344-356) ------------------------------------------------------------ */
 uint32_t dcmp_adler32(uint32_t adler, const uint8_t *p, int64_t n);

@@ -49,3 +49,20 @@ def inflate_streams(streams, caps, fmt=0, mode=0, ctas=2):
         q = int(min(max(prod[k], 0), dc[k]))
         out.append((int(st[k]), int(cons[k]), int(prod[k]), dst[do[k]:do[k] + q].tobytes()))
     return out, retried
+
+
+def lzo_blocks(blocks, caps, mode=0):
+    """LZO kernel on the emulator: list of (status, consumed, produced, bytes)."""
+    from decompress_b200 import batch
+
+    src, so, sl, dst, do, dc = batch.pack(blocks, caps)
+    n = len(blocks)
+    cons = np.zeros(n, dtype=np.int64)
+    prod = np.zeros(n, dtype=np.int64)
+    st = np.full(n, -1, dtype=np.int32)
+    p = lambda a: C.c_void_p(a.ctypes.data)
+    L = lib()
+    L.emu_lzo_batch.restype = C.c_int
+    L.emu_lzo_batch.argtypes = [C.c_int, C.c_int64] + [C.c_void_p] * 9
+    L.emu_lzo_batch(mode, n, p(src), p(so), p(sl), p(dst), p(do), p(dc), p(cons), p(prod), p(st))
+    return [(int(st[k]), int(cons[k]), int(prod[k]), dst[do[k]:do[k] + int(min(max(prod[k], 0), dc[k]))].tobytes()) for k in range(n)]

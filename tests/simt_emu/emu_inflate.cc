@@ -4,6 +4,7 @@
 #include "simt_emu.h"
 #include "../../decompress_b200/csrc/inflate_serial.cu"
 #include "../../decompress_b200/csrc/inflate_parallel.cu"
+#include "../../decompress_b200/csrc/lzo_decode.cu"
 
 extern "C" {
 
@@ -33,6 +34,15 @@ int emu_inflate_batch(int mode, int fmt, int64_t n, const uint8_t *src, const in
     });
   }
   return retried;
+}
+
+int emu_lzo_batch(int mode, int64_t n, const uint8_t *src, const int64_t *soff, const int64_t *slen, uint8_t *dst,
+                  const int64_t *doff, const int64_t *dcap, int64_t *cons, int64_t *prod, int32_t *status) {
+  using namespace dcmp;
+  simt::launch(simt::dim3((unsigned)((n + LZO_WARPS - 1) / LZO_WARPS)), simt::dim3(LZO_WARPS * 32), 0, [&]() {
+    lzo_decode_kernel(mode, n, src, soff, slen, dst, doff, dcap, cons, prod, status);
+  });
+  return 0;
 }
 
 long emu_switches() { return simt::g_switches; }

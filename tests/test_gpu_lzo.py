@@ -1,0 +1,136 @@
+"""GPU parity tests for the LZO1X decode path (dcmp_lzo_uncompress_batch through the C ABI) against the
+CPU oracle, the reference's golden vectors (test/test_lzo.ml, test/test.ml) and the reference's own
+differential oracle, vendored minilzo.  Bit-exact: status, produced and every output byte."""
+import json
+import os
+import random
+
+import numpy as np
+import pytest
+
+import workloads
+from decompress_b200 import Error, Ok, _lib, lzo
+from tests import oracle
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(__file__), "golden")
+_ST = {0: 0, 1: 16, 2: 17, 3: 18}  # oracle code -> include/dcmp.h status
+
+
+def _vectors():
+    with open(os.path.join(G, "lzo.json")) as f:
+        return json.load(f)["vectors"]
+
+
+def _src(v):
+    if "src" in v:
+        return bytes.fromhex(v["src"])
+    pre, times, post = v["src_repeat"]
+    return bytes.fromhex(pre) * times + bytes.fromhex(post)
+
+
+def _out(v):
+    if "out" in v:
+        return bytes.fromhex(v["out"])
+    if "out_repeat" in v:
+        pre, times = v["out_repeat"]
+        return bytes.fromhex(pre) * times
+    return None
+
+
+@pytest.fixture(scope="module")
+def eng():
+    return _lib.Engine(0)
+
+
+@pytest.mark.parametrize("v", _vectors(), ids=lambda v: v["name"] + "@" + v["cite"].split("/")[-1])
+def test_lzo_golden(v, eng):
+    """The reference's KATs, called the way test/test_lzo.ml calls them."""
+    src = _src(v)
+    if v["api"] == "uncompress_with_buffer":
+        res = lzo.uncompress_with_buffer(src, engine=eng)
+        got = res.value if res.is_ok() else None
+    else:
+        out = np.zeros(1 << 22, dtype=np.uint8)
+        res = lzo.uncompress(src, out, engine=eng)
+        got = res.value.tobytes() if res.is_ok() else None
+    if v["raw_hint"] == "error":
+        assert not res.is_ok(), v["cite"]
+        if "error" in v:
+            assert res == Error(v["error"]), v["cite"]
+    else:
+        assert res.is_ok(), (res, v["cite"])
+        want = _out(v)
+        if want is not None:
+            assert got == want, v["cite"]
+
+
+def _mutants(comps, count, seed):
+    rnd = random.Random(seed)
+    out = []
+    for _ in range(count):
+        s = bytearray(rnd.choice(comps))
+        m = rnd.randrange(4)
+        if m == 0:
+            s = s[:rnd.randrange(1, len(s))]
+        elif m == 1:
+            s[rnd.randrange(len(s))] ^= 1 << rnd.randrange(8)
+        elif m == 2:
+            s = bytearray(rnd.randrange(256) for _ in range(rnd.randrange(1, 100)))
+        else:
+            s[rnd.randrange(min(40, len(s)))] ^= 1 << rnd.randrange(8)
+        out.append(bytes(s))
+    return out
+
+
+def _check(blocks, caps, mode, eng):
+    fn = oracle.lzo_uncompress if mode == 0 else oracle.lzo_uncompress_with_buffer
+    res = lzo.uncompress_batch(blocks, caps, mode=mode, engine=eng)
+    for k, (b, cap) in enumerate(zip(blocks, caps)):
+        rc, cons, prod, out = fn(b, cap)
+        st, gc, gp, go = res[k]
+        if mode == 1 and rc == 1 and st == 2:
+            continue  # a full dst is reported distinctly in mode 1 (the reference's Buffer.t is unbounded)
+        assert st == _ST[rc], (k, st, rc)
+        assert (gp, go) == (prod, out), k
+        if rc == 0:
+            assert gc == cons, k
+
+
+def test_minilzo_blocks_and_mutants_vs_oracle(eng):
+    """fuzz/fuzz_lzo.ml:30-39: whatever minilzo compresses, Lzo.uncompress must decode identically; plus
+    corrupted / truncated variants against the oracle in both error mappings."""
+    sizes = [0, 1, 5, 100, 4096, 49152, 70000, 300000]
+    plains = [workloads.text(n, 900 + n) for n in sizes]
+    plains += [bytes(50000), (b"abcdefg" * 9000)[:60000], np.random.default_rng(3).integers(0, 256, 30000, dtype=np.uint8).tobytes()]
+    comps = [workloads.lzo1x_1_compress(p) for p in plains]
+    res = lzo.uncompress_batch(comps, [len(p) for p in plains], engine=eng)
+    for k, (st, cons, prod, out) in enumerate(res):
+        assert (st, cons, prod) == (0, len(comps[k]), len(plains[k])), k
+        assert out == plains[k], k
+        rc, ref = workloads.lzo1x_decompress_safe(comps[k], len(plains[k]))
+        assert rc == 0 and ref == out, k
+    muts = _mutants([c for c in comps if len(c) > 10], 300, 11)
+    for mode in (0, 1):
+        _check(comps + muts, [1 << 19] * (len(comps) + len(muts)), mode, eng)
+        _check(comps + muts, [40000] * (len(comps) + len(muts)), mode, eng)
+        _check(comps, [max(0, len(p) - 1) for p in plains], mode, eng)
+
+
+def test_c5_blocks_1mib(eng):
+    """BASELINE config 5 at reduced count: 1 MiB blocks compressed by minilzo's lzo1x_1_compress."""
+    comps, plains = workloads.c5_blocks(24)
+    res = lzo.uncompress_batch(comps, [len(p) for p in plains], engine=eng)
+    for k, (st, cons, prod, out) in enumerate(res):
+        assert (st, cons, prod) == (0, len(comps[k]), 1 << 20), k
+        assert out == plains[k], k
+
+
+def test_single_call_mirrors(eng):
+    comp = workloads.lzo1x_1_compress(b"againandagainandagain" * 50)
+    out = np.zeros(2000, dtype=np.uint8)
+    r = lzo.uncompress(comp, out, engine=eng)
+    assert r.is_ok() and r.value.tobytes() == b"againandagainandagain" * 50
+    assert lzo.uncompress(comp, np.zeros(10, dtype=np.uint8), engine=eng) == Error("Invalid_argument")
+    assert lzo.uncompress_with_buffer(comp, chunk=16, engine=eng) == Ok(b"againandagainandagain" * 50)
+    assert lzo.uncompress_with_buffer(b"\x10\x00\x00", engine=eng) == Error("Malformed")

@@ -8,6 +8,7 @@ C1  one stored block                       stored_block(payload)
 C2  n x 64 KiB dynamic-Huffman zlib streams  c2_streams(n)
 C3  enwik-style text for deflate            text(nbytes, seed)
 C4  concatenated gzip members               c4_members(total, seed)
+C5  LZO1X blocks (vendored minilzo)         c5_blocks(n, size, seed)
 """
 import os
 import struct
@@ -124,3 +125,49 @@ def c4_members(total_plain, seed=0, lo=16 << 10, hi=256 << 10):
         have += size
         k += 1
     return out
+
+
+_MINILZO = None
+
+
+def minilzo():
+    """The reference's own vendored LZO1X implementation (test/minilzo-2.10, built by oracle/Makefile into
+    oracle/_ref/libminilzo.so — the reference's differential oracle for Lzo, fuzz/fuzz_lzo.ml)."""
+    global _MINILZO
+    if _MINILZO is None:
+        import ctypes as C
+        path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "oracle", "_ref", "libminilzo.so")
+        L = C.CDLL(path)
+        for fn in (L.lzo1x_1_compress, L.lzo1x_decompress_safe):
+            fn.restype = C.c_int
+            fn.argtypes = [C.c_char_p, C.c_ulong, C.c_char_p, C.POINTER(C.c_ulong), C.c_void_p]
+        _MINILZO = L
+    return _MINILZO
+
+
+def lzo1x_1_compress(data):
+    import ctypes as C
+    L = minilzo()
+    data = bytes(data)
+    out = C.create_string_buffer(len(data) + len(data) // 16 + 64 + 3)
+    n = C.c_ulong(len(out))
+    wrk = C.create_string_buffer(16384 * 8)
+    rc = L.lzo1x_1_compress(data, len(data), out, C.byref(n), wrk)
+    assert rc == 0
+    return out.raw[:n.value]
+
+
+def lzo1x_decompress_safe(comp, cap):
+    import ctypes as C
+    L = minilzo()
+    out = C.create_string_buffer(max(cap, 1))
+    n = C.c_ulong(cap)
+    rc = L.lzo1x_decompress_safe(bytes(comp), len(comp), out, C.byref(n), None)
+    return rc, out.raw[:n.value]
+
+
+def c5_blocks(n, size=1 << 20, seed0=0):
+    """n LZO1X blocks, each `size` bytes of the C3 text compressed by minilzo's lzo1x_1_compress.
+    Returns (list of compressed blocks, list of plaintexts)."""
+    plains = [text(size, 7000 + seed0 + k) for k in range(n)]
+    return [lzo1x_1_compress(p) for p in plains], plains
