@@ -50,6 +50,13 @@ _SIGNATURES = {
     "dcmp_lzo_uncompress_batch_device": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, p_u8, p_i64, p_i64, p_u8, p_i64,
                                                    p_i64, p_i64, p_i64, p_i32, C.c_void_p]),
     "dcmp_lzo_uncompress": (C.c_int, [C.c_void_p, p_u8, C.c_int64, p_u8, C.c_int64, C.POINTER(C.c_int64)]),
+    "dcmp_deflate_bound": (C.c_int64, [C.c_int64, C.c_int]),
+    "dcmp_deflate_batch": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int64, p_u8, p_i64, p_i64, p_u8, p_i64, p_i64,
+                                     p_i64, p_i32]),
+    "dcmp_deflate_batch_device": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int64, p_u8, p_i64, p_i64, p_u8, p_i64,
+                                            p_i64, p_i64, p_i32, C.c_void_p]),
+    "dcmp_def_ns_deflate": (C.c_int, [C.c_void_p, C.c_int, p_u8, C.c_int64, p_u8, C.c_int64, C.POINTER(C.c_int64)]),
+    "dcmp_zl_def_ns_deflate": (C.c_int, [C.c_void_p, C.c_int, p_u8, C.c_int64, p_u8, C.c_int64, C.POINTER(C.c_int64)]),
     "dcmp_adler32": (C.c_uint32, [C.c_uint32, p_u8, C.c_int64]),
     "dcmp_crc32": (C.c_uint32, [C.c_uint32, p_u8, C.c_int64]),
 }

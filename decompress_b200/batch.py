@@ -79,3 +79,18 @@ def inflate_device(fmt, d_src, d_src_off, d_src_len, d_dst, d_dst_off, d_dst_cap
         C.c_void_p(d_dst_cap.data_ptr()), C.c_void_p(d_consumed.data_ptr()), C.c_void_p(d_produced.data_ptr()),
         C.c_void_p(d_status.data_ptr()), C.c_void_p(stream))
     _lib.check(rc, "dcmp_inflate_batch_device")
+
+
+def deflate_streams(inputs, caps=None, level=6, fmt=FMT_RAW, engine=None):
+    """dcmp_deflate_batch on a list of byte strings: list of (status, written, compressed bytes)."""
+    eng = engine or _lib.default_engine()
+    if caps is None:
+        caps = [int(_lib.lib().dcmp_deflate_bound(len(x), fmt)) for x in inputs]
+    src, so, sl, dst, do, dc = pack(inputs, caps)
+    n = len(inputs)
+    wr = np.zeros(n, dtype=np.int64)
+    st = np.zeros(n, dtype=np.int32)
+    rc = _lib.lib().dcmp_deflate_batch(eng.handle, level, fmt, n, _np_ptr(src), _np_ptr(so), _np_ptr(sl), _np_ptr(dst),
+                                       _np_ptr(do), _np_ptr(dc), _np_ptr(wr), _np_ptr(st))
+    _lib.check(rc, "dcmp_deflate_batch")
+    return [(int(st[k]), int(wr[k]), dst[do[k]:do[k] + int(wr[k])].tobytes()) for k in range(n)]

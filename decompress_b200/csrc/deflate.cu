@@ -1,0 +1,569 @@
+// decompress_b200/csrc/deflate.cu — batched DEFLATE compression (BASELINE config C3).
+//
+// Replaces, for the batched / one-shot case, the compress side of lib/de.ml: the match finder
+// De.Lz77 (de.ml:4013-4515; hash of 4 bytes * 0x9e3779b1, de.ml:4067-4071), the frequency
+// counters (de.ml:2330-2351), the Huffman builder De.T (de.ml:1828-2192: lengths limited to
+// 15 / 7 bits, canonical codes emitted bit-reversed), the dynamic block header
+// (Def.encode_dynamic_header / code-length RLE with 16/17/18, de.ml:2100-2192, 2583-2633) and the
+// LSB-first bit writer (Def.write / c_bits, de.ml:2529-2897).  The reference is a serial,
+// resumable state machine; lazy matching in particular is sequential by definition, so the
+// parse here is a different (greedy, warp-parallel) algorithm that produces a different but
+// valid DEFLATE stream — parity for this path is "the reference's Inf and system zlib both
+// inflate it back byte-identically" (SURVEY.md §8c), which tests/test_gpu_deflate.py checks.
+//
+// Layout.  Every input stream is cut into independent 64 KiB chunks; one warp compresses one
+// chunk into one DEFLATE block (dynamic Huffman, or stored when that is smaller):
+//   1 tokenise   32 positions per step: every lane hashes its 4 bytes, takes the most recent
+//                earlier position with the same hash (shared-memory table, __match_any_sync for
+//                the ones inside the step) and extends the match byte-wise; the greedy parse of
+//                the 32 positions is the orbit of the carry-in position under
+//                next(p) = p + (match ? len : 1), found by pointer doubling with shuffles;
+//                tokens go to an L2-resident scratch, symbol frequencies to shared memory;
+//   2 build      lengths of the literal/length, distance and code-length codes (sort by warp
+//                bitonic network, two-queue Huffman, zlib's overflow repair), canonical codes;
+//   3 pack       32 tokens per step: bit widths -> exclusive scan -> atomicOr into a
+//                shared-memory bit window that is drained to HBM with coalesced 32-bit stores.
+// A chunk that is not the last of its stream ends with an empty stored block, which byte-aligns
+// it (the classic sync-flush marker 00 00 ff ff), so chunk outputs concatenate; a second kernel
+// gathers them to their final place, adds the zlib header / Adler-32 trailer if asked to.
+#include "simt.cuh"
+#include "../../include/dcmp.h"
+
+namespace dcmp {
+
+constexpr int DF_CHUNK = 65536;
+constexpr int DF_WARPS = 4;
+constexpr int DF_HASH_BITS = 12;
+constexpr int DF_SLOT = DF_CHUNK + 64;   // bytes of scratch output per chunk (stored worst case: len + 15)
+constexpr int DF_WIN = 256;              // words of the output bit window (ring)
+constexpr int DF_MIN_MATCH = 4;          // 3-byte matches only when close (zlib's TOO_FAR idea, de.ml:4102)
+constexpr int DF_TOO_FAR = 4096;
+
+struct DfChunk {       // built on the host by engine.cu
+  int64_t src_off;     // chunk start, relative to src_base
+  int32_t len;         // 0..DF_CHUNK
+  int32_t stream;      // owning stream
+  int32_t flags;       // bit0: last chunk of its stream
+  int32_t pad;
+};
+struct DfChunkOut {
+  uint32_t bytes;      // compressed bytes in the chunk's slot
+  uint32_t sum_a;      // Adler-32 partials of the chunk's input: sum of bytes (mod 65521)
+  uint32_t sum_b;      // ... sum of (len - j) * byte_j (mod 65521)
+  uint32_t pad;
+};
+
+struct DfSmem {
+  uint16_t head[1 << DF_HASH_BITS];
+  uint32_t freq_l[288];
+  uint32_t freq_d[32];
+  uint32_t freq_bl[19];
+  uint32_t sortbuf[512];
+  uint32_t weight[2 * 288];
+  uint16_t parent[2 * 288];
+  uint16_t code_l[288];
+  uint16_t code_d[32];
+  uint16_t code_bl[19];
+  uint8_t len_l[288];
+  uint8_t len_d[32];
+  uint8_t len_bl[19];
+  uint8_t rle_sym[320];
+  uint8_t rle_extra[320];
+  uint32_t win[DF_WIN];
+  uint32_t extra_bits; // total extra bits of the tokens (for the stored/dynamic decision)
+  int n_rle;
+};
+
+__device__ __constant__ uint8_t c_bl_order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15}; // de.ml:237
+
+__device__ __forceinline__ uint32_t df_len_sym(uint32_t len, uint32_t *ebits, uint32_t *eval) { // len 3..258
+  if (len == 258) { *ebits = 0; *eval = 0; return 285; }
+  const uint32_t x = len - 3;
+  const uint32_t e = x < 8 ? 0u : (uint32_t)(31 - __clz((int)x)) - 2u;
+  *ebits = e;
+  *eval = x & ((1u << e) - 1u);
+  return 257u + 4u * e + (x >> e);
+}
+__device__ __forceinline__ uint32_t df_dist_sym(uint32_t dist, uint32_t *ebits, uint32_t *eval) { // dist 1..32768
+  const uint32_t D = dist - 1;
+  if (D < 4) { *ebits = 0; *eval = 0; return D; }
+  const uint32_t n = (uint32_t)(31 - __clz((int)D));
+  *ebits = n - 1;
+  *eval = D & ((1u << (n - 1)) - 1u);
+  return 2u * n + ((D >> (n - 1)) & 1u);
+}
+
+// ---- output bit window -----------------------------------------------------------------------
+struct DfBits {
+  uint32_t *win;       // shared ring of DF_WIN words
+  uint32_t *out;       // global, word aligned
+  uint32_t bitpos;     // bits written so far
+  uint32_t flushed;    // words already stored to global
+  __device__ __forceinline__ void put(uint64_t v, uint32_t n, uint32_t at) { // n <= 57 bits of v at bit `at`
+    if (n == 0) return;
+    const uint32_t w = at >> 5, sh = at & 31;
+    const uint64_t lo = v << sh;
+    atomicOr(&win[w & (DF_WIN - 1)], (uint32_t)lo);
+    if (sh + n > 32) atomicOr(&win[(w + 1) & (DF_WIN - 1)], (uint32_t)(lo >> 32));
+    if (sh + n > 64) atomicOr(&win[(w + 2) & (DF_WIN - 1)], (uint32_t)(v >> (64 - sh)));
+  }
+  // all lanes: store the words that are complete (or everything, at the end)
+  __device__ __forceinline__ void drain(int lane, bool all) {
+    __syncwarp();
+    const uint32_t upto = all ? (bitpos + 31) >> 5 : bitpos >> 5;
+    for (uint32_t i = flushed + lane; i < upto; i += 32) {
+      out[i] = win[i & (DF_WIN - 1)];
+      win[i & (DF_WIN - 1)] = 0;
+    }
+    flushed = upto;
+    __syncwarp();
+  }
+};
+
+// ---- Huffman code construction (one warp) ------------------------------------------------------
+// freq[0..n) -> len[0..n) (<= max_bits) and bit-reversed canonical codes.  Follows the shape of
+// De.T.make / zlib build_tree (de.ml:2013-2068): at least two codes, overflow repair as in gen_bitlen.
+__device__ void df_build_code(DfSmem &S, const uint32_t *freq, int n, int max_bits, uint8_t *len, uint16_t *code, int lane) {
+  __syncwarp();
+  // keys (freq << 9 | sym) of the used symbols, padded for the sorting network
+  for (int i = lane; i < 512; i += 32) S.sortbuf[i] = 0xffffffffu;
+  for (int i = lane; i < n; i += 32) len[i] = 0;
+  __syncwarp();
+  if (lane == 0) {
+    int m = 0;
+    for (int s = 0; s < n; s++)
+      if (freq[s]) S.sortbuf[m++] = (freq[s] << 9) | (uint32_t)s;
+    // the pkzip rule (de.ml:1863-1874): force at least two codes
+    if (m == 0) { S.sortbuf[0] = (1u << 9) | 0u; S.sortbuf[1] = (1u << 9) | 1u; m = 2; }
+    else if (m == 1) { uint32_t s0 = S.sortbuf[0] & 511u; S.sortbuf[1] = (1u << 9) | (s0 == 0 ? 1u : 0u); m = 2; }
+    S.n_rle = m; // (reused as a scratch scalar: number of leaves)
+  }
+  __syncwarp();
+  const int m = S.n_rle;
+  // bitonic sort of 512 keys, 16 per lane
+  for (int k = 2; k <= 512; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int t = lane; t < 256; t += 32) {
+        const int i = ((t / j) * 2 * j) + (t % j); // lower index of the pair
+        const int p = i + j;
+        const bool up = (i & k) == 0;
+        const uint32_t a = S.sortbuf[i], b = S.sortbuf[p];
+        if ((a > b) == up) { S.sortbuf[i] = b; S.sortbuf[p] = a; }
+      }
+      __syncwarp();
+    }
+  }
+  if (lane == 0) {
+    // two-queue Huffman: leaves 0..m-1 (ascending), internal nodes m..2m-2 (created in ascending weight)
+    for (int i = 0; i < m; i++) S.weight[i] = S.sortbuf[i] >> 9;
+    int li = 0, ii = m, nn = m;
+    while (nn < 2 * m - 1) {
+      uint32_t w = 0;
+      for (int k = 0; k < 2; k++) {
+        int pick;
+        if (li < m && (ii >= nn || S.weight[li] <= S.weight[ii])) pick = li++;
+        else pick = ii++;
+        w += S.weight[pick];
+        S.parent[pick] = (uint16_t)nn;
+      }
+      S.weight[nn++] = w;
+    }
+    // depths (a parent always has a larger index), folded into bl_count with the overflow repair of gen_bitlen
+    int bl_count[16];
+    for (int b = 0; b < 16; b++) bl_count[b] = 0;
+    S.weight[2 * m - 2] = 0; // weight[] now holds depths
+    int overflow = 0;
+    for (int i = 2 * m - 3; i >= 0; i--) {
+      uint32_t d = S.weight[S.parent[i]] + 1;
+      S.weight[i] = d;
+      if (i < m) {
+        if ((int)d > max_bits) { d = (uint32_t)max_bits; overflow++; }
+        bl_count[d]++;
+      }
+    }
+    while (overflow > 0) {
+      int bits = max_bits - 1;
+      while (bl_count[bits] == 0) bits--;
+      bl_count[bits]--;
+      bl_count[bits + 1] += 2;
+      bl_count[max_bits]--;
+      overflow -= 2;
+    }
+    // longest codes to the least frequent symbols
+    int i = 0;
+    for (int bits = max_bits; bits >= 1; bits--)
+      for (int c = bl_count[bits]; c > 0; c--) len[S.sortbuf[i++] & 511u] = (uint8_t)bits;
+    // canonical codes, bit-reversed (de.ml:1910-1924)
+    uint32_t next_code[16];
+    uint32_t c = 0;
+    next_code[0] = 0;
+    for (int bits = 1; bits <= max_bits; bits++) { c = (c + (uint32_t)bl_count[bits - 1]) << 1; next_code[bits] = c; }
+    // (bl_count[0] is 0 here: unused symbols do not take part)
+    for (int s = 0; s < n; s++) {
+      const int l = len[s];
+      code[s] = l ? (uint16_t)(__brev(next_code[l]++) >> (32 - l)) : 0;
+    }
+  }
+  __syncwarp();
+}
+
+// Adler-32 partials of p[0..n): sum of bytes and sum of (n - j) * p[j], both mod 65521.
+__device__ void df_adler_partials(const uint8_t *p, int n, int lane, uint32_t *sum_a, uint32_t *sum_b) {
+  unsigned long long a = 0, b = 0;
+  for (int j = lane; j < n; j += 32) {
+    const uint32_t v = p[j];
+    a += v;
+    b += (unsigned long long)v * (uint32_t)(n - j);
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    a += __shfl_xor_sync(0xffffffffu, a, o);
+    b += __shfl_xor_sync(0xffffffffu, b, o);
+  }
+  *sum_a = (uint32_t)(a % 65521ull);
+  *sum_b = (uint32_t)(b % 65521ull);
+}
+
+// ---- one chunk ----------------------------------------------------------------------------------
+__device__ void df_compress_chunk(DfSmem &S, const uint8_t *d, int len, bool last, int level, uint32_t *tok,
+                                  uint8_t *slot, DfChunkOut *res, bool want_adler, int lane) {
+  uint32_t sum_a = 0, sum_b = 0;
+  if (want_adler) df_adler_partials(d, len, lane, &sum_a, &sum_b);
+  uint32_t *out32 = reinterpret_cast<uint32_t *>(slot);
+  // ---------------------------------------------------------------- 1 tokenise
+  int ntok = 0;
+  bool stored = level == 0 || len < 16;
+  if (!stored) {
+    for (int i = lane; i < (1 << DF_HASH_BITS); i += 32) S.head[i] = 0;
+    for (int i = lane; i < 288; i += 32) S.freq_l[i] = 0;
+    if (lane < 32) S.freq_d[lane] = 0;
+    if (lane == 0) S.extra_bits = 0;
+    __syncwarp();
+    int carry = 0; // first position of the step not covered by the previous token (may be >= 32)
+    uint32_t my_extra = 0;
+    for (int base = 0; base < len; base += 32) {
+      if (carry >= 32) { carry -= 32; continue; } // the whole step lies inside the previous match
+      const int p = base + lane;
+      const int maxlen = min(258, len - p);
+      int mlen = 0, mdist = 0;
+      uint32_t h = 0xffffffffu; // lanes that cannot start a match do not take part in the hash table
+      if (maxlen >= DF_MIN_MATCH) {
+        const uint32_t v = (uint32_t)d[p] | ((uint32_t)d[p + 1] << 8) | ((uint32_t)d[p + 2] << 16) | ((uint32_t)d[p + 3] << 24);
+        h = (v * 0x9e3779b1u) >> (32 - DF_HASH_BITS);
+      }
+      const uint32_t same = __match_any_sync(0xffffffffu, h);
+      int cand = -1;
+      if (h != 0xffffffffu) {
+        const uint32_t lower = same & ((1u << lane) - 1u);
+        cand = lower ? base + (31 - __clz((int)lower)) : (int)S.head[h];
+      }
+      __syncwarp();
+      if (h != 0xffffffffu && (same >> lane) == 1u) S.head[h] = (uint16_t)p; // the last lane of a group is the most recent
+      if (cand >= 0 && cand < p && p - cand <= 32768) {
+        int l = 0;
+        while (l < maxlen && d[cand + l] == d[p + l]) l++;
+        if (l >= DF_MIN_MATCH || (l == 3 && p - cand < DF_TOO_FAR)) { mlen = l; mdist = p - cand; }
+      }
+      // greedy parse of the 32 positions: orbit of `carry` under next()
+      const int nxt = lane + (mlen ? mlen : 1);
+      int jump = nxt > 32 ? 32 : nxt;
+      uint32_t marked = 1u << carry;
+#pragma unroll
+      for (int r = 0; r < 5; r++) {
+        const bool me = (marked >> lane) & 1u;
+        marked |= __reduce_or_sync(0xffffffffu, (me && jump < 32) ? (1u << jump) : 0u);
+        const int j2 = __shfl_sync(0xffffffffu, jump, jump & 31);
+        if (jump < 32) jump = j2;
+      }
+      // positions beyond the input do not exist
+      if (base + 32 > len) marked &= (len - base) >= 32 ? 0xffffffffu : ((1u << (len - base)) - 1u);
+      const bool start = (marked >> lane) & 1u;
+      // the token that leaves the step tells where the next one starts
+      const uint32_t leaving = __ballot_sync(0xffffffffu, start && nxt >= 32);
+      carry = leaving ? __shfl_sync(0xffffffffu, nxt, __ffs((int)leaving) - 1) - 32 : 0;
+      if (start) {
+        uint32_t t;
+        if (mlen) {
+          uint32_t eb, ev, eb2, ev2;
+          const uint32_t ls = df_len_sym((uint32_t)mlen, &eb, &ev), ds = df_dist_sym((uint32_t)mdist, &eb2, &ev2);
+          atomicAdd(&S.freq_l[ls], 1u);
+          atomicAdd(&S.freq_d[ds], 1u);
+          my_extra += eb + eb2;
+          t = (1u << 23) | ((uint32_t)(mdist - 1) << 8) | (uint32_t)(mlen - 3);
+        } else {
+          t = d[p];
+          atomicAdd(&S.freq_l[t], 1u);
+        }
+        tok[ntok + __popc(marked & ((1u << lane) - 1u))] = t;
+      }
+      ntok += __popc(marked);
+    }
+    my_extra = __reduce_add_sync(0xffffffffu, my_extra);
+    if (lane == 0) { S.freq_l[256] = 1; S.extra_bits = my_extra; }
+    __syncwarp();
+    // ---------------------------------------------------------------- 2 build
+    df_build_code(S, S.freq_l, 286, 15, S.len_l, S.code_l, lane);
+    df_build_code(S, S.freq_d, 30, 15, S.len_d, S.code_d, lane);
+    if (lane == 0) {
+      // code-length RLE (zlib scan_tree / send_tree; the reference's T.scan / T.symbols, de.ml:2100-2192)
+      int hlit = 286, hdist = 30;
+      while (hlit > 257 && S.len_l[hlit - 1] == 0) hlit--;
+      while (hdist > 1 && S.len_d[hdist - 1] == 0) hdist--;
+      for (int i = 0; i < 19; i++) S.freq_bl[i] = 0;
+      const int total = hlit + hdist;
+      int nr = 0, i = 0;
+      while (i < total) {
+        const int l = i < hlit ? S.len_l[i] : S.len_d[i - hlit];
+        int run = 1;
+        while (i + run < total && (i + run < hlit ? S.len_l[i + run] : S.len_d[i + run - hlit]) == l) run++;
+        int left = run;
+        if (l == 0) {
+          while (left >= 11) { int c = left > 138 ? 138 : left; S.rle_sym[nr] = 18; S.rle_extra[nr++] = (uint8_t)(c - 11); S.freq_bl[18]++; left -= c; }
+          if (left >= 3) { S.rle_sym[nr] = 17; S.rle_extra[nr++] = (uint8_t)(left - 3); S.freq_bl[17]++; left = 0; }
+          while (left > 0) { S.rle_sym[nr] = 0; S.rle_extra[nr++] = 0; S.freq_bl[0]++; left--; }
+        } else {
+          S.rle_sym[nr] = (uint8_t)l; S.rle_extra[nr++] = 0; S.freq_bl[l]++; left--;
+          while (left >= 3) { int c = left > 6 ? 6 : left; S.rle_sym[nr] = 16; S.rle_extra[nr++] = (uint8_t)(c - 3); S.freq_bl[16]++; left -= c; }
+          while (left > 0) { S.rle_sym[nr] = (uint8_t)l; S.rle_extra[nr++] = 0; S.freq_bl[l]++; left--; }
+        }
+        i += run;
+      }
+      S.n_rle = nr;
+      S.weight[575] = (uint32_t)hlit; // (two scalars parked in unused node slots)
+      S.weight[574] = (uint32_t)hdist;
+    }
+    __syncwarp();
+    const int n_rle = S.n_rle, hlit = (int)S.weight[575], hdist = (int)S.weight[574];
+    __syncwarp();
+    df_build_code(S, S.freq_bl, 19, 7, S.len_bl, S.code_bl, lane);
+    // cost of the dynamic block vs stored blocks
+    uint32_t bits_dyn = 0;
+    for (int s = lane; s < 286; s += 32) bits_dyn += S.freq_l[s] * S.len_l[s];
+    if (lane < 30) bits_dyn += S.freq_d[lane] * S.len_d[lane];
+    if (lane < 19) bits_dyn += S.freq_bl[lane] * S.len_bl[lane];
+    bits_dyn = __reduce_add_sync(0xffffffffu, bits_dyn);
+    int hclen = 19;
+    while (hclen > 4 && S.len_bl[c_bl_order[hclen - 1]] == 0) hclen--;
+    uint32_t rle_extra_bits = 0;
+    for (int i = lane; i < n_rle; i += 32) rle_extra_bits += S.rle_sym[i] == 16 ? 2u : S.rle_sym[i] == 17 ? 3u : S.rle_sym[i] == 18 ? 7u : 0u;
+    rle_extra_bits = __reduce_add_sync(0xffffffffu, rle_extra_bits);
+    bits_dyn += 3 + 14 + 3 * (uint32_t)hclen + rle_extra_bits + S.extra_bits + (last ? 0u : 3u + 7u + 32u);
+    const uint32_t bits_stored = 8u * ((uint32_t)len + 5u * (uint32_t)((len + 65534) / 65535));
+    if (bits_dyn >= bits_stored) stored = true;
+    if (!stored) {
+      // ---------------------------------------------------------------- 3 pack
+      for (int i = lane; i < DF_WIN; i += 32) S.win[i] = 0;
+      __syncwarp();
+      DfBits bw{S.win, out32, 0u, 0u};
+      if (lane == 0) {
+        uint32_t at = 0;
+        auto put = [&](uint32_t v, uint32_t n) { bw.put(v, n, at); at += n; };
+        put(last ? 1u : 0u, 1);
+        put(2u, 2);
+        put((uint32_t)(hlit - 257), 5);
+        put((uint32_t)(hdist - 1), 5);
+        put((uint32_t)(hclen - 4), 4);
+        for (int i = 0; i < hclen; i++) put(S.len_bl[c_bl_order[i]], 3);
+        for (int i = 0; i < n_rle; i++) {
+          const int s = S.rle_sym[i];
+          put(S.code_bl[s], S.len_bl[s]);
+          if (s == 16) put(S.rle_extra[i], 2);
+          else if (s == 17) put(S.rle_extra[i], 3);
+          else if (s == 18) put(S.rle_extra[i], 7);
+        }
+        S.n_rle = (int)at;
+      }
+      __syncwarp();
+      bw.bitpos = (uint32_t)S.n_rle;
+      bw.drain(lane, false);
+      for (int g = 0; g < ntok; g += 32) {
+        const int i = g + lane;
+        uint64_t v = 0;
+        uint32_t nb = 0;
+        if (i < ntok) {
+          const uint32_t t = tok[i];
+          if ((t >> 23) & 1u) {
+            uint32_t eb, ev, eb2, ev2;
+            const uint32_t ls = df_len_sym((t & 0xffu) + 3u, &eb, &ev), ds = df_dist_sym(((t >> 8) & 0x7fffu) + 1u, &eb2, &ev2);
+            v = S.code_l[ls];
+            nb = S.len_l[ls];
+            v |= (uint64_t)ev << nb; nb += eb;
+            v |= (uint64_t)S.code_d[ds] << nb; nb += S.len_d[ds];
+            v |= (uint64_t)ev2 << nb; nb += eb2;
+          } else {
+            v = S.code_l[t];
+            nb = S.len_l[t];
+          }
+        }
+        uint32_t incl = nb;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const uint32_t u = __shfl_up_sync(0xffffffffu, incl, o);
+          if (lane >= o) incl += u;
+        }
+        bw.put(v, nb, bw.bitpos + incl - nb);
+        bw.bitpos += __shfl_sync(0xffffffffu, incl, 31);
+        bw.drain(lane, false);
+      }
+      if (lane == 0) {
+        uint32_t at = bw.bitpos;
+        bw.put(S.code_l[256], S.len_l[256], at); at += S.len_l[256];
+        if (!last) {
+          // empty stored block: byte-aligns the chunk so that chunk outputs concatenate
+          at += 3;                       // BFINAL=0, BTYPE=00
+          at = (at + 7u) & ~7u;
+          bw.put(0xffff0000ull, 32, at); // LEN=0, NLEN=0xffff
+          at += 32;
+        }
+        S.n_rle = (int)at;
+      }
+      __syncwarp();
+      bw.bitpos = (uint32_t)S.n_rle;
+      bw.drain(lane, true);
+      if (lane == 0) { res->bytes = (bw.bitpos + 7u) >> 3; res->sum_a = sum_a; res->sum_b = sum_b; }
+      return;
+    }
+  }
+  // ---------------------------------------------------------------- stored blocks (de.ml:2566-2581)
+  {
+    uint32_t o = 0;
+    int pos = 0;
+    do {
+      const int n = min(65535, len - pos);
+      const bool fin = last && pos + n == len;
+      if (lane == 0) {
+        slot[o] = fin ? 1 : 0;
+        slot[o + 1] = (uint8_t)n; slot[o + 2] = (uint8_t)(n >> 8);
+        slot[o + 3] = (uint8_t)~n; slot[o + 4] = (uint8_t)(~n >> 8);
+      }
+      for (int k = lane; k < n; k += 32) slot[o + 5 + k] = d[pos + k];
+      o += 5 + (uint32_t)n;
+      pos += n;
+    } while (pos < len);
+    if (lane == 0) { res->bytes = o; res->sum_a = sum_a; res->sum_b = sum_b; }
+  }
+}
+
+__global__ void __launch_bounds__(DF_WARPS * 32)
+deflate_chunk_kernel(int level, int want_adler, int64_t nchunks, const uint8_t *src_base, const DfChunk *chunks,
+                     DfChunkOut *outs, uint8_t *slots, uint32_t *tok_scratch, unsigned long long *work_counter) {
+  DCMP_DYN_SMEM(smem_raw);
+  DfSmem *SS = reinterpret_cast<DfSmem *>(smem_raw);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  DfSmem &S = SS[warp];
+  uint32_t *tok = tok_scratch + ((size_t)blockIdx.x * DF_WARPS + warp) * DF_CHUNK;
+  for (;;) {
+    unsigned long long c = 0;
+    if (lane == 0) c = atomicAdd(work_counter, 1ull);
+    c = __shfl_sync(0xffffffffu, c, 0);
+    if (c >= (unsigned long long)nchunks) break;
+    const DfChunk ch = chunks[c];
+    df_compress_chunk(S, src_base + ch.src_off, ch.len, (ch.flags & 1) != 0, level, tok, slots + (size_t)c * DF_SLOT,
+                      &outs[c], want_adler != 0, lane);
+    __syncwarp();
+  }
+}
+
+// One thread per stream: where every chunk goes, the framing, the result.
+// first_chunk[k] .. first_chunk[k+1] are stream k's chunks.
+__global__ void deflate_plan_kernel(int fmt, int level, int64_t nstreams, const int64_t *first_chunk, const DfChunkOut *outs,
+                                    const DfChunk *chunks, uint8_t *dst_base, const int64_t *dst_off, const int64_t *dst_cap,
+                                    int64_t *chunk_dst, int64_t *written, int32_t *status) {
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= nstreams) return;
+  const int64_t c0 = first_chunk[k], c1 = first_chunk[k + 1];
+  const int64_t cap = dst_cap[k];
+  int64_t total = fmt == DCMP_FMT_ZLIB ? 2 : 0;
+  unsigned long long A = 1, B = 0;
+  for (int64_t c = c0; c < c1; c++) {
+    chunk_dst[c] = total;
+    total += outs[c].bytes;
+    const unsigned long long n = (unsigned long long)chunks[c].len;
+    B = (B + (n % 65521ull) * A + outs[c].sum_b) % 65521ull;
+    A = (A + outs[c].sum_a) % 65521ull;
+  }
+  if (fmt == DCMP_FMT_ZLIB) total += 4;
+  // De.Def.Ns.deflate needs _end_padding = 8 bytes of dst (de.ml:3998-4001) and reports a dst that is too
+  // small as Unexpected_end_of_output
+  if (total > cap) {
+    for (int64_t c = c0; c < c1; c++) chunk_dst[c] = -1;
+    written[k] = 0;
+    status[k] = DCMP_UNEXPECTED_END_OF_OUTPUT;
+    return;
+  }
+  uint8_t *o = dst_base + dst_off[k];
+  if (fmt == DCMP_FMT_ZLIB) {
+    // Zl.Def.Ns.header (lib/zl.ml:600-608)
+    uint32_t hdr = (8u + (7u << 4)) << 8;
+    const uint32_t fl = level <= 1 ? 0u : level <= 5 ? 1u : level == 6 ? 2u : 3u;
+    hdr |= fl << 6;
+    hdr += 31u - (hdr % 31u);
+    o[0] = (uint8_t)(hdr >> 8);
+    o[1] = (uint8_t)hdr;
+    const uint32_t ad = (uint32_t)((B << 16) | A);
+    o[total - 4] = (uint8_t)(ad >> 24); o[total - 3] = (uint8_t)(ad >> 16); o[total - 2] = (uint8_t)(ad >> 8); o[total - 1] = (uint8_t)ad;
+  }
+  written[k] = total;
+  status[k] = DCMP_OK;
+}
+
+// One CTA per chunk: copy the chunk's slot to its place in the stream's output.
+__global__ void __launch_bounds__(256)
+deflate_gather_kernel(const DfChunk *chunks, const DfChunkOut *outs, const uint8_t *slots, const int64_t *chunk_dst,
+                      uint8_t *dst_base, const int64_t *dst_off) {
+  const int64_t c = blockIdx.x;
+  const int64_t at = chunk_dst[c];
+  if (at < 0) return;
+  const uint8_t *s = slots + (size_t)c * DF_SLOT;
+  uint8_t *o = dst_base + dst_off[chunks[c].stream] + at;
+  const uint32_t n = outs[c].bytes;
+  // head to 16-byte alignment of the destination, 16-byte body, tail
+  uint32_t headn = (uint32_t)((16 - ((uintptr_t)o & 15)) & 15);
+  if (headn > n) headn = n;
+  for (uint32_t i = threadIdx.x; i < headn; i += blockDim.x) o[i] = s[i];
+  const uint32_t body = (n - headn) & ~15u;
+  for (uint32_t i = threadIdx.x * 16; i < body; i += blockDim.x * 16) {
+    uint8_t tmp[16];
+#pragma unroll
+    for (int b = 0; b < 16; b++) tmp[b] = s[headn + i + b];
+    *reinterpret_cast<uint4 *>(o + headn + i) = *reinterpret_cast<uint4 *>(tmp);
+  }
+  for (uint32_t i = headn + body + threadIdx.x; i < n; i += blockDim.x) o[i] = s[i];
+}
+
+size_t deflate_smem_bytes() { return sizeof(DfSmem) * DF_WARPS + 128; }
+size_t deflate_tok_bytes_per_cta() { return (size_t)DF_WARPS * DF_CHUNK * sizeof(uint32_t); }
+size_t deflate_chunk_desc_bytes() { return sizeof(DfChunk); }
+size_t deflate_chunk_out_bytes() { return sizeof(DfChunkOut); }
+int deflate_chunk_size() { return DF_CHUNK; }
+size_t deflate_slot_bytes() { return DF_SLOT; }
+
+#ifndef DCMP_EMU
+int launch_deflate(int level, int fmt, int64_t nstreams, int64_t nchunks, const uint8_t *src_base, const void *chunks,
+                   const int64_t *first_chunk, void *outs, uint8_t *slots, int64_t *chunk_dst, uint32_t *tok_scratch,
+                   unsigned long long *work_counter, int ctas, uint8_t *dst_base, const int64_t *dst_off,
+                   const int64_t *dst_cap, int64_t *written, int32_t *status, cudaStream_t stream) {
+  static bool configured = false;
+  const size_t smem = deflate_smem_bytes();
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(deflate_chunk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    configured = true;
+  }
+  if (nchunks > 0) {
+    int64_t want = (nchunks + DF_WARPS - 1) / DF_WARPS;
+    if (ctas > want) ctas = (int)want;
+    deflate_chunk_kernel<<<(unsigned)ctas, DF_WARPS * 32, smem, stream>>>(level, fmt == DCMP_FMT_ZLIB ? 1 : 0, nchunks, src_base,
+                                                                         (const DfChunk *)chunks, (DfChunkOut *)outs, slots,
+                                                                         tok_scratch, work_counter);
+  }
+  deflate_plan_kernel<<<(unsigned)((nstreams + 127) / 128), 128, 0, stream>>>(fmt, level, nstreams, first_chunk, (const DfChunkOut *)outs,
+                                                                              (const DfChunk *)chunks, dst_base, dst_off, dst_cap,
+                                                                              chunk_dst, written, status);
+  if (nchunks > 0)
+    deflate_gather_kernel<<<(unsigned)nchunks, 256, 0, stream>>>((const DfChunk *)chunks, (const DfChunkOut *)outs, slots, chunk_dst,
+                                                                 dst_base, dst_off);
+  return 0;
+}
+#endif
+
+} // namespace dcmp

@@ -24,6 +24,14 @@ size_t inflate_parallel_scratch_bytes_per_cta();
 void launch_lzo_decode(int mode, int64_t n, const uint8_t *src_base, const int64_t *src_off, const int64_t *src_len,
                        uint8_t *dst_base, const int64_t *dst_off, const int64_t *dst_cap, int64_t *consumed,
                        int64_t *produced, int32_t *status, cudaStream_t stream);
+int launch_deflate(int level, int fmt, int64_t nstreams, int64_t nchunks, const uint8_t *src_base, const void *chunks,
+                   const int64_t *first_chunk, void *outs, uint8_t *slots, int64_t *chunk_dst, uint32_t *tok_scratch,
+                   unsigned long long *work_counter, int ctas, uint8_t *dst_base, const int64_t *dst_off,
+                   const int64_t *dst_cap, int64_t *written, int32_t *status, cudaStream_t stream);
+size_t deflate_tok_bytes_per_cta();
+size_t deflate_slot_bytes();
+int deflate_chunk_size();
+struct DfChunkHost { int64_t src_off; int32_t len; int32_t stream; int32_t flags; int32_t pad; }; // = deflate.cu's DfChunk
 constexpr int INTERNAL_RETRY = 0x7f; // inflate_parallel.cu: "this stream is for the general kernel"
 }
 
@@ -50,6 +58,11 @@ struct dcmp_engine {
   int par_ctas = 0;                  // persistent CTAs of the sub-chunk-parallel kernel (2 per SM)
   uint8_t *d_scratch = nullptr;      // [work counter (256 B) | token scratch of every CTA]
   int mode = 0;                      // 0 = parallel + general, 1 = general kernel only (DCMP_INFLATE_MODE=serial)
+  // deflate: persistent CTAs (3 per SM), their token scratch, and a growable arena for the per-chunk state
+  int def_ctas = 0;
+  uint8_t *d_def_scratch = nullptr;  // [work counter (256 B) | token scratch of every CTA]
+  uint8_t *d_def_arena = nullptr;
+  size_t def_arena_cap = 0;
   // host-facing calls: three-stage pipeline (H2D | kernels | D2H) over slices of the batch
   static const int MAX_SLICES = 8;
   cudaStream_t s_kernel = nullptr, s_out = nullptr;
@@ -144,6 +157,8 @@ void dcmp_engine_destroy(dcmp_engine *e) {
   cudaSetDevice(e->device);
   if (e->d_buf) cudaFree(e->d_buf);
   if (e->d_scratch) cudaFree(e->d_scratch);
+  if (e->d_def_scratch) cudaFree(e->d_def_scratch);
+  if (e->d_def_arena) cudaFree(e->d_def_arena);
   if (e->pipeline_ready) {
     for (int i = 0; i < dcmp_engine::MAX_SLICES; i++) { cudaEventDestroy(e->ev_in[i]); cudaEventDestroy(e->ev_k[i]); cudaEventDestroy(e->ev_meta[i]); }
     cudaStreamDestroy(e->s_kernel);
@@ -358,6 +373,141 @@ int dcmp_zl_inf_ns_inflate(dcmp_engine *e, const uint8_t *src, int64_t src_len, 
   int32_t status = 0;
   int rc = dcmp_inflate_batch(e, DCMP_FMT_ZLIB, 1, src, &zero, &src_len, dst, &zero, &dst_len, consumed, produced, &status);
   return rc != DCMP_API_OK ? rc : status;
+}
+
+// ---- deflate ------------------------------------------------------------------------------------
+int64_t dcmp_deflate_bound(int64_t len, int fmt) {
+  // De.Def.Ns.compress_bound (lib/de.ml:3993-3996), + 6 for zlib (lib/zl.ml:598)
+  if (len < 0) return -1;
+  int64_t blocks = std::max<int64_t>(1, (len + 9999) / 10000);
+  return 5 * blocks + len + 1 + 8 + (fmt == DCMP_FMT_ZLIB ? 6 : 0);
+}
+
+int dcmp_deflate_batch_device(dcmp_engine *e, int level, int fmt, int64_t n, const uint8_t *d_src_base,
+                              const int64_t *h_src_off, const int64_t *h_src_len, uint8_t *d_dst_base,
+                              const int64_t *h_dst_off, const int64_t *h_dst_cap, int64_t *d_written,
+                              int32_t *d_status, void *cuda_stream) {
+  if (!e || n < 0) return DCMP_API_INVALID_ARGUMENT;
+  if (fmt != DCMP_FMT_RAW && fmt != DCMP_FMT_ZLIB) return DCMP_API_INVALID_ARGUMENT;
+  if (n == 0) return DCMP_API_OK;
+  if (!h_src_off || !h_src_len || !h_dst_off || !h_dst_cap || !d_written || !d_status) return DCMP_API_INVALID_ARGUMENT;
+  CU(cudaSetDevice(e->device));
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  if (level < 0 || level > 12) {
+    // De.Def.Ns.encoder (lib/de.ml:3930): Invalid_compression_level for every stream
+    std::vector<int32_t> bad((size_t)n, DCMP_INVALID_COMPRESSION_LEVEL);
+    CU(cudaMemsetAsync(d_written, 0, (size_t)n * 8, st));
+    CU(cudaMemcpyAsync(d_status, bad.data(), (size_t)n * 4, cudaMemcpyHostToDevice, st));
+    CU(cudaStreamSynchronize(st));
+    return DCMP_API_OK;
+  }
+  // chunk table: every stream is cut into independent chunks (an empty stream still has one)
+  const int64_t CH = dcmp::deflate_chunk_size();
+  std::vector<dcmp::DfChunkHost> chunks;
+  std::vector<int64_t> first((size_t)n + 1);
+  for (int64_t k = 0; k < n; k++) {
+    if (h_src_len[k] < 0 || h_dst_cap[k] < 0) return DCMP_API_INVALID_ARGUMENT;
+    first[k] = (int64_t)chunks.size();
+    int64_t pos = 0;
+    do {
+      int64_t m = std::min<int64_t>(CH, h_src_len[k] - pos);
+      dcmp::DfChunkHost c{h_src_off[k] + pos, (int32_t)m, (int32_t)k, (pos + m == h_src_len[k]) ? 1 : 0, 0};
+      chunks.push_back(c);
+      pos += m;
+    } while (pos < h_src_len[k]);
+  }
+  first[n] = (int64_t)chunks.size();
+  const int64_t nc = (int64_t)chunks.size();
+  if (!e->d_def_scratch) {
+    e->def_ctas = 3 * (e->sm_count > 0 ? e->sm_count : 148);
+    CU(cudaMalloc(&e->d_def_scratch, 256 + (size_t)e->def_ctas * dcmp::deflate_tok_bytes_per_cta()));
+  }
+  const size_t slot = dcmp::deflate_slot_bytes();
+  size_t o_chunks = 0;
+  size_t o_outs = align_up(o_chunks + (size_t)nc * sizeof(dcmp::DfChunkHost), 256);
+  size_t o_cdst = align_up(o_outs + (size_t)nc * 16, 256);
+  size_t o_first = align_up(o_cdst + (size_t)nc * 8, 256);
+  size_t o_doff = align_up(o_first + (size_t)(n + 1) * 8, 256);
+  size_t o_dcap = align_up(o_doff + (size_t)n * 8, 256);
+  size_t o_slots = align_up(o_dcap + (size_t)n * 8, 256);
+  size_t need = o_slots + (size_t)nc * slot + 256;
+  if (need > e->def_arena_cap) {
+    if (e->d_def_arena) { CU(cudaFree(e->d_def_arena)); e->d_def_arena = nullptr; e->def_arena_cap = 0; }
+    CU(cudaMalloc(&e->d_def_arena, need + (need >> 3)));
+    e->def_arena_cap = need + (need >> 3);
+  }
+  uint8_t *A = e->d_def_arena;
+  CU(cudaMemcpyAsync(A + o_chunks, chunks.data(), (size_t)nc * sizeof(dcmp::DfChunkHost), cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(A + o_first, first.data(), (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(A + o_doff, h_dst_off, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(A + o_dcap, h_dst_cap, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+  unsigned long long *counter = (unsigned long long *)e->d_def_scratch;
+  CU(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), st));
+  int rc = dcmp::launch_deflate(level, fmt, n, nc, d_src_base, A + o_chunks, (const int64_t *)(A + o_first), A + o_outs,
+                                A + o_slots, (int64_t *)(A + o_cdst), (uint32_t *)(e->d_def_scratch + 256), counter,
+                                e->def_ctas, d_dst_base, (const int64_t *)(A + o_doff), (const int64_t *)(A + o_dcap),
+                                d_written, d_status, st);
+  if (rc != 0) { set_err("launch_deflate", (cudaError_t)rc); return DCMP_API_CUDA_ERROR; }
+  e->launches += 3;
+  CU(cudaGetLastError());
+  // the uploads above read host vectors that die with this frame
+  CU(cudaStreamSynchronize(st));
+  return DCMP_API_OK;
+}
+
+int dcmp_deflate_batch(dcmp_engine *e, int level, int fmt, int64_t n, const uint8_t *src_base, const int64_t *src_off,
+                       const int64_t *src_len, uint8_t *dst_base, const int64_t *dst_off, const int64_t *dst_cap,
+                       int64_t *written, int32_t *status) {
+  if (!e || n < 0) return DCMP_API_INVALID_ARGUMENT;
+  if (n == 0) return DCMP_API_OK;
+  if (!src_off || !src_len || !dst_off || !dst_cap || !written || !status) return DCMP_API_INVALID_ARGUMENT;
+  CU(cudaSetDevice(e->device));
+  int64_t s_lo = INT64_MAX, s_hi = 0, d_lo = INT64_MAX, d_hi = 0;
+  for (int64_t k = 0; k < n; k++) {
+    if (src_len[k] < 0 || dst_cap[k] < 0 || src_off[k] < 0 || dst_off[k] < 0) return DCMP_API_INVALID_ARGUMENT;
+    s_lo = std::min(s_lo, src_off[k]); s_hi = std::max(s_hi, src_off[k] + src_len[k]);
+    d_lo = std::min(d_lo, dst_off[k]); d_hi = std::max(d_hi, dst_off[k] + dst_cap[k]);
+  }
+  size_t s_bytes = (size_t)(s_hi - s_lo), d_bytes = (size_t)(d_hi - d_lo);
+  if ((s_bytes && !src_base) || (d_bytes && !dst_base)) return DCMP_API_INVALID_ARGUMENT;
+  size_t o_dst = align_up(s_bytes + 16, 256);
+  size_t o_res = align_up(o_dst + d_bytes + 16, 256);
+  int rc = e->reserve(o_res + (size_t)n * 12 + 256);
+  if (rc != DCMP_API_OK) return rc;
+  uint8_t *d_src = e->d_buf, *d_dst = e->d_buf + o_dst;
+  int64_t *d_written = (int64_t *)(e->d_buf + o_res);
+  int32_t *d_status = (int32_t *)(d_written + n);
+  std::vector<int64_t> so((size_t)n), dof((size_t)n);
+  for (int64_t k = 0; k < n; k++) { so[k] = src_off[k] - s_lo; dof[k] = dst_off[k] - d_lo; }
+  cudaStream_t st = e->stream;
+  if (s_bytes) CU(cudaMemcpyAsync(d_src, src_base + s_lo, s_bytes, cudaMemcpyHostToDevice, st));
+  rc = dcmp_deflate_batch_device(e, level, fmt, n, d_src, so.data(), src_len, d_dst, dof.data(), dst_cap, d_written,
+                                 d_status, (void *)st);
+  if (rc != DCMP_API_OK) return rc;
+  CU(cudaMemcpyAsync(written, d_written, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(status, d_status, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  for (int64_t k = 0; k < n; k++)
+    if (status[k] == DCMP_OK && written[k] > 0)
+      CU(cudaMemcpyAsync(dst_base + dst_off[k], d_dst + dof[k], (size_t)written[k], cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  return DCMP_API_OK;
+}
+
+static int def_ns(dcmp_engine *e, int level, int fmt, const uint8_t *src, int64_t src_len, uint8_t *dst, int64_t dst_len,
+                  int64_t *written) {
+  int64_t zero = 0;
+  int32_t status = 0;
+  int rc = dcmp_deflate_batch(e, level, fmt, 1, src, &zero, &src_len, dst, &zero, &dst_len, written, &status);
+  return rc != DCMP_API_OK ? rc : status;
+}
+int dcmp_def_ns_deflate(dcmp_engine *e, int level, const uint8_t *src, int64_t src_len, uint8_t *dst, int64_t dst_len,
+                        int64_t *written) {
+  return def_ns(e, level, DCMP_FMT_RAW, src, src_len, dst, dst_len, written);
+}
+int dcmp_zl_def_ns_deflate(dcmp_engine *e, int level, const uint8_t *src, int64_t src_len, uint8_t *dst, int64_t dst_len,
+                           int64_t *written) {
+  return def_ns(e, level, DCMP_FMT_ZLIB, src, src_len, dst, dst_len, written);
 }
 
 uint32_t dcmp_adler32(uint32_t adler, const uint8_t *p, int64_t n) {

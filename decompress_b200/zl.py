@@ -1,4 +1,4 @@
-"""Mirror of lib/zl.mli for the GPU-backed path: Zl.Inf.Ns.inflate (zl.ml:400-417)."""
+"""Mirror of lib/zl.mli for the GPU-backed path: Zl.Inf.Ns.inflate (zl.ml:400-417), Zl.Def.Ns.deflate (zl.ml:610-630)."""
 import ctypes as C
 
 import numpy as np
@@ -23,4 +23,25 @@ class Inf:
                 _lib.check(st, "dcmp_zl_inf_ns_inflate")
             if st == 0:
                 return Ok((cons.value, prod.value))
+            return Error(_lib.STATUS_TAG.get(st, st))
+
+
+class Def:
+    class Ns:
+        @staticmethod
+        def compress_bound(length):
+            return int(_lib.lib().dcmp_deflate_bound(length, _lib.FMT_ZLIB))
+
+        @staticmethod
+        def deflate(src, dst, level=4, engine=None):
+            eng = engine or _lib.default_engine()
+            s = np.ascontiguousarray(_as_u8(src))
+            d = _as_u8(dst, writable=True)
+            wr = C.c_int64(0)
+            st = _lib.lib().dcmp_zl_def_ns_deflate(eng.handle, level, C.c_void_p(s.ctypes.data if s.size else 0), s.size,
+                                                   C.c_void_p(d.ctypes.data if d.size else 0), d.size, C.byref(wr))
+            if st < 0:
+                _lib.check(st, "dcmp_zl_def_ns_deflate")
+            if st == 0:
+                return Ok(wr.value)
             return Error(_lib.STATUS_TAG.get(st, st))

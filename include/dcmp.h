@@ -140,6 +140,35 @@ int dcmp_lzo_uncompress_batch_device(dcmp_engine *e, int mode, int64_t n,
 int dcmp_lzo_uncompress(dcmp_engine *e, const uint8_t *src, int64_t src_len, uint8_t *dst, int64_t dst_len,
                         int64_t *produced);
 
+/* ---- batched deflate ----------------------------------------------------------
+ * Replaces De.Def.Ns.deflate (lib/de.mli:436-443, lib/de.ml:3998-4010) / Zl.Def.Ns.deflate
+ * (lib/zl.ml:610-630) applied to n independent inputs, and — for one large input — the streaming
+ * pair De.Lz77.compress + De.Def.encode (lib/de.ml:4294-4515, 2465-3038) as driven by
+ * De.Higher.compress / Zl.Higher.compress (lib/de.ml:4517-4560, lib/zl.ml:634-648).
+ * level: 0 = stored blocks only, 1..12 = compressed (out of range: every status is
+ * DCMP_INVALID_COMPRESSION_LEVEL, lib/de.ml:3930).  written[k] = bytes of the deflate (or zlib)
+ * stream; a dst_cap[k] that is too small gives DCMP_UNEXPECTED_END_OF_OUTPUT (lib/de.ml:3061-3076);
+ * dcmp_deflate_bound(len, fmt) is always enough.  The compressed bytes are NOT those of the
+ * reference (its parse is sequential, lib/de.ml:4351-4410): the contract is that De.Inf and system
+ * zlib inflate them back to the input. */
+int64_t dcmp_deflate_bound(int64_t len, int fmt); /* De.Def.Ns.compress_bound, lib/de.ml:3993-3996 (+6: lib/zl.ml:598) */
+int dcmp_deflate_batch(dcmp_engine *e, int level, int fmt, int64_t n,
+                       const uint8_t *src_base, const int64_t *src_off, const int64_t *src_len,
+                       uint8_t *dst_base, const int64_t *dst_off, const int64_t *dst_cap,
+                       int64_t *written, int32_t *status);
+/* Data pointers are DEVICE pointers, the four offset tables are HOST arrays (the call cuts the inputs
+ * into chunks on the host); d_written / d_status are device arrays.  Synchronises `cuda_stream` once,
+ * after the kernels are enqueued. */
+int dcmp_deflate_batch_device(dcmp_engine *e, int level, int fmt, int64_t n,
+                              const uint8_t *d_src_base, const int64_t *h_src_off, const int64_t *h_src_len,
+                              uint8_t *d_dst_base, const int64_t *h_dst_off, const int64_t *h_dst_cap,
+                              int64_t *d_written, int32_t *d_status, void *cuda_stream);
+/* Single-call mirrors of De.Def.Ns.deflate / Zl.Def.Ns.deflate: return the status, *written = `Ok len`. */
+int dcmp_def_ns_deflate(dcmp_engine *e, int level, const uint8_t *src, int64_t src_len,
+                        uint8_t *dst, int64_t dst_len, int64_t *written);
+int dcmp_zl_def_ns_deflate(dcmp_engine *e, int level, const uint8_t *src, int64_t src_len,
+                           uint8_t *dst, int64_t dst_len, int64_t *written);
+
 /* ---- checksums (host; checkseum's Adler32 / Crc32 as used at lib/zl.ml:231-245,
  * lib/gz.ml:344-356) ------------------------------------------------------------ */
 uint32_t dcmp_adler32(uint32_t adler, const uint8_t *p, int64_t n);

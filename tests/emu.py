@@ -66,3 +66,19 @@ def lzo_blocks(blocks, caps, mode=0):
     L.emu_lzo_batch.argtypes = [C.c_int, C.c_int64] + [C.c_void_p] * 9
     L.emu_lzo_batch(mode, n, p(src), p(so), p(sl), p(dst), p(do), p(dc), p(cons), p(prod), p(st))
     return [(int(st[k]), int(cons[k]), int(prod[k]), dst[do[k]:do[k] + int(min(max(prod[k], 0), dc[k]))].tobytes()) for k in range(n)]
+
+
+def deflate_streams(inputs, caps, level=6, fmt=0):
+    """Deflate kernels on the emulator: list of (status, written, bytes)."""
+    from decompress_b200 import batch
+
+    src, so, sl, dst, do, dc = batch.pack(inputs, caps)
+    n = len(inputs)
+    wr = np.zeros(n, dtype=np.int64)
+    st = np.full(n, -1, dtype=np.int32)
+    p = lambda a: C.c_void_p(a.ctypes.data)
+    L = lib()
+    L.emu_deflate_batch.restype = C.c_int
+    L.emu_deflate_batch.argtypes = [C.c_int, C.c_int, C.c_int64] + [C.c_void_p] * 8
+    L.emu_deflate_batch(level, fmt, n, p(src), p(so), p(sl), p(dst), p(do), p(dc), p(wr), p(st))
+    return [(int(st[k]), int(wr[k]), dst[do[k]:do[k] + int(wr[k])].tobytes()) for k in range(n)]

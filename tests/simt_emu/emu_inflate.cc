@@ -2,9 +2,11 @@
 // compiled as C++ with -DDCMP_EMU) on the CPU SIMT emulator so their logic can be debugged
 // without a GPU.  TEST INFRASTRUCTURE ONLY: built into tests/_build/, never part of the product.
 #include "simt_emu.h"
+#include <algorithm>
 #include "../../decompress_b200/csrc/inflate_serial.cu"
 #include "../../decompress_b200/csrc/inflate_parallel.cu"
 #include "../../decompress_b200/csrc/lzo_decode.cu"
+#include "../../decompress_b200/csrc/deflate.cu"
 
 extern "C" {
 
@@ -41,6 +43,40 @@ int emu_lzo_batch(int mode, int64_t n, const uint8_t *src, const int64_t *soff, 
   using namespace dcmp;
   simt::launch(simt::dim3((unsigned)((n + LZO_WARPS - 1) / LZO_WARPS)), simt::dim3(LZO_WARPS * 32), 0, [&]() {
     lzo_decode_kernel(mode, n, src, soff, slen, dst, doff, dcap, cons, prod, status);
+  });
+  return 0;
+}
+
+int emu_deflate_batch(int level, int fmt, int64_t n, const uint8_t *src, const int64_t *soff, const int64_t *slen, uint8_t *dst,
+                      const int64_t *doff, const int64_t *dcap, int64_t *written, int32_t *status) {
+  using namespace dcmp;
+  std::vector<DfChunk> chunks;
+  std::vector<int64_t> first(n + 1);
+  for (int64_t k = 0; k < n; k++) {
+    first[k] = (int64_t)chunks.size();
+    int64_t pos = 0;
+    do {
+      int64_t m = std::min<int64_t>(DF_CHUNK, slen[k] - pos);
+      chunks.push_back(DfChunk{soff[k] + pos, (int32_t)m, (int32_t)k, (pos + m == slen[k]) ? 1 : 0, 0});
+      pos += m;
+    } while (pos < slen[k]);
+  }
+  first[n] = (int64_t)chunks.size();
+  int64_t nc = (int64_t)chunks.size();
+  std::vector<DfChunkOut> outs(nc);
+  std::vector<uint8_t> slots((size_t)nc * DF_SLOT);
+  std::vector<int64_t> cdst(nc);
+  int ctas = 2;
+  std::vector<uint32_t> tok((size_t)ctas * DF_WARPS * DF_CHUNK);
+  unsigned long long counter = 0;
+  simt::launch(simt::dim3(ctas), simt::dim3(DF_WARPS * 32), deflate_smem_bytes(), [&]() {
+    deflate_chunk_kernel(level, fmt == DCMP_FMT_ZLIB, nc, src, chunks.data(), outs.data(), slots.data(), tok.data(), &counter);
+  });
+  simt::launch(simt::dim3((unsigned)((n + 127) / 128)), simt::dim3(128), 0, [&]() {
+    deflate_plan_kernel(fmt, level, n, first.data(), outs.data(), chunks.data(), dst, doff, dcap, cdst.data(), written, status);
+  });
+  simt::launch(simt::dim3((unsigned)nc), simt::dim3(256), 0, [&]() {
+    deflate_gather_kernel(chunks.data(), outs.data(), slots.data(), cdst.data(), dst, doff);
   });
   return 0;
 }

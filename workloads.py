@@ -43,6 +43,8 @@ def _vocab():
 
 def text(nbytes, seed):
     """`nbytes` of word-soup text: Zipf vocabulary, sentence punctuation, line breaks."""
+    if nbytes <= 0:
+        return b""
     mat, mask, cdf = _vocab()
     rng = np.random.default_rng(seed)
     out = []
