@@ -4,6 +4,6 @@ module signatures.  `de`, `zl`, `gz`, `lzo` mirror lib/de.mli, lib/zl.mli, lib/g
 libdcmp_b200.so (include/dcmp.h); there is no CPU implementation in this package."""
 from . import _lib  # noqa: F401
 from .result import Ok, Error  # noqa: F401
-from . import batch, de, zl, lzo  # noqa: F401
+from . import batch, de, zl, gz, lzo  # noqa: F401
 
-__all__ = ["Ok", "Error", "batch", "de", "zl", "lzo"]
+__all__ = ["Ok", "Error", "batch", "de", "zl", "gz", "lzo"]

@@ -321,12 +321,79 @@ static int host_batch(dcmp_engine *e, device_batch_fn launch, int fmt, int64_t n
   return DCMP_API_OK;
 }
 
+// ---- gzip member framing (host side, as north_star prescribes) -----------------------------------
+static uint32_t crc32_fast(uint32_t crc, const uint8_t *p, int64_t n);
+
+// Gz.Inf header (lib/gz.ml:463-492, 358-461): only the magic is checked (not CM); FEXTRA's XLEN is read
+// big-endian (gz.ml:455); FHCRC covers the 10 fixed bytes + FNAME + FCOMMENT, not FEXTRA (gz.ml:399-440).
+static int gz_parse_header(const uint8_t *p, int64_t n, int64_t *hdr_len) {
+  if (n < 10) return DCMP_UNEXPECTED_END_OF_INPUT;
+  if (p[0] != 0x1f || p[1] != 0x8b) return DCMP_INVALID_GZIP_HEADER;
+  const int flg = p[3];
+  int64_t i = 10;
+  if (flg & 4) {
+    if (n - i < 2) return DCMP_UNEXPECTED_END_OF_INPUT;
+    int64_t xlen = ((int64_t)p[i] << 8) | p[i + 1];
+    i += 2;
+    if (n - i < xlen) return DCMP_UNEXPECTED_END_OF_INPUT;
+    i += xlen;
+  }
+  uint32_t crc = crc32_fast(0, p, 10);
+  for (int bit = 8; bit <= 16; bit <<= 1) { // FNAME, then FCOMMENT: zero-terminated
+    if (!(flg & bit)) continue;
+    int64_t j = i;
+    while (j < n && p[j] != 0) j++;
+    if (j >= n) return DCMP_UNEXPECTED_END_OF_INPUT;
+    crc = crc32_fast(crc, p + i, j + 1 - i);
+    i = j + 1;
+  }
+  if (flg & 2) {
+    if (n - i < 2) return DCMP_UNEXPECTED_END_OF_INPUT;
+    uint32_t have = ((uint32_t)p[i] << 8) | p[i + 1];
+    if ((crc >> 16) != have) return DCMP_INVALID_GZIP_HEADER_CHECKSUM;
+    i += 2;
+  }
+  *hdr_len = i;
+  return DCMP_OK;
+}
+
 int dcmp_inflate_batch(dcmp_engine *e, int fmt, int64_t n, const uint8_t *src_base, const int64_t *src_off,
                        const int64_t *src_len, uint8_t *dst_base, const int64_t *dst_off, const int64_t *dst_cap,
                        int64_t *consumed, int64_t *produced, int32_t *status) {
-  if (fmt != DCMP_FMT_RAW && fmt != DCMP_FMT_ZLIB) return DCMP_API_INVALID_ARGUMENT;
-  return host_batch(e, dcmp_inflate_batch_device, fmt, n, src_base, src_off, src_len, dst_base, dst_off, dst_cap,
-                    consumed, produced, status);
+  if (fmt == DCMP_FMT_RAW || fmt == DCMP_FMT_ZLIB)
+    return host_batch(e, dcmp_inflate_batch_device, fmt, n, src_base, src_off, src_len, dst_base, dst_off, dst_cap,
+                      consumed, produced, status);
+  if (fmt != DCMP_FMT_GZIP) return DCMP_API_INVALID_ARGUMENT;
+  // One gzip member per unit (Gz.Inf returns `End after one member, lib/gz.ml:344-356): header and trailer
+  // are handled here on the host, the DEFLATE body goes to the device as a raw stream.
+  if (n < 0) return DCMP_API_INVALID_ARGUMENT;
+  if (n == 0) return DCMP_API_OK;
+  if (!src_off || !src_len || !dst_off || !dst_cap || !consumed || !produced || !status || !src_base)
+    return DCMP_API_INVALID_ARGUMENT;
+  std::vector<int64_t> so((size_t)n), sl((size_t)n), hdr((size_t)n, 0);
+  std::vector<int32_t> pre((size_t)n);
+  for (int64_t k = 0; k < n; k++) {
+    if (src_len[k] < 0 || src_off[k] < 0) return DCMP_API_INVALID_ARGUMENT;
+    pre[k] = gz_parse_header(src_base + src_off[k], src_len[k], &hdr[k]);
+    so[k] = src_off[k] + (pre[k] == DCMP_OK ? hdr[k] : 0);
+    sl[k] = pre[k] == DCMP_OK ? src_len[k] - hdr[k] : 0;
+  }
+  int rc = host_batch(e, dcmp_inflate_batch_device, DCMP_FMT_RAW, n, src_base, so.data(), sl.data(), dst_base, dst_off,
+                      dst_cap, consumed, produced, status);
+  if (rc != DCMP_API_OK) return rc;
+  for (int64_t k = 0; k < n; k++) {
+    if (pre[k] != DCMP_OK) { status[k] = pre[k]; consumed[k] = 0; produced[k] = 0; continue; }
+    if (status[k] != DCMP_OK) continue;
+    const uint8_t *t = src_base + so[k] + consumed[k];
+    if (sl[k] - consumed[k] < 8) { status[k] = DCMP_UNEXPECTED_END_OF_INPUT; continue; }
+    const uint32_t crc = (uint32_t)t[0] | ((uint32_t)t[1] << 8) | ((uint32_t)t[2] << 16) | ((uint32_t)t[3] << 24);
+    const uint32_t isize = (uint32_t)t[4] | ((uint32_t)t[5] << 8) | ((uint32_t)t[6] << 16) | ((uint32_t)t[7] << 24);
+    const uint32_t got = crc32_fast(0, dst_base + dst_off[k], produced[k]);
+    if (got != crc) status[k] = DCMP_INVALID_CHECKSUM;             // lib/gz.ml:352-354: the checksum is compared first
+    else if ((uint32_t)produced[k] != isize) status[k] = DCMP_INVALID_INPUT_SIZE;
+    else consumed[k] += hdr[k] + 8;
+  }
+  return DCMP_API_OK;
 }
 
 int dcmp_lzo_uncompress_batch_device(dcmp_engine *e, int mode, int64_t n, const uint8_t *d_src_base,
@@ -521,20 +588,35 @@ uint32_t dcmp_adler32(uint32_t adler, const uint8_t *p, int64_t n) {
   return (b << 16) | a;
 }
 
-uint32_t dcmp_crc32(uint32_t crc, const uint8_t *p, int64_t n) {
-  static uint32_t table[256];
+static uint32_t crc32_fast(uint32_t crc, const uint8_t *p, int64_t n) {
+  static uint32_t T[8][256];
   static bool ready = false;
   if (!ready) {
     for (uint32_t i = 0; i < 256; i++) {
       uint32_t c = i;
       for (int k = 0; k < 8; k++) c = (c & 1) ? 0xedb88320u ^ (c >> 1) : c >> 1;
-      table[i] = c;
+      T[0][i] = c;
     }
+    for (uint32_t i = 0; i < 256; i++)
+      for (int t = 1; t < 8; t++) T[t][i] = (T[t - 1][i] >> 8) ^ T[0][T[t - 1][i] & 0xff];
     ready = true;
   }
   uint32_t c = crc ^ 0xffffffffu;
-  while (n--) c = table[(c ^ *p++) & 0xff] ^ (c >> 8);
+  while (n >= 8) {
+    uint32_t a, b;
+    memcpy(&a, p, 4);
+    memcpy(&b, p + 4, 4);
+    a ^= c;
+    c = T[7][a & 0xff] ^ T[6][(a >> 8) & 0xff] ^ T[5][(a >> 16) & 0xff] ^ T[4][a >> 24] ^ T[3][b & 0xff] ^
+        T[2][(b >> 8) & 0xff] ^ T[1][(b >> 16) & 0xff] ^ T[0][b >> 24];
+    p += 8;
+    n -= 8;
+  }
+  while (n-- > 0) c = T[0][(c ^ *p++) & 0xff] ^ (c >> 8);
   return c ^ 0xffffffffu;
 }
 
+uint32_t dcmp_crc32(uint32_t crc, const uint8_t *p, int64_t n) {
+  return crc32_fast(crc, p, n);
+}
 } // extern "C"
