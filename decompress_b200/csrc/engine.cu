@@ -21,6 +21,7 @@ int launch_inflate_parallel(int fmt, int64_t n, const uint8_t *src_base, const i
                             int64_t *produced, int32_t *status, unsigned long long *work_counter, uint32_t *tok_scratch,
                             int ctas, cudaStream_t stream);
 size_t inflate_parallel_scratch_bytes_per_cta();
+int inflate_parallel_ctas_per_sm();
 void launch_lzo_decode(int mode, int64_t n, const uint8_t *src_base, const int64_t *src_off, const int64_t *src_len,
                        uint8_t *dst_base, const int64_t *dst_off, const int64_t *dst_cap, int64_t *consumed,
                        int64_t *produced, int32_t *status, cudaStream_t stream);
@@ -143,7 +144,7 @@ int dcmp_engine_create(int device, dcmp_engine **out) {
   cudaError_t se = cudaStreamCreateWithFlags(&eng->stream, cudaStreamNonBlocking);
   if (se != cudaSuccess) { set_err("cudaStreamCreate", se); delete eng; return DCMP_API_CUDA_ERROR; }
   cudaDeviceGetAttribute(&eng->sm_count, cudaDevAttrMultiProcessorCount, device);
-  eng->par_ctas = 2 * (eng->sm_count > 0 ? eng->sm_count : 148);
+  eng->par_ctas = dcmp::inflate_parallel_ctas_per_sm() * (eng->sm_count > 0 ? eng->sm_count : 148);
   se = cudaMalloc(&eng->d_scratch, 256 + (size_t)eng->par_ctas * dcmp::inflate_parallel_scratch_bytes_per_cta());
   if (se != cudaSuccess) { set_err("cudaMalloc(scratch)", se); cudaStreamDestroy(eng->stream); delete eng; return DCMP_API_OUT_OF_MEMORY; }
   const char *m = getenv("DCMP_INFLATE_MODE");

@@ -26,14 +26,16 @@
 //                           gives every lane its output offset;
 //   D  symbol replay        every lane replays its tokens into a 16-bit symbol buffer at
 //                           its output offset.  A back-reference into the 32 KiB history
-//                           (earlier rounds; a byte ring in shared memory) or into the
-//                           lane's own output is copied; a back-reference into bytes that
-//                           ANOTHER lane produces in this round is not waited for: the
-//                           lane stores a marker 256 + (index of the source symbol);
+//                           (earlier rounds: the stream's own output, read back through L2
+//                           with .cg loads — keeping it out of shared memory buys a third CTA
+//                           per SM; DCMP_HIST_GLOBAL=0 keeps a shared byte ring instead) is
+//                           copied; a back-reference into bytes produced in this round — by
+//                           another lane or by this one — is not waited for: the lane stores
+//                           a marker 256 + (index of the source symbol);
 //   E  resolve + drain      16 symbols per thread: markers are chased to a literal
 //                           (markers only point backwards, chains are short), the 16
-//                           bytes leave through one 128-bit store to HBM and one to the
-//                           history ring; Adler-32 is folded over the same registers.
+//                           bytes leave through one 128-bit store to HBM; Adler-32 is
+//                           folded over the same registers.
 //
 // Anything that is not the happy path — stored blocks, malformed input, exotic code sets, an
 // output buffer that is too small — makes the CTA give the stream up with status
@@ -47,10 +49,10 @@
 namespace dcmp {
 
 #ifndef DCMP_PT
-#define DCMP_PT 352
+#define DCMP_PT 256
 #endif
 #ifndef DCMP_SUB_WORDS
-#define DCMP_SUB_WORDS 7
+#define DCMP_SUB_WORDS 9
 #endif
 
 constexpr int PT = DCMP_PT;               // threads (= lanes = sub-chunks per round)
@@ -65,7 +67,13 @@ constexpr int CKPT_SHIFT = 5;             // one checkpoint per 32-bit window of
 constexpr int NCKPT = (SUB_BITS >> CKPT_SHIFT) + 1;
 constexpr int HIST = 32768;               // history ring (the sliding window, de.ml:439-440) in bytes
 constexpr int HIST_MASK = HIST - 1;
-constexpr int RSYM = 28 * 1024;           // symbols one round may produce (+ up to 15 of alignment bias)
+#ifndef DCMP_HIST_GLOBAL
+#define DCMP_HIST_GLOBAL 1                // 1: read the history from the output buffer in HBM/L2 instead of a shared ring
+#endif
+#ifndef DCMP_RSYM_K
+#define DCMP_RSYM_K 26
+#endif
+constexpr int RSYM = DCMP_RSYM_K * 1024;  // symbols one round may produce (+ up to 15 of alignment bias)
 constexpr int SYM_SLOTS = RSYM + 32;
 constexpr int WIN_WORDS = 3 + SUB_WORDS * PT + 4;        // staged input per round
 constexpr int WIN_BYTES = (WIN_WORDS * 4 + 15) & ~15;
@@ -139,7 +147,9 @@ struct HuffMeta {      // canonical-code description for codes longer than the r
 
 struct ParSmem {
   __align__(16) uint16_t sym[SYM_SLOTS];   // phase D/E: symbols of the round; phase A/B: checkpoints [NCKPT][PT] u32
+#if !DCMP_HIST_GLOBAL
   __align__(16) uint8_t ring[HIST];        // last 32 KiB of output, indexed by (global address & HIST_MASK)
+#endif
   __align__(16) uint32_t win[WIN_BYTES / 4 + 4]; // staged compressed input (TMA destination)
   uint32_t lit[1 << LIT_ROOT];
   uint32_t dist[1 << DIST_ROOT];
@@ -179,7 +189,11 @@ struct ParSmem {
   int abort_round;               // a lane met an invalid distance: the general kernel reports it
   __align__(8) uint64_t mbar;
 };
+#if DCMP_HIST_GLOBAL
+static_assert(sizeof(ParSmem) <= 74 * 1024, "three CTAs per SM need <= ~74.6 KiB each");
+#else
 static_assert(sizeof(ParSmem) <= 112 * 1024, "two CTAs per SM need <= ~113 KiB each");
+#endif
 
 // ------------------------------------------------------------------------------------------
 // bit cursor over a lane's sub-chunk inside the staged window
@@ -488,7 +502,7 @@ __device__ void stage_window(ParSmem &S, const uint8_t *g, int bytes, int valid,
 }
 
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(PT, 2)
+__global__ void __launch_bounds__(PT, DCMP_HIST_GLOBAL ? 3 : 2)
 inflate_parallel_kernel(int fmt, int64_t nstreams, const uint8_t *src_base, const int64_t *src_off,
                         const int64_t *src_len, uint8_t *dst_base, const int64_t *dst_off, const int64_t *dst_cap,
                         int64_t *consumed, int64_t *produced, int32_t *status, unsigned long long *work_counter,
@@ -884,7 +898,13 @@ inflate_parallel_kernel(int fmt, int64_t nstreams, const uint8_t *src_base, cons
         const int delta = HEAD_CAP + d_k - d_nh; // token index -> slot for the speculative part
         const uint4 *head_lane = reinterpret_cast<const uint4 *>(tok_scratch + ((size_t)blockIdx.x * PT + d_owner) * TOK_SLOTS);
         STAT(if (tid < n_valid) { g_stats.head_tokens += d_nh; g_stats.used_tokens += total_tok; } long iters = 0;)
+#if DCMP_HIST_GLOBAL
+        // history = the stream's own output in HBM/L2; symbol index s <-> address G0 + s.  L2-coherent loads
+        // (.cg): the bytes were stored by this CTA in earlier rounds, a barrier ago at least.
+        const uint32_t *hist32 = reinterpret_cast<const uint32_t *>(G0 - ((uintptr_t)G0 & 3)); // G0 is 16-aligned: no-op
+#else
         const uint32_t *ring32 = reinterpret_cast<const uint32_t *>(S.ring);
+#endif
         int ti = 0;
         int32_t i = (int32_t)(my_off - out0 + bias); // next symbol to write
         int32_t s = 0;                // next source symbol of the pending match
@@ -936,9 +956,17 @@ inflate_parallel_kernel(int fmt, int64_t nstreams, const uint8_t *src_base, cons
           const uint32_t wi0 = r >> 2;
           uint32_t w0 = 0, w1 = 0, w2 = 0;
           if (in_hist && rem > 0u) {
+#if DCMP_HIST_GLOBAL
+            const int32_t gw = s >> 2; // word index relative to G0 (negative: before this round)
+            const uint32_t span = ((uint32_t)s & 3u) + n; // only words that hold a source byte are touched
+            w0 = __ldcg(hist32 + gw);
+            if (span > 4u) w1 = __ldcg(hist32 + gw + 1);
+            if (span > 8u) w2 = __ldcg(hist32 + gw + 2);
+#else
             w0 = ring32[wi0 & (HIST / 4 - 1)];
             w1 = ring32[(wi0 + 1u) & (HIST / 4 - 1)];
             w2 = ring32[(wi0 + 2u) & (HIST / 4 - 1)];
+#endif
           }
           const uint32_t sh8 = 8u * (r & 3u);
           const uint32_t ha = __funnelshift_r(w0, w1, sh8), hb = __funnelshift_r(w1, w2, sh8);
@@ -954,7 +982,11 @@ inflate_parallel_kernel(int fmt, int64_t nstreams, const uint8_t *src_base, cons
               const int32_t sk = s + (int32_t)(dist < n ? k % dist : k);
               uint32_t v;
               if (sk >= (int32_t)bias) { v = 256u + (uint32_t)sk; STAT(g_stats.markers++;) }
+#if DCMP_HIST_GLOBAL
+              else { v = __ldcg(G0 + sk); STAT(g_stats.hist_bytes++;) }
+#else
               else { v = S.ring[(g0_low + (uint32_t)sk) & HIST_MASK]; STAT(g_stats.hist_bytes++;) }
+#endif
               S.sym[i + (int32_t)k] = (uint16_t)v;
             }
           } else {
@@ -1021,7 +1053,9 @@ inflate_parallel_kernel(int fmt, int64_t nstreams, const uint8_t *src_base, cons
           if (full) {
             uint4 q = make_uint4(wv[0], wv[1], wv[2], wv[3]);
             *(uint4 *)(G0 + i0) = q;
+#if !DCMP_HIST_GLOBAL
             *(uint4 *)(S.ring + ((g0_low + i0) & HIST_MASK)) = q;
+#endif
           } else {
 #pragma unroll
             for (int k = 0; k < 4; k++) {
@@ -1032,7 +1066,9 @@ inflate_parallel_kernel(int fmt, int64_t nstreams, const uint8_t *src_base, cons
                 if (idx >= bias && idx < E) {
                   uint8_t b = (uint8_t)(wv[k] >> (8 * j));
                   G0[idx] = b;
+#if !DCMP_HIST_GLOBAL
                   S.ring[(g0_low + idx) & HIST_MASK] = b;
+#endif
                   m |= 0xffu << (8 * j);
                 }
               }
@@ -1113,6 +1149,7 @@ inflate_parallel_kernel(int fmt, int64_t nstreams, const uint8_t *src_base, cons
 }
 
 size_t inflate_parallel_smem_bytes() { return sizeof(ParSmem) + 128; }
+int inflate_parallel_ctas_per_sm() { return DCMP_HIST_GLOBAL ? 3 : 2; }
 // bytes of token scratch one CTA needs (global memory, stays L2-resident)
 size_t inflate_parallel_scratch_bytes_per_cta() { return (size_t)TOK_SLOTS * PT * sizeof(uint32_t) + 64; }
 

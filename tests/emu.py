@@ -18,7 +18,8 @@ def build():
     if os.path.exists(_SO) and all(os.path.getmtime(s) <= os.path.getmtime(_SO) for s in srcs):
         return
     os.makedirs(os.path.dirname(_SO), exist_ok=True)
-    subprocess.check_call(["g++", "-O1", "-g", "-std=c++17", "-fPIC", "-shared", "-DDCMP_EMU",
+    extra = os.environ.get("DCMP_EMU_FLAGS", "").split()
+    subprocess.check_call(["g++", "-O1", "-g", "-std=c++17", "-fPIC", "-shared", "-DDCMP_EMU"] + extra + [
                            "-I" + os.path.join(ROOT, "tests", "simt_emu"), "-I" + os.path.join(ROOT, "decompress_b200", "csrc"),
                            "-o", _SO, srcs[0], srcs[1]])
 
