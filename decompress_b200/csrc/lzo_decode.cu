@@ -6,7 +6,10 @@
 // interprets one byte at a time through a free-monad DSL; here the warp parses the opcode
 // stream uniformly from a shared-memory cache of the input (filled by coalesced loads) and
 // spreads the two byte movers — literal runs input->output and back-references output->output
-// — over its 32 lanes.  Blocks are independent, so a batch shards one block per warp.
+// — over its 32 lanes.  The sliding window (LZO1X distances reach 49151) is a 64 KiB ring in
+// shared memory: a back-reference costs a shared-memory round trip instead of an L2 one, and
+// every produced byte is stored once to the ring and once (fire and forget) to HBM.  Blocks
+// are independent, so a batch shards one block per single-warp CTA, three CTAs per SM.
 //
 // Error vocabulary (include/dcmp.h): DCMP_LZO_MALFORMED / _INVALID_ARGUMENT / _INVALID_DICTIONARY.
 // mode 0 = Lzo.uncompress (Out_of_bound -> Invalid_argument, lzo.ml:395-403)
@@ -18,8 +21,10 @@
 
 namespace dcmp {
 
-constexpr int LZO_WARPS = 4;
-constexpr int LZO_CACHE = 512; // input bytes cached per warp
+constexpr int LZO_WARPS = 1;    // one warp per CTA: 64 KiB ring + input cache each, 3 CTAs per SM
+constexpr int LZO_CACHE = 2048; // input bytes cached per warp
+constexpr int LZO_RING = 65536;
+constexpr int LZO_RING_MASK = LZO_RING - 1;
 enum : int { LZ_OK = 0, LZ_MALFORMED = 1, LZ_OOB = 2, LZ_DICT = 3, LZ_OUTFULL = 4 };
 
 struct LzoWarp {
@@ -29,6 +34,7 @@ struct LzoWarp {
   int64_t o_pos, o_len;
   int64_t cbase; // first input position held in the cache (-1: empty)
   uint8_t *cache;
+  uint8_t *ring; // last 64 KiB of output, indexed by (o_pos & LZO_RING_MASK)
   int lane, mode;
 
   // byte at input position p (p < i_len), through the cache
@@ -45,7 +51,12 @@ struct LzoWarp {
   __device__ int transmit(int64_t len) {
     if (len < 0 || i_pos > i_len - len) return LZ_OOB;
     if (o_pos > o_len - len) return mode == 1 ? LZ_OUTFULL : LZ_OOB;
-    for (int64_t k = lane; k < len; k += 32) out[o_pos + k] = in[i_pos + k];
+    for (int64_t k = lane; k < len; k += 32) {
+      const int64_t p = i_pos + k;
+      const uint8_t b = (p >= cbase && p < cbase + LZO_CACHE) ? cache[p - cbase] : in[p];
+      ring[(o_pos + k) & LZO_RING_MASK] = b;
+      out[o_pos + k] = b;
+    }
     i_pos += len;
     o_pos += len;
     return LZ_OK;
@@ -57,7 +68,11 @@ struct LzoWarp {
     else if (s < 0) return LZ_OOB;
     if (o_pos > o_len - len) return mode == 1 ? LZ_OUTFULL : LZ_OOB;
     __syncwarp(); // bytes stored by other lanes before this point are visible
-    for (int64_t k = lane; k < len; k += 32) out[o_pos + k] = out[s + (off >= len ? k : k % off)];
+    for (int64_t k = lane; k < len; k += 32) {
+      const uint8_t b = ring[(s + (off >= len ? k : k % off)) & LZO_RING_MASK];
+      ring[(o_pos + k) & LZO_RING_MASK] = b;
+      out[o_pos + k] = b;
+    }
     o_pos += len;
     return LZ_OK;
   }
@@ -155,7 +170,8 @@ __global__ void __launch_bounds__(LZO_WARPS * 32)
 lzo_decode_kernel(int mode, int64_t nblocks, const uint8_t *src_base, const int64_t *src_off, const int64_t *src_len,
                   uint8_t *dst_base, const int64_t *dst_off, const int64_t *dst_cap, int64_t *consumed,
                   int64_t *produced, int32_t *status) {
-  __shared__ uint8_t cache[LZO_WARPS][LZO_CACHE];
+  DCMP_DYN_SMEM(smem_raw);
+  uint8_t(*cache)[LZO_CACHE] = reinterpret_cast<uint8_t(*)[LZO_CACHE]>(smem_raw + (size_t)LZO_WARPS * LZO_RING);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t k = (int64_t)blockIdx.x * LZO_WARPS + warp;
   if (k >= nblocks) return;
@@ -168,6 +184,7 @@ lzo_decode_kernel(int mode, int64_t nblocks, const uint8_t *src_base, const int6
   w.o_len = dst_cap[k];
   w.cbase = -(int64_t)LZO_CACHE - 1;
   w.cache = cache[warp];
+  w.ring = smem_raw + (size_t)warp * LZO_RING;
   w.lane = lane;
   w.mode = mode;
   int r = lzo_run(w);
@@ -190,7 +207,13 @@ void launch_lzo_decode(int mode, int64_t n, const uint8_t *src_base, const int64
                        int64_t *produced, int32_t *status, cudaStream_t stream) {
   if (n <= 0) return;
   const int64_t blocks = (n + LZO_WARPS - 1) / LZO_WARPS;
-  lzo_decode_kernel<<<(unsigned)blocks, LZO_WARPS * 32, 0, stream>>>(mode, n, src_base, src_off, src_len, dst_base,
+  const size_t smem = (size_t)LZO_WARPS * (LZO_RING + LZO_CACHE);
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(lzo_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    configured = true;
+  }
+  lzo_decode_kernel<<<(unsigned)blocks, LZO_WARPS * 32, smem, stream>>>(mode, n, src_base, src_off, src_len, dst_base,
                                                                     dst_off, dst_cap, consumed, produced, status);
 }
 #endif

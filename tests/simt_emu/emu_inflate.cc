@@ -41,7 +41,7 @@ int emu_inflate_batch(int mode, int fmt, int64_t n, const uint8_t *src, const in
 int emu_lzo_batch(int mode, int64_t n, const uint8_t *src, const int64_t *soff, const int64_t *slen, uint8_t *dst,
                   const int64_t *doff, const int64_t *dcap, int64_t *cons, int64_t *prod, int32_t *status) {
   using namespace dcmp;
-  simt::launch(simt::dim3((unsigned)((n + LZO_WARPS - 1) / LZO_WARPS)), simt::dim3(LZO_WARPS * 32), 0, [&]() {
+  simt::launch(simt::dim3((unsigned)((n + LZO_WARPS - 1) / LZO_WARPS)), simt::dim3(LZO_WARPS * 32), (size_t)LZO_WARPS * (LZO_RING + LZO_CACHE), [&]() {
     lzo_decode_kernel(mode, n, src, soff, slen, dst, doff, dcap, cons, prod, status);
   });
   return 0;
