@@ -74,3 +74,146 @@ class Def:
             if st == 0:
                 return Ok(wr.value)
             return Error(_lib.STATUS_TAG.get(st, st))
+
+
+# ---- streaming facade ---------------------------------------------------------------------------------------------
+class Window:
+    """De.window (de.mli:59-75).  The GPU engine keeps its own sliding window; the value only carries `bits`."""
+
+    def __init__(self, bits=15):
+        self.bits = bits
+
+
+def make_window(bits=15):
+    return Window(bits)
+
+
+class _InfDecoder:
+    """De.Inf.decoder (de.mli:82-148) over the batch engine: the non-blocking `Await / `Flush / `End / `Malformed
+    protocol is a host-side state machine (as in the reference, de.ml:651-753); the inflate itself runs on the GPU
+    once the whole stream has been supplied (`src d buf off 0` signals end of input, de.ml:736-742).
+
+    Signal sequence for a given output buffer `o`: `Await until the input is complete, then `Flush each time `o`
+    is full (read o[0 .. len(o) - dst_rem()), call flush()), `End with the last partial buffer — the output side of
+    what test/test.ml:1536-1568 pins.  On malformed input the bytes decoded before the error are flushed first,
+    then `Malformed msg with the reference's message (de.ml:702-730)."""
+
+    def __init__(self, src, o, w=None, engine=None, fmt=_lib.FMT_RAW):
+        self._o = _as_u8(o, writable=True)
+        self._eng = engine
+        self._fmt = fmt
+        self._manual = src == "Manual"
+        self._chunks = []
+        self._eof = not self._manual
+        if not self._manual:
+            kind, data = src  # ("String", bytes)
+            assert kind == "String"
+            self._chunks.append(bytes(data))
+        self._out = None
+        self._served = 0
+        self._o_pos = 0
+        self._status = 0
+        self._consumed = 0
+        self._done = False
+        self._adler = 1
+
+    # De.Inf.src (de.mli:118-124)
+    def src(self, buf, off, length):
+        if off < 0 or length < 0 or off + length > len(buf):
+            raise ValueError("Invalid bounds (off: %d, len: %d)" % (off, length))  # de.ml:736-737
+        if length == 0:
+            self._eof = True
+        else:
+            self._chunks.append(bytes(buf[off:off + length]))
+
+    def dst_rem(self):
+        return len(self._o) - self._o_pos
+
+    def src_rem(self):
+        if self._out is None:
+            return 0
+        return max(0, sum(len(c) for c in self._chunks) - self._consumed)
+
+    def flush(self):
+        self._o_pos = 0
+
+    def checksum(self):
+        return self._adler
+
+    def _run(self):
+        import zlib as _z
+        from . import batch
+        data = b"".join(self._chunks)
+        cap = max(4 * len(data), 1 << 16)
+        while True:
+            st, cons, prod, out = batch.inflate_streams([data], [cap], fmt=self._fmt, engine=self._eng)[0]
+            if st == 2 and cap < (1 << 34):  # Unexpected_end_of_output: the provisional buffer was too small
+                cap *= 4
+                continue
+            break
+        self._status, self._consumed, self._out = st, cons, out
+        self._adler = _z.adler32(out)
+
+    def decode(self):
+        if self._done:
+            return "End" if self._status == 0 else ("Malformed", _lib.lib().dcmp_status_string(self._status).decode())
+        if self._out is None:
+            if not self._eof:
+                return "Await"
+            self._run()
+        if self._o_pos == len(self._o) and self._served < len(self._out):
+            return "Flush"  # idempotent until the caller flushes (zl.ml:288-291)
+        n = min(len(self._o) - self._o_pos, len(self._out) - self._served)
+        self._o[self._o_pos:self._o_pos + n] = np.frombuffer(self._out, dtype=np.uint8)[self._served:self._served + n]
+        self._o_pos += n
+        self._served += n
+        if self._served < len(self._out):
+            return "Flush"
+        self._done = True
+        if self._status == 0:
+            return "End"
+        return ("Malformed", _lib.lib().dcmp_status_string(self._status).decode())
+
+
+def _decoder(src, o, w=None, engine=None):
+    return _InfDecoder(src, o, w, engine)
+
+
+Inf.decoder = staticmethod(_decoder)
+
+
+class Higher:
+    """De.Higher (de.mli:533-665): refill/flush callback loops over the streaming facade."""
+
+    @staticmethod
+    def uncompress(w, refill, flush, i, o, engine=None):
+        d = Inf.decoder("Manual", o, w, engine=engine)
+        while True:
+            r = d.decode()
+            if r == "Await":
+                n = refill(i)
+                d.src(i, 0, n)
+            elif r == "Flush":
+                flush(o, len(o) - d.dst_rem())
+                d.flush()
+            elif r == "End":
+                flush(o, len(o) - d.dst_rem())
+                return Ok(None)
+            else:
+                return Error(("Msg", r[1]))
+
+    @staticmethod
+    def of_string(o, w, s, flush, engine=None):
+        d = Inf.decoder(("String", s), o, w, engine=engine)
+        while True:
+            r = d.decode()
+            if r == "Flush":
+                flush(o, len(o) - d.dst_rem())
+                d.flush()
+            elif r == "End":
+                flush(o, len(o) - d.dst_rem())
+                return Ok(None)
+            elif r == "Await":
+                raise AssertionError("a `String source never awaits")
+            else:
+                return Error(("Msg", r[1]))

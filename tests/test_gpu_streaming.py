@@ -1,0 +1,96 @@
+"""The streaming facade (De.Inf.decoder / De.Higher over the batch engine) against the reference's streaming KATs
+(test/test.ml:97-300, 302-767: input -> output bytes or `Malformed message) and its signal protocol."""
+import json
+import os
+import zlib
+
+import numpy as np
+import pytest
+
+import workloads
+from decompress_b200 import Ok, _lib, de
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.fixture(scope="module")
+def eng():
+    return _lib.Engine(0)
+
+
+def _vectors():
+    with open(os.path.join(G, "inflate_stream.json")) as f:
+        return json.load(f)["vectors"]
+
+
+@pytest.mark.parametrize("v", _vectors(), ids=lambda v: v["name"])
+def test_stream_goldens_through_the_decoder(v, eng):
+    o = de.bigstring_create(de.io_buffer_size)
+    d = de.Inf.decoder(("String", bytes.fromhex(v["src"])), o, de.make_window(bits=15), engine=eng)
+    out = bytearray()
+    while True:
+        r = d.decode()
+        if r == "Flush":
+            out += o[:len(o) - d.dst_rem()].tobytes()
+            d.flush()
+        elif r == "End":
+            out += o[:len(o) - d.dst_rem()].tobytes()
+            assert "malformed" not in v, v["cite"]
+            break
+        else:
+            assert r[0] == "Malformed" and r[1] == v["malformed"], (r, v["cite"])
+            break
+    if "out" in v and "malformed" not in v:
+        assert bytes(out) == bytes.fromhex(v["out"]), v["cite"]
+
+
+def test_signal_protocol_manual_source_small_output_buffer(eng):
+    """test/test.ml:1515-1568: byte-per-byte feeding, a 4-byte output buffer, idempotent `Flush."""
+    txt = workloads.text(1000, 4)
+    co = zlib.compressobj(6, zlib.DEFLATED, -15)
+    comp = co.compress(txt) + co.flush()
+    o = de.bigstring_create(4)
+    d = de.Inf.decoder("Manual", o, de.make_window(bits=15), engine=eng)
+    out, sigs = bytearray(), []
+    k = 0
+    while True:
+        r = d.decode()
+        sigs.append(r if isinstance(r, str) else r[0])
+        if r == "Await":
+            d.src(comp, k, 1 if k < len(comp) else 0)   # one byte at a time, then end of input
+            k += 1
+        elif r == "Flush":
+            assert d.decode() == "Flush"                # nothing moves until flush (zl.ml:288-291)
+            out += o[:4 - d.dst_rem()].tobytes()
+            d.flush()
+        else:
+            out += o[:4 - d.dst_rem()].tobytes()
+            break
+    assert r == "End" and bytes(out) == txt
+    assert sigs.count("Await") == len(comp) + 1 and sigs.count("Flush") == 250 - 1 and sigs[-1] == "End"
+    assert d.checksum() == zlib.adler32(txt)
+
+
+def test_higher_uncompress_and_of_string(eng):
+    txt = workloads.text(300000, 8)
+    co = zlib.compressobj(6, zlib.DEFLATED, -15)
+    comp = co.compress(txt) + co.flush()
+    i, o = de.bigstring_create(de.io_buffer_size), de.bigstring_create(de.io_buffer_size)
+    pos, out = [0], bytearray()
+
+    def refill(buf):
+        n = min(len(buf), len(comp) - pos[0])
+        buf[:n] = np.frombuffer(comp, dtype=np.uint8)[pos[0]:pos[0] + n]
+        pos[0] += n
+        return n
+
+    def flush(buf, n):
+        out.extend(buf[:n].tobytes())
+
+    assert de.Higher.uncompress(de.make_window(bits=15), refill, flush, i, o, engine=eng) == Ok(None)
+    assert bytes(out) == txt
+    out.clear()
+    assert de.Higher.of_string(o, de.make_window(bits=15), comp, flush, engine=eng) == Ok(None) and bytes(out) == txt
+    r = de.Higher.of_string(o, de.make_window(bits=15), b"\x06", flush, engine=eng)
+    assert not r.is_ok() and r.error == ("Msg", "Invalid kind of block")
