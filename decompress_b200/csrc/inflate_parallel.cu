@@ -910,10 +910,22 @@ inflate_parallel_kernel(int fmt, int64_t nstreams, const uint8_t *src_base, cons
         int32_t s = 0;                // next source symbol of the pending match
         uint32_t rem = 0;             // symbols the pending match still owes
         uint32_t dist = 0;
-        uint4 cur = make_uint4(0, 0, 0, 0), nxt = make_uint4(0, 0, 0, 0);
+        // token batches (four tokens, 128 bits) are fetched two batches ahead of their use
+        uint4 cur = make_uint4(0, 0, 0, 0), nx1 = make_uint4(0, 0, 0, 0), nx2 = make_uint4(0, 0, 0, 0);
         int cur_b = -1;
         bool active = total_tok > 0;
-        if (active) nxt = d_nh > 0 ? head_lane[d_h0 >> 2] : tok_lane[delta >> 2];
+        auto slot_of = [&](int t) { return t < d_nh ? t + d_h0 : t + delta; };
+        auto load_batch = [&](int t) { return t < d_nh ? head_lane[(t + d_h0) >> 2] : tok_lane[(t + delta) >> 2]; };
+        auto next_batch_start = [&](int t) { // first token of the batch after the one that holds token t
+          int t2 = t + 4 - (slot_of(t) & 3);
+          if (t < d_nh && t2 > d_nh) t2 = d_nh;
+          return t2;
+        };
+        if (active) {
+          nx1 = load_batch(0);
+          const int t1 = next_batch_start(0);
+          if (t1 < total_tok) nx2 = load_batch(t1);
+        }
         while (__any_sync(0xffffffffu, active)) {
           STAT(if (active) iters++;)
           // -- next token, for the lanes that finished the previous one
@@ -921,13 +933,16 @@ inflate_parallel_kernel(int fmt, int64_t nstreams, const uint8_t *src_base, cons
           if (fetch && ti == total_tok) { active = false; fetch = false; }
           uint32_t t = 0;
           if (fetch) {
-            const int slot = ti < d_nh ? ti + d_h0 : ti + delta;
+            const int slot = slot_of(ti);
             if ((slot >> 2) != cur_b) {
-              cur = nxt;
+              cur = nx1;
+              nx1 = nx2;
               cur_b = slot >> 2;
-              int t2 = ti + 4 - (slot & 3);          // first token of the batch after this one
-              if (ti < d_nh && t2 > d_nh) t2 = d_nh;
-              if (t2 < total_tok) nxt = t2 < d_nh ? head_lane[(t2 + d_h0) >> 2] : tok_lane[(t2 + delta) >> 2];
+              const int ta = next_batch_start(ti);
+              if (ta < total_tok) {
+                const int tb = next_batch_start(ta);
+                if (tb < total_tok) nx2 = load_batch(tb);
+              }
             }
             t = batch_get(cur, slot & 3);
             ti++;
@@ -1025,30 +1040,29 @@ inflate_parallel_kernel(int fmt, int64_t nstreams, const uint8_t *src_base, cons
           uint32_t pr[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
           uint32_t wv[4];
           const bool any_marker = ((qa.x | qa.y | qa.z | qa.w | qb.x | qb.y | qb.z | qb.w) & 0xff00ff00u) != 0u;
-#pragma unroll
-          for (int k = 0; k < 4; k++) {
-            uint32_t w = 0;
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-              uint32_t v = (pr[2 * k + (j >> 1)] >> (16 * (j & 1))) & 0xffffu;
-              STAT(long hops = 0;)
-              while (v >= 256u) { v = S.sym[v - 256u]; STAT(hops++;) }
-              STAT(g_stats.chase_hops += hops; if (hops > g_stats.chase_max) g_stats.chase_max = hops;)
-              w |= v << (8 * j);
-            }
-            wv[k] = w;
-          }
-          // path compression: later chases that land here stop after one hop (a racing reader sees
-          // either the old marker or the final literal — both lead to the same byte)
           if (any_marker) {
-            uint4 ra, rb;
-            ra.x = __byte_perm(wv[0], 0u, 0x4140); ra.y = __byte_perm(wv[0], 0u, 0x4342);
-            ra.z = __byte_perm(wv[1], 0u, 0x4140); ra.w = __byte_perm(wv[1], 0u, 0x4342);
-            rb.x = __byte_perm(wv[2], 0u, 0x4140); rb.y = __byte_perm(wv[2], 0u, 0x4342);
-            rb.z = __byte_perm(wv[3], 0u, 0x4140); rb.w = __byte_perm(wv[3], 0u, 0x4342);
-            *(uint4 *)(S.sym + i0) = ra;
-            *(uint4 *)(S.sym + i0 + 8) = rb;
+            // chase in rounds: every unresolved symbol of the chunk hops once per round, so up to 16 independent
+            // shared-memory loads are in flight instead of one dependent chain per symbol
+            bool pending = true;
+            while (pending) {
+              uint32_t acc = 0;
+#pragma unroll
+              for (int q = 0; q < 8; q++) {
+                uint32_t lo = pr[q] & 0xffffu, hi = pr[q] >> 16;
+                if (lo >= 256u) { lo = S.sym[lo - 256u]; STAT(g_stats.chase_hops++;) }
+                if (hi >= 256u) { hi = S.sym[hi - 256u]; STAT(g_stats.chase_hops++;) }
+                pr[q] = lo | (hi << 16);
+                acc |= pr[q];
+              }
+              pending = (acc & 0xff00ff00u) != 0u;
+            }
+            // path compression: later chases that land here stop after one hop (a racing reader sees
+            // either the old marker or the final literal — both lead to the same byte)
+            *(uint4 *)(S.sym + i0) = make_uint4(pr[0], pr[1], pr[2], pr[3]);
+            *(uint4 *)(S.sym + i0 + 8) = make_uint4(pr[4], pr[5], pr[6], pr[7]);
           }
+#pragma unroll
+          for (int k = 0; k < 4; k++) wv[k] = __byte_perm(pr[2 * k], pr[2 * k + 1], 0x6420);
           const bool full = i0 >= bias && i0 + 16u <= E;
           if (full) {
             uint4 q = make_uint4(wv[0], wv[1], wv[2], wv[3]);
