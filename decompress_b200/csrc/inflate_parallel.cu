@@ -121,7 +121,7 @@ static EmuStats g_stats;
 #endif
 
 enum : int { X_NORMAL = 0, X_EOB = 1, X_CAP = 2, X_ERR = 3, X_NOSYNC = 4 };
-enum : int { NEXT_CONTINUE = 0, NEXT_HEADER = 1, NEXT_FINISH = 2, NEXT_RETRY = 3 };
+enum : int { NEXT_CONTINUE = 0, NEXT_HEADER = 1, NEXT_FINISH = 2, NEXT_RETRY = 3, NEXT_STORED = 4 };
 
 // token: [23] match flag; match: [22:8] distance-1, [7:0] length-3;  literal: [7:0] byte
 // checkpoint: [4:0] bit offset of the first token start inside the 32-bit window,
@@ -182,6 +182,7 @@ struct ParSmem {
   int64_t base_bit;              // next bit of the deflate stream to decode
   uint32_t out_pos;              // bytes produced so far
   int last_block, next, status;
+  uint32_t stored_rem;           // payload bytes of the current stored block still to copy
   int n_valid;                   // lanes accepted in this round
   uint32_t round_out;            // bytes produced by this round
   uint32_t adler_a, adler_b;
@@ -501,6 +502,112 @@ __device__ void stage_window(ParSmem &S, const uint8_t *g, int bytes, int valid,
   __syncthreads();
 }
 
+// ---- E: resolve markers, drain to HBM (and to the history ring), fold Adler-32.  All threads call.
+__device__ __forceinline__ void phase_e_drain(ParSmem &S, const int fmt, uint8_t *const G0, const uint32_t g0_low,
+                                              const uint32_t bias, const uint32_t E, const uint32_t out0,
+                                              const uint32_t round_out, const int tid, const int lane, const int warp) {
+        const uint32_t nchunks = (E + 15u) >> 4;
+        unsigned long long s_sum = 0;
+        long long b_sum = 0;
+        for (uint32_t c = (uint32_t)tid; c < nchunks; c += PT) {
+          const uint32_t i0 = c << 4;
+          uint4 qa = *(const uint4 *)(S.sym + i0);
+          uint4 qb = *(const uint4 *)(S.sym + i0 + 8);
+          uint32_t pr[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
+          uint32_t wv[4];
+          const bool any_marker = ((qa.x | qa.y | qa.z | qa.w | qb.x | qb.y | qb.z | qb.w) & 0xff00ff00u) != 0u;
+          if (any_marker) {
+            // chase in rounds: every unresolved symbol of the chunk hops once per round, so up to 16 independent
+            // shared-memory loads are in flight instead of one dependent chain per symbol
+            bool pending = true;
+            while (pending) {
+              uint32_t acc = 0;
+#pragma unroll
+              for (int q = 0; q < 8; q++) {
+                uint32_t lo = pr[q] & 0xffffu, hi = pr[q] >> 16;
+                if (lo >= 256u) { lo = S.sym[lo - 256u]; STAT(g_stats.chase_hops++;) }
+                if (hi >= 256u) { hi = S.sym[hi - 256u]; STAT(g_stats.chase_hops++;) }
+                pr[q] = lo | (hi << 16);
+                acc |= pr[q];
+              }
+              pending = (acc & 0xff00ff00u) != 0u;
+            }
+            // path compression: later chases that land here stop after one hop (a racing reader sees
+            // either the old marker or the final literal — both lead to the same byte)
+            *(uint4 *)(S.sym + i0) = make_uint4(pr[0], pr[1], pr[2], pr[3]);
+            *(uint4 *)(S.sym + i0 + 8) = make_uint4(pr[4], pr[5], pr[6], pr[7]);
+          }
+#pragma unroll
+          for (int k = 0; k < 4; k++) wv[k] = __byte_perm(pr[2 * k], pr[2 * k + 1], 0x6420);
+          const bool full = i0 >= bias && i0 + 16u <= E;
+          if (full) {
+            uint4 q = make_uint4(wv[0], wv[1], wv[2], wv[3]);
+            *(uint4 *)(G0 + i0) = q;
+#if !DCMP_HIST_GLOBAL
+            *(uint4 *)(S.ring + ((g0_low + i0) & HIST_MASK)) = q;
+#endif
+          } else {
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+              uint32_t m = 0;
+#pragma unroll
+              for (int j = 0; j < 4; j++) {
+                uint32_t idx = i0 + 4u * k + j;
+                if (idx >= bias && idx < E) {
+                  uint8_t b = (uint8_t)(wv[k] >> (8 * j));
+                  G0[idx] = b;
+#if !DCMP_HIST_GLOBAL
+                  S.ring[(g0_low + idx) & HIST_MASK] = b;
+#endif
+                  m |= 0xffu << (8 * j);
+                }
+              }
+              wv[k] &= m;
+            }
+          }
+          if (fmt == DCMP_FMT_ZLIB) {
+            uint32_t sb = 0, bb = 0;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+              sb = __dp4a(wv[k], 0x01010101u, sb);
+              // weight of byte j of word k: distance to the chunk end = 16 - (4k + j)
+              bb = __dp4a(wv[k], (uint32_t)(((16 - 4 * k) & 0xff) | (((15 - 4 * k) & 0xff) << 8) |
+                                            (((14 - 4 * k) & 0xff) << 16) | (((13 - 4 * k) & 0xff) << 24)), bb);
+            }
+            // bytes of the round after this chunk's end (negative by < 16 for a ragged last chunk)
+            long long after = (long long)E - (long long)(i0 + 16u);
+            s_sum += sb;
+            b_sum += (long long)bb + (long long)sb * after;
+          }
+        }
+        if (fmt == DCMP_FMT_ZLIB) {
+          for (int o = 16; o > 0; o >>= 1) {
+            s_sum += __shfl_xor_sync(0xffffffffu, s_sum, o);
+            b_sum += __shfl_xor_sync(0xffffffffu, b_sum, o);
+          }
+          if (lane == 0) { S.adl_s[warp] = s_sum; S.adl_b[warp] = b_sum; }
+        }
+        __syncthreads();
+        if (tid == 0) {
+          if (fmt == DCMP_FMT_ZLIB && round_out) {
+            unsigned long long ts = 0;
+            long long tb = 0;
+            for (int w = 0; w < NWARP; w++) { ts += S.adl_s[w]; tb += S.adl_b[w]; }
+            const unsigned long long M = 65521ull;
+            // (A,B) after appending a segment of n bytes with byte sum s and suffix-weighted sum b:
+            // B' = B + n*A + b ; A' = A + s
+            unsigned long long a = S.adler_a, b = S.adler_b;
+            b = (b + (round_out % M) * a + (unsigned long long)tb % M) % M;
+            a = (a + ts % M) % M;
+            S.adler_a = (uint32_t)a;
+            S.adler_b = (uint32_t)b;
+          }
+          S.out_pos = out0 + round_out;
+          STAT(g_stats.out_bytes += round_out;)
+        }
+        __syncthreads();
+}
+
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(PT, DCMP_HIST_GLOBAL ? 3 : 2)
 inflate_parallel_kernel(int fmt, int64_t nstreams, const uint8_t *src_base, const int64_t *src_off,
@@ -560,7 +667,7 @@ inflate_parallel_kernel(int fmt, int64_t nstreams, const uint8_t *src_base, cons
     if (S.stream < 0) break;
 
     // ---------------------------------------------------------------- rounds
-    while (S.next == NEXT_HEADER || S.next == NEXT_CONTINUE) {
+    while (S.next == NEXT_HEADER || S.next == NEXT_CONTINUE || S.next == NEXT_STORED) {
       const int64_t base_bit = S.base_bit;
       const uint32_t A = (uint32_t)((uintptr_t)S.src & 15);
       const int64_t vbit = base_bit + 8 * (int64_t)A;        // bit position from the 16-aligned address below src
@@ -603,14 +710,32 @@ inflate_parallel_kernel(int fmt, int64_t nstreams, const uint8_t *src_base, cons
               S.hdr_hlit = 288;
               S.hdr_hdist = 32;
               S.base_bit = base_bit + (hb.pos() - bit0);
+            } else if (type == 0) {
+              // stored block (de.ml:1613-1627): skip to the byte boundary, LEN / NLEN, then LEN raw bytes
+              const int64_t sb = (base_bit + (hb.pos() - bit0) + 7) & ~(int64_t)7; // stream bit of LEN
+              if (8 * S.src_len - sb < 32) nx = NEXT_RETRY;
+              else {
+                HdrBits h2;
+                h2.init((const uint8_t *)S.win, (int)(sb - base_bit) + bit0, HDR_BYTES);
+                h2.refill();
+                const uint32_t len = h2.pop(16), nlen = h2.pop(16);
+                const int64_t payload = (sb >> 3) + 4;
+                if (nlen != 0xffffu - len || (int64_t)len > S.src_len - payload) nx = NEXT_RETRY; // exact error: general kernel
+                else {
+                  S.stored_rem = len;
+                  S.base_bit = 8 * payload;
+                  nx = len ? NEXT_STORED : (S.last_block ? NEXT_FINISH : NEXT_HEADER);
+                }
+              }
             } else {
-              nx = NEXT_RETRY; // stored blocks and BTYPE=3: general kernel
+              nx = NEXT_RETRY; // BTYPE=3: general kernel
             }
           }
           S.next = nx;
         }
         __syncthreads();
         if (S.next == NEXT_RETRY) break;
+        if (S.next != NEXT_CONTINUE) continue; // stored block (or an empty one): no tables to build
         const int hlit = (int)S.hdr_hlit, hdist = (int)S.hdr_hdist;
         bool ok = build_fast_table(S, KIND_LENS, S.lens, hlit, S.lit, LIT_ROOT, S.ml, S.sorted_l, tid);
         ok = ok && build_fast_table(S, KIND_DISTS, S.lens + hlit, hdist, S.dist, DIST_ROOT, S.md, S.sorted_d, tid);
@@ -621,6 +746,38 @@ inflate_parallel_kernel(int fmt, int64_t nstreams, const uint8_t *src_base, cons
           break;
         }
         continue; // S.next == NEXT_CONTINUE, S.base_bit moved past the header
+      }
+
+      if (S.next == NEXT_STORED) {
+        // ------------------------------------------------------------ stored payload: the bytes become literal
+        // symbols and leave through the same drain (128-bit stores, Adler-32) as a decoded round
+        const uint32_t out0 = S.out_pos;
+        const uint32_t n = umin32(S.stored_rem, (uint32_t)RSYM);
+        if ((int64_t)out0 + n > S.dst_cap) {
+          __syncthreads();
+          if (tid == 0) S.next = NEXT_RETRY; // Unexpected_end_of_output: exact point needed
+          __syncthreads();
+          break;
+        }
+        const uint32_t bias = (uint32_t)((uintptr_t)(S.dst + out0) & 15);
+        uint8_t *const G0 = S.dst + out0 - bias;
+        const uint32_t g0_low = (uint32_t)((uintptr_t)G0 & HIST_MASK);
+        const uint32_t E = bias + n;
+        const uint8_t *sp = S.src + (base_bit >> 3);
+        if (tid < 16) {
+          if ((uint32_t)tid < bias) S.sym[tid] = 0;
+          S.sym[E + tid] = 0;
+        }
+        for (uint32_t j = (uint32_t)tid; j < n; j += PT) S.sym[bias + j] = sp[j];
+        __syncthreads();
+        phase_e_drain(S, fmt, G0, g0_low, bias, E, out0, n, tid, lane, warp);
+        if (tid == 0) {
+          S.stored_rem -= n;
+          S.base_bit = base_bit + 8 * (int64_t)n;
+          if (S.stored_rem == 0) S.next = S.last_block ? NEXT_FINISH : NEXT_HEADER;
+        }
+        __syncthreads();
+        continue;
       }
 
       // -------------------------------------------------------------- data round
@@ -1028,109 +1185,7 @@ inflate_parallel_kernel(int fmt, int64_t nstreams, const uint8_t *src_base, cons
         __syncthreads();
         break;
       }
-      // ---- E: resolve markers, drain to HBM and to the history ring, fold Adler-32
-      {
-        const uint32_t nchunks = (E + 15u) >> 4;
-        unsigned long long s_sum = 0;
-        long long b_sum = 0;
-        for (uint32_t c = (uint32_t)tid; c < nchunks; c += PT) {
-          const uint32_t i0 = c << 4;
-          uint4 qa = *(const uint4 *)(S.sym + i0);
-          uint4 qb = *(const uint4 *)(S.sym + i0 + 8);
-          uint32_t pr[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
-          uint32_t wv[4];
-          const bool any_marker = ((qa.x | qa.y | qa.z | qa.w | qb.x | qb.y | qb.z | qb.w) & 0xff00ff00u) != 0u;
-          if (any_marker) {
-            // chase in rounds: every unresolved symbol of the chunk hops once per round, so up to 16 independent
-            // shared-memory loads are in flight instead of one dependent chain per symbol
-            bool pending = true;
-            while (pending) {
-              uint32_t acc = 0;
-#pragma unroll
-              for (int q = 0; q < 8; q++) {
-                uint32_t lo = pr[q] & 0xffffu, hi = pr[q] >> 16;
-                if (lo >= 256u) { lo = S.sym[lo - 256u]; STAT(g_stats.chase_hops++;) }
-                if (hi >= 256u) { hi = S.sym[hi - 256u]; STAT(g_stats.chase_hops++;) }
-                pr[q] = lo | (hi << 16);
-                acc |= pr[q];
-              }
-              pending = (acc & 0xff00ff00u) != 0u;
-            }
-            // path compression: later chases that land here stop after one hop (a racing reader sees
-            // either the old marker or the final literal — both lead to the same byte)
-            *(uint4 *)(S.sym + i0) = make_uint4(pr[0], pr[1], pr[2], pr[3]);
-            *(uint4 *)(S.sym + i0 + 8) = make_uint4(pr[4], pr[5], pr[6], pr[7]);
-          }
-#pragma unroll
-          for (int k = 0; k < 4; k++) wv[k] = __byte_perm(pr[2 * k], pr[2 * k + 1], 0x6420);
-          const bool full = i0 >= bias && i0 + 16u <= E;
-          if (full) {
-            uint4 q = make_uint4(wv[0], wv[1], wv[2], wv[3]);
-            *(uint4 *)(G0 + i0) = q;
-#if !DCMP_HIST_GLOBAL
-            *(uint4 *)(S.ring + ((g0_low + i0) & HIST_MASK)) = q;
-#endif
-          } else {
-#pragma unroll
-            for (int k = 0; k < 4; k++) {
-              uint32_t m = 0;
-#pragma unroll
-              for (int j = 0; j < 4; j++) {
-                uint32_t idx = i0 + 4u * k + j;
-                if (idx >= bias && idx < E) {
-                  uint8_t b = (uint8_t)(wv[k] >> (8 * j));
-                  G0[idx] = b;
-#if !DCMP_HIST_GLOBAL
-                  S.ring[(g0_low + idx) & HIST_MASK] = b;
-#endif
-                  m |= 0xffu << (8 * j);
-                }
-              }
-              wv[k] &= m;
-            }
-          }
-          if (fmt == DCMP_FMT_ZLIB) {
-            uint32_t sb = 0, bb = 0;
-#pragma unroll
-            for (int k = 0; k < 4; k++) {
-              sb = __dp4a(wv[k], 0x01010101u, sb);
-              // weight of byte j of word k: distance to the chunk end = 16 - (4k + j)
-              bb = __dp4a(wv[k], (uint32_t)(((16 - 4 * k) & 0xff) | (((15 - 4 * k) & 0xff) << 8) |
-                                            (((14 - 4 * k) & 0xff) << 16) | (((13 - 4 * k) & 0xff) << 24)), bb);
-            }
-            // bytes of the round after this chunk's end (negative by < 16 for a ragged last chunk)
-            long long after = (long long)E - (long long)(i0 + 16u);
-            s_sum += sb;
-            b_sum += (long long)bb + (long long)sb * after;
-          }
-        }
-        if (fmt == DCMP_FMT_ZLIB) {
-          for (int o = 16; o > 0; o >>= 1) {
-            s_sum += __shfl_xor_sync(0xffffffffu, s_sum, o);
-            b_sum += __shfl_xor_sync(0xffffffffu, b_sum, o);
-          }
-          if (lane == 0) { S.adl_s[warp] = s_sum; S.adl_b[warp] = b_sum; }
-        }
-        __syncthreads();
-        if (tid == 0) {
-          if (fmt == DCMP_FMT_ZLIB && round_out) {
-            unsigned long long ts = 0;
-            long long tb = 0;
-            for (int w = 0; w < NWARP; w++) { ts += S.adl_s[w]; tb += S.adl_b[w]; }
-            const unsigned long long M = 65521ull;
-            // (A,B) after appending a segment of n bytes with byte sum s and suffix-weighted sum b:
-            // B' = B + n*A + b ; A' = A + s
-            unsigned long long a = S.adler_a, b = S.adler_b;
-            b = (b + (round_out % M) * a + (unsigned long long)tb % M) % M;
-            a = (a + ts % M) % M;
-            S.adler_a = (uint32_t)a;
-            S.adler_b = (uint32_t)b;
-          }
-          S.out_pos = out0 + round_out;
-          STAT(g_stats.out_bytes += round_out;)
-        }
-        __syncthreads();
-      }
+      phase_e_drain(S, fmt, G0, g0_low, bias, E, out0, round_out, tid, lane, warp);
     } // rounds
 
     // ---------------------------------------------------------------- finish the stream

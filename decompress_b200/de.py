@@ -217,3 +217,44 @@ class Higher:
                 raise AssertionError("a `String source never awaits")
             else:
                 return Error(("Msg", r[1]))
+
+
+def _higher_compress(fmt, level, refill, flush, i, o, engine=None):
+    """Shared body of De.Higher.compress / Zl.Higher.compress: pull the whole input through `refill`
+    (it returns 0 at the end, de.ml:4517-4560), deflate it on the GPU, hand the result to `flush` in pieces of
+    len(o)."""
+    from . import batch
+    chunks = []
+    while True:
+        n = refill(i)
+        if n == 0:
+            break
+        chunks.append(bytes(i[:n]))
+    data = b"".join(chunks)
+    st, wr, comp = batch.deflate_streams([data], level=level, fmt=fmt, engine=engine)[0]
+    if st != 0:
+        raise RuntimeError(_lib.lib().dcmp_status_string(st).decode())
+    ov = _as_u8(o, writable=True)
+    for k in range(0, len(comp), len(ov)):
+        n = min(len(ov), len(comp) - k)
+        ov[:n] = np.frombuffer(comp, dtype=np.uint8)[k:k + n]
+        flush(o, n)
+
+
+def _compress(w, q, refill, flush, i, o, level=4, engine=None):
+    """De.Higher.compress ~w ~q ~refill ~flush i o (de.mli:540-575).  `w` (Lz77 window) and `q` (Queue) are the
+    reference's scratch for its serial matcher; the GPU path keeps its own (hash tables and token scratch on the
+    device), so they are accepted and ignored."""
+    _higher_compress(_lib.FMT_RAW, level, refill, flush, i, o, engine)
+
+
+def _to_string(w, q, refill, i, buffer=4096, level=4, engine=None):
+    """De.Higher.to_string ?buffer ~w ~q ~refill i (de.mli:640-665)."""
+    out = bytearray()
+    o = bigstring_create(max(int(buffer), 1))
+    _higher_compress(_lib.FMT_RAW, level, refill, lambda buf, n: out.extend(buf[:n].tobytes()), i, o, engine)
+    return bytes(out)
+
+
+Higher.compress = staticmethod(_compress)
+Higher.to_string = staticmethod(_to_string)

@@ -45,3 +45,30 @@ class Def:
             if st == 0:
                 return Ok(wr.value)
             return Error(_lib.STATUS_TAG.get(st, st))
+
+
+class Higher:
+    """Zl.Higher (zl.mli:265-368): compress ?level (default 6, zl.ml:634) and uncompress over the batch engine."""
+
+    @staticmethod
+    def compress(w, q, refill, flush, i, o, level=6, dynamic=True, engine=None):
+        from .de import _higher_compress
+        _higher_compress(_lib.FMT_ZLIB, level, refill, flush, i, o, engine)
+
+    @staticmethod
+    def uncompress(allocate, refill, flush, i, o, engine=None):
+        from .de import _InfDecoder
+        d = _InfDecoder("Manual", o, allocate(15) if allocate else None, engine, fmt=_lib.FMT_ZLIB)
+        while True:
+            r = d.decode()
+            if r == "Await":
+                n = refill(i)
+                d.src(i, 0, n)
+            elif r == "Flush":
+                flush(o, len(o) - d.dst_rem())
+                d.flush()
+            elif r == "End":
+                flush(o, len(o) - d.dst_rem())
+                return Ok(None)
+            else:
+                return Error(("Msg", r[1]))

@@ -94,3 +94,32 @@ def test_higher_uncompress_and_of_string(eng):
     assert de.Higher.of_string(o, de.make_window(bits=15), comp, flush, engine=eng) == Ok(None) and bytes(out) == txt
     r = de.Higher.of_string(o, de.make_window(bits=15), b"\x06", flush, engine=eng)
     assert not r.is_ok() and r.error == ("Msg", "Invalid kind of block")
+
+
+def test_higher_compress_roundtrips(eng):
+    """Zl.Higher.compress -> Zl.Higher.uncompress and De.Higher.compress / to_string -> system zlib (bench/b.ml's loop)."""
+    from decompress_b200 import zl
+    txt = workloads.text(500000, 12)
+    i, o = de.bigstring_create(de.io_buffer_size), de.bigstring_create(de.io_buffer_size)
+
+    def reader(data):
+        pos = [0]
+
+        def refill(buf):
+            n = min(len(buf), len(data) - pos[0])
+            buf[:n] = np.frombuffer(data, dtype=np.uint8)[pos[0]:pos[0] + n]
+            pos[0] += n
+            return n
+        return refill
+
+    comp = bytearray()
+    zl.Higher.compress(None, None, reader(txt), lambda buf, n: comp.extend(buf[:n].tobytes()), i, o, level=6, engine=eng)
+    assert zlib.decompress(bytes(comp)) == txt
+    back = bytearray()
+    r = zl.Higher.uncompress(lambda bits: de.make_window(bits), reader(bytes(comp)), lambda buf, n: back.extend(buf[:n].tobytes()), i, o, engine=eng)
+    assert r == Ok(None) and bytes(back) == txt
+    raw = de.Higher.to_string(None, None, reader(txt), i, engine=eng)
+    assert zlib.decompress(raw, -15) == txt
+    bad = bytearray(comp); bad[-1] ^= 1
+    r = zl.Higher.uncompress(None, reader(bytes(bad)), lambda buf, n: None, i, o, engine=eng)
+    assert not r.is_ok() and r.error[1].startswith("Invalid checksum")
