@@ -24,7 +24,8 @@ from bench import load_peaks  # noqa: E402
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--what", default="c1,c3,c5")
+    ap.add_argument("--what", default="c1,c3,c4,c5")
+    ap.add_argument("--c4-mib", type=int, default=512)
     ap.add_argument("--c3-mib", type=int, default=256)
     ap.add_argument("--c5-blocks", type=int, default=256)
     ap.add_argument("--steps", type=int, default=5)
@@ -102,6 +103,32 @@ def main():
                           "roofline": {"achieved": round(algo / sec / 1e9, 1), "peak": peak, "frac": round(algo / sec / 1e9 / peak, 4)},
                           "cpu_baseline": {"value": round((64 << 20) / zsec / 1e9, 4), "unit": "GB/s", "cores": 1, "kind": "system zlib level 6 (bench/b.ml's yardstick)",
                                            "sample": "first 64 MiB of the same text"}}), flush=True)
+    if "c4" in what:
+        # C4 at one GPU's share: concatenated gzip members (16..256 KiB payloads), boundaries from a sidecar index;
+        # the 10-byte headers are skipped on the host (framing stays on the host), bodies inflate on the device,
+        # CRC-32 / ISIZE are verified on the host after the timed region.
+        members = workloads.c4_members(args.c4_mib << 20, seed=0)
+        bodies = [m[10:] for m, _ in members]            # raw DEFLATE + 8-byte trailer (ignored by the raw decoder)
+        plains = [p for _, p in members]
+        n = len(bodies)
+        src, so, sl, dst, do, dc = batch.pack(bodies, [len(p) for p in plains])
+        d = [t(x) for x in (src, so, sl, dst, do, dc)]
+        cons, prod = torch.zeros(n, dtype=torch.int64, device=dev), torch.zeros(n, dtype=torch.int64, device=dev)
+        st = torch.zeros(n, dtype=torch.int32, device=dev)
+        fn = lambda: batch.inflate_device(batch.FMT_RAW, d[0], d[1], d[2], d[3], d[4], d[5], cons, prod, st, engine=eng)
+        sec = timed(fn, args.steps)
+        assert int(st.abs().sum()) == 0
+        out = d[3].cpu().numpy()
+        hc = cons.cpu().numpy()
+        for k in range(0, n, max(1, n // 50)):
+            got = out[do[k]:do[k] + len(plains[k])].tobytes()
+            tr = bodies[k][int(hc[k]):int(hc[k]) + 8]
+            assert zlib.crc32(got) == int.from_bytes(tr[:4], "little") and len(got) == int.from_bytes(tr[4:], "little"), k
+        total = float(sum(len(p) for p in plains))
+        algo = float(sl.sum()) + total
+        print(json.dumps({"config": "C4 (one GPU's share): %d gzip members, %d MiB inflated, payloads 16..256 KiB, several DEFLATE blocks each" % (n, args.c4_mib),
+                          "metric": "inflate_uncompressed_GBps", "value": round(total / sec / 1e9, 2), "ms": round(sec * 1e3, 3),
+                          "roofline": {"achieved": round(algo / sec / 1e9, 1), "peak": peak, "frac": round(algo / sec / 1e9 / peak, 4)}}), flush=True)
     if "c5" in what:
         n = args.c5_blocks
         comps, plains = workloads.c5_blocks(n)

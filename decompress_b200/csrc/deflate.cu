@@ -13,10 +13,12 @@
 //
 // Layout.  Every input stream is cut into independent 64 KiB chunks; one warp compresses one
 // chunk into one DEFLATE block (dynamic Huffman, or stored when that is smaller):
-//   1 tokenise   32 positions per step: every lane hashes its 4 bytes, takes the most recent
-//                earlier position with the same hash (shared-memory table, __match_any_sync for
-//                the ones inside the step) and extends the match byte-wise; the greedy parse of
-//                the 32 positions is the orbit of the carry-in position under
+//   1 tokenise   32 positions per step: every lane hashes its 4 bytes, takes the two most recent
+//                earlier positions with the same hash (two-way buckets in a shared-memory table,
+//                __match_any_sync for the ones inside the step) and extends both matches four
+//                bytes at a time (level 1: one candidate); from level 4 on a match yields to a
+//                longer one starting at the next position (one step of lazy evaluation); the
+//                parse of the 32 positions is the orbit of the carry-in position under
 //                next(p) = p + (match ? len : 1), found by pointer doubling with shuffles;
 //                tokens go to an L2-resident scratch, symbol frequencies to shared memory;
 //   2 build      lengths of the literal/length, distance and code-length codes (sort by warp
@@ -53,14 +55,19 @@ struct DfChunkOut {
   uint32_t pad;
 };
 
-struct DfSmem {
-  uint16_t head[1 << DF_HASH_BITS];
-  uint32_t freq_l[288];
-  uint32_t freq_d[32];
-  uint32_t freq_bl[19];
+struct DfTree {            // Huffman construction scratch; only alive after tokenising, so it overlays the hash table
   uint32_t sortbuf[512];
   uint32_t weight[2 * 288];
   uint16_t parent[2 * 288];
+};
+struct DfSmem {
+  union {
+    uint32_t head[1 << DF_HASH_BITS];   // two most recent positions per hash: [15:0] newest, [31:16] the one before
+    DfTree tree;
+  };
+  uint32_t freq_l[288];
+  uint32_t freq_d[32];
+  uint32_t freq_bl[19];
   uint16_t code_l[288];
   uint16_t code_d[32];
   uint16_t code_bl[19];
@@ -72,7 +79,9 @@ struct DfSmem {
   uint32_t win[DF_WIN];
   uint32_t extra_bits; // total extra bits of the tokens (for the stored/dynamic decision)
   int n_rle;
+  int hlit, hdist;
 };
+static_assert(sizeof(DfTree) <= sizeof(uint32_t) * (1 << DF_HASH_BITS), "tree scratch overlays the hash table");
 
 __device__ __constant__ uint8_t c_bl_order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15}; // de.ml:237
 
@@ -91,6 +100,26 @@ __device__ __forceinline__ uint32_t df_dist_sym(uint32_t dist, uint32_t *ebits, 
   *ebits = n - 1;
   *eval = D & ((1u << (n - 1)) - 1u);
   return 2u * n + ((D >> (n - 1)) & 1u);
+}
+
+// ---- match extension ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t df_load32(const uint8_t *p) { // unaligned little-endian load from two aligned words
+  const uintptr_t a = (uintptr_t)p;
+  const uint32_t *w = reinterpret_cast<const uint32_t *>(a & ~(uintptr_t)3);
+  return __funnelshift_r(w[0], w[1], 8u * (uint32_t)(a & 3));
+}
+// length of the common prefix of d[a..] and d[b..] (a < b), at most maxlen; `safe` = bytes from b that may be
+// read with the 8-byte-footprint word loads
+__device__ __forceinline__ int df_match_len(const uint8_t *d, int a, int b, int maxlen, int safe) {
+  int l = 0;
+  const int wmax = maxlen < safe - 7 ? maxlen : safe - 7;
+  while (l + 4 <= wmax) {
+    const uint32_t x = df_load32(d + a + l) ^ df_load32(d + b + l);
+    if (x) return l + ((__ffs((int)x) - 1) >> 3);
+    l += 4;
+  }
+  while (l < maxlen && d[a + l] == d[b + l]) l++;
+  return l;
 }
 
 // ---- output bit window -----------------------------------------------------------------------
@@ -126,16 +155,16 @@ struct DfBits {
 __device__ void df_build_code(DfSmem &S, const uint32_t *freq, int n, int max_bits, uint8_t *len, uint16_t *code, int lane) {
   __syncwarp();
   // keys (freq << 9 | sym) of the used symbols, padded for the sorting network
-  for (int i = lane; i < 512; i += 32) S.sortbuf[i] = 0xffffffffu;
+  for (int i = lane; i < 512; i += 32) S.tree.sortbuf[i] = 0xffffffffu;
   for (int i = lane; i < n; i += 32) len[i] = 0;
   __syncwarp();
   if (lane == 0) {
     int m = 0;
     for (int s = 0; s < n; s++)
-      if (freq[s]) S.sortbuf[m++] = (freq[s] << 9) | (uint32_t)s;
+      if (freq[s]) S.tree.sortbuf[m++] = (freq[s] << 9) | (uint32_t)s;
     // the pkzip rule (de.ml:1863-1874): force at least two codes
-    if (m == 0) { S.sortbuf[0] = (1u << 9) | 0u; S.sortbuf[1] = (1u << 9) | 1u; m = 2; }
-    else if (m == 1) { uint32_t s0 = S.sortbuf[0] & 511u; S.sortbuf[1] = (1u << 9) | (s0 == 0 ? 1u : 0u); m = 2; }
+    if (m == 0) { S.tree.sortbuf[0] = (1u << 9) | 0u; S.tree.sortbuf[1] = (1u << 9) | 1u; m = 2; }
+    else if (m == 1) { uint32_t s0 = S.tree.sortbuf[0] & 511u; S.tree.sortbuf[1] = (1u << 9) | (s0 == 0 ? 1u : 0u); m = 2; }
     S.n_rle = m; // (reused as a scratch scalar: number of leaves)
   }
   __syncwarp();
@@ -147,35 +176,35 @@ __device__ void df_build_code(DfSmem &S, const uint32_t *freq, int n, int max_bi
         const int i = ((t / j) * 2 * j) + (t % j); // lower index of the pair
         const int p = i + j;
         const bool up = (i & k) == 0;
-        const uint32_t a = S.sortbuf[i], b = S.sortbuf[p];
-        if ((a > b) == up) { S.sortbuf[i] = b; S.sortbuf[p] = a; }
+        const uint32_t a = S.tree.sortbuf[i], b = S.tree.sortbuf[p];
+        if ((a > b) == up) { S.tree.sortbuf[i] = b; S.tree.sortbuf[p] = a; }
       }
       __syncwarp();
     }
   }
   if (lane == 0) {
     // two-queue Huffman: leaves 0..m-1 (ascending), internal nodes m..2m-2 (created in ascending weight)
-    for (int i = 0; i < m; i++) S.weight[i] = S.sortbuf[i] >> 9;
+    for (int i = 0; i < m; i++) S.tree.weight[i] = S.tree.sortbuf[i] >> 9;
     int li = 0, ii = m, nn = m;
     while (nn < 2 * m - 1) {
       uint32_t w = 0;
       for (int k = 0; k < 2; k++) {
         int pick;
-        if (li < m && (ii >= nn || S.weight[li] <= S.weight[ii])) pick = li++;
+        if (li < m && (ii >= nn || S.tree.weight[li] <= S.tree.weight[ii])) pick = li++;
         else pick = ii++;
-        w += S.weight[pick];
-        S.parent[pick] = (uint16_t)nn;
+        w += S.tree.weight[pick];
+        S.tree.parent[pick] = (uint16_t)nn;
       }
-      S.weight[nn++] = w;
+      S.tree.weight[nn++] = w;
     }
     // depths (a parent always has a larger index), folded into bl_count with the overflow repair of gen_bitlen
     int bl_count[16];
     for (int b = 0; b < 16; b++) bl_count[b] = 0;
-    S.weight[2 * m - 2] = 0; // weight[] now holds depths
+    S.tree.weight[2 * m - 2] = 0; // weight[] now holds depths
     int overflow = 0;
     for (int i = 2 * m - 3; i >= 0; i--) {
-      uint32_t d = S.weight[S.parent[i]] + 1;
-      S.weight[i] = d;
+      uint32_t d = S.tree.weight[S.tree.parent[i]] + 1;
+      S.tree.weight[i] = d;
       if (i < m) {
         if ((int)d > max_bits) { d = (uint32_t)max_bits; overflow++; }
         bl_count[d]++;
@@ -192,7 +221,7 @@ __device__ void df_build_code(DfSmem &S, const uint32_t *freq, int n, int max_bi
     // longest codes to the least frequent symbols
     int i = 0;
     for (int bits = max_bits; bits >= 1; bits--)
-      for (int c = bl_count[bits]; c > 0; c--) len[S.sortbuf[i++] & 511u] = (uint8_t)bits;
+      for (int c = bl_count[bits]; c > 0; c--) len[S.tree.sortbuf[i++] & 511u] = (uint8_t)bits;
     // canonical codes, bit-reversed (de.ml:1910-1924)
     uint32_t next_code[16];
     uint32_t c = 0;
@@ -251,17 +280,40 @@ __device__ void df_compress_chunk(DfSmem &S, const uint8_t *d, int len, bool las
         h = (v * 0x9e3779b1u) >> (32 - DF_HASH_BITS);
       }
       const uint32_t same = __match_any_sync(0xffffffffu, h);
-      int cand = -1;
+      int cand0 = -1, cand1 = -1; // the two most recent earlier positions with this hash
       if (h != 0xffffffffu) {
         const uint32_t lower = same & ((1u << lane) - 1u);
-        cand = lower ? base + (31 - __clz((int)lower)) : (int)S.head[h];
+        const uint32_t hd = S.head[h];
+        if (lower) {
+          const int l0 = 31 - __clz((int)lower);
+          cand0 = base + l0;
+          const uint32_t lower2 = lower & ~(1u << l0);
+          cand1 = lower2 ? base + (31 - __clz((int)lower2)) : (int)(hd & 0xffffu);
+        } else {
+          cand0 = (int)(hd & 0xffffu);
+          cand1 = (int)(hd >> 16);
+        }
       }
       __syncwarp();
-      if (h != 0xffffffffu && (same >> lane) == 1u) S.head[h] = (uint16_t)p; // the last lane of a group is the most recent
-      if (cand >= 0 && cand < p && p - cand <= 32768) {
-        int l = 0;
-        while (l < maxlen && d[cand + l] == d[p + l]) l++;
-        if (l >= DF_MIN_MATCH || (l == 3 && p - cand < DF_TOO_FAR)) { mlen = l; mdist = p - cand; }
+      if (h != 0xffffffffu && (same >> lane) == 1u) { // the last lane of a group records the group's two newest positions
+        const uint32_t lower = same & ((1u << lane) - 1u);
+        const uint32_t prev = lower ? (uint32_t)(base + (31 - __clz((int)lower))) : (S.head[h] & 0xffffu);
+        S.head[h] = (prev << 16) | (uint32_t)p;
+      }
+      if (cand0 >= 0 && cand0 < p && p - cand0 <= 32768) {
+        int l = df_match_len(d, cand0, p, maxlen, len - p);
+        int dist = p - cand0;
+        if (level >= 2 && l < maxlen && cand1 >= 0 && cand1 < cand0 && p - cand1 <= 32768) {
+          const int l1 = df_match_len(d, cand1, p, maxlen, len - p);
+          if (l1 > l) { l = l1; dist = p - cand1; }
+        }
+        if (l >= DF_MIN_MATCH || (l == 3 && dist < DF_TOO_FAR)) { mlen = l; mdist = dist; }
+      }
+      if (level >= 4) {
+        // lazy evaluation, one step (the idea of de.ml:4351-4410): a match loses to a longer one starting at the
+        // next position; the byte in front of it goes out as a literal
+        const int nlen = __shfl_down_sync(0xffffffffu, mlen, 1);
+        if (lane < 31 && mlen && nlen > mlen) mlen = 0;
       }
       // greedy parse of the 32 positions: orbit of `carry` under next()
       const int nxt = lane + (mlen ? mlen : 1);
@@ -328,11 +380,11 @@ __device__ void df_compress_chunk(DfSmem &S, const uint8_t *d, int len, bool las
         i += run;
       }
       S.n_rle = nr;
-      S.weight[575] = (uint32_t)hlit; // (two scalars parked in unused node slots)
-      S.weight[574] = (uint32_t)hdist;
+      S.hlit = hlit;
+      S.hdist = hdist;
     }
     __syncwarp();
-    const int n_rle = S.n_rle, hlit = (int)S.weight[575], hdist = (int)S.weight[574];
+    const int n_rle = S.n_rle, hlit = S.hlit, hdist = S.hdist;
     __syncwarp();
     df_build_code(S, S.freq_bl, 19, 7, S.len_bl, S.code_bl, lane);
     // cost of the dynamic block vs stored blocks
