@@ -22,6 +22,11 @@ int launch_inflate_parallel(int fmt, int64_t n, const uint8_t *src_base, const i
                             int ctas, cudaStream_t stream);
 size_t inflate_parallel_scratch_bytes_per_cta();
 int inflate_parallel_ctas_per_sm();
+void launch_gzip_header(int64_t n, const uint8_t *src_base, const int64_t *src_off, const int64_t *src_len, int64_t *body_off,
+                        int64_t *body_len, int32_t *pre_status, cudaStream_t stream);
+void launch_gzip_trailer(int64_t n, const uint8_t *src_base, const int64_t *src_off, const int64_t *body_off, const int64_t *body_len,
+                         const int32_t *pre_status, const uint8_t *dst_base, const int64_t *dst_off, int64_t *consumed,
+                         int64_t *produced, int32_t *status, cudaStream_t stream);
 void launch_lzo_decode(int mode, int64_t n, const uint8_t *src_base, const int64_t *src_off, const int64_t *src_len,
                        uint8_t *dst_base, const int64_t *dst_off, const int64_t *dst_cap, int64_t *consumed,
                        int64_t *produced, int32_t *status, cudaStream_t stream);
@@ -59,6 +64,8 @@ struct dcmp_engine {
   int par_ctas = 0;                  // persistent CTAs of the sub-chunk-parallel kernel (2 per SM)
   uint8_t *d_scratch = nullptr;      // [work counter (256 B) | token scratch of every CTA]
   int mode = 0;                      // 0 = parallel + general, 1 = general kernel only (DCMP_INFLATE_MODE=serial)
+  uint8_t *d_gz = nullptr;           // gzip: rebased body offsets / lengths / header status per member
+  size_t gz_cap = 0;
   // deflate: persistent CTAs (3 per SM), their token scratch, and a growable arena for the per-chunk state
   int def_ctas = 0;
   uint8_t *d_def_scratch = nullptr;  // [work counter (256 B) | token scratch of every CTA]
@@ -158,6 +165,7 @@ void dcmp_engine_destroy(dcmp_engine *e) {
   cudaSetDevice(e->device);
   if (e->d_buf) cudaFree(e->d_buf);
   if (e->d_scratch) cudaFree(e->d_scratch);
+  if (e->d_gz) cudaFree(e->d_gz);
   if (e->d_def_scratch) cudaFree(e->d_def_scratch);
   if (e->d_def_arena) cudaFree(e->d_def_arena);
   if (e->pipeline_ready) {
@@ -176,11 +184,33 @@ int dcmp_inflate_batch_device(dcmp_engine *e, int fmt, int64_t n, const uint8_t 
                               const int64_t *d_dst_cap, int64_t *d_consumed, int64_t *d_produced, int32_t *d_status,
                               void *cuda_stream) {
   if (!e) return DCMP_API_INVALID_ARGUMENT;
-  if (fmt != DCMP_FMT_RAW && fmt != DCMP_FMT_ZLIB) return DCMP_API_INVALID_ARGUMENT;
+  if (fmt != DCMP_FMT_RAW && fmt != DCMP_FMT_ZLIB && fmt != DCMP_FMT_GZIP) return DCMP_API_INVALID_ARGUMENT;
   if (n < 0) return DCMP_API_INVALID_ARGUMENT;
   if (n == 0) return DCMP_API_OK;
   CU(cudaSetDevice(e->device));
   cudaStream_t st = (cudaStream_t)cuda_stream; // NULL = the legacy default stream, as everywhere in CUDA
+  // gzip: one member per unit.  The header is parsed on the device, the DEFLATE body goes through the raw
+  // kernels with rebased offset tables, then CRC-32 / ISIZE are checked on the device (gzip_frame.cu).
+  const int64_t *g_src_off = d_src_off, *g_src_len = d_src_len;
+  int64_t *gz_off = nullptr, *gz_len = nullptr;
+  int32_t *gz_pre = nullptr;
+  if (fmt == DCMP_FMT_GZIP) {
+    const size_t need = (size_t)n * 20 + 256;
+    if (need > e->gz_cap) {
+      // (stream-ordered free: earlier launches on other streams may still read the old scratch)
+      if (e->d_gz) { CU(cudaDeviceSynchronize()); CU(cudaFree(e->d_gz)); e->d_gz = nullptr; e->gz_cap = 0; }
+      CU(cudaMalloc(&e->d_gz, need * 2));
+      e->gz_cap = need * 2;
+    }
+    gz_off = (int64_t *)e->d_gz;
+    gz_len = gz_off + n;
+    gz_pre = (int32_t *)(gz_len + n);
+    dcmp::launch_gzip_header(n, d_src_base, d_src_off, d_src_len, gz_off, gz_len, gz_pre, st);
+    e->launches += 1;
+    d_src_off = gz_off;
+    d_src_len = gz_len;
+    fmt = DCMP_FMT_RAW;
+  }
   if (e->mode == 0) {
     // stage 1: sub-chunk-parallel kernel, persistent CTAs pulling streams from a device counter;
     // stage 2: the general kernel on exactly the streams stage 1 marked INTERNAL_RETRY.
@@ -199,6 +229,12 @@ int dcmp_inflate_batch_device(dcmp_engine *e, int fmt, int64_t n, const uint8_t 
                                 d_produced, d_status, -1, st);
     e->launches += 1;
   }
+  if (gz_pre) {
+    dcmp::launch_gzip_trailer(n, d_src_base, g_src_off, gz_off, gz_len, gz_pre, d_dst_base, d_dst_off, d_consumed, d_produced,
+                              d_status, st);
+    e->launches += 1;
+  }
+  (void)g_src_len;
   CU(cudaGetLastError());
   return DCMP_API_OK;
 }
@@ -322,79 +358,12 @@ static int host_batch(dcmp_engine *e, device_batch_fn launch, int fmt, int64_t n
   return DCMP_API_OK;
 }
 
-// ---- gzip member framing (host side, as north_star prescribes) -----------------------------------
-static uint32_t crc32_fast(uint32_t crc, const uint8_t *p, int64_t n);
-
-// Gz.Inf header (lib/gz.ml:463-492, 358-461): only the magic is checked (not CM); FEXTRA's XLEN is read
-// big-endian (gz.ml:455); FHCRC covers the 10 fixed bytes + FNAME + FCOMMENT, not FEXTRA (gz.ml:399-440).
-static int gz_parse_header(const uint8_t *p, int64_t n, int64_t *hdr_len) {
-  if (n < 10) return DCMP_UNEXPECTED_END_OF_INPUT;
-  if (p[0] != 0x1f || p[1] != 0x8b) return DCMP_INVALID_GZIP_HEADER;
-  const int flg = p[3];
-  int64_t i = 10;
-  if (flg & 4) {
-    if (n - i < 2) return DCMP_UNEXPECTED_END_OF_INPUT;
-    int64_t xlen = ((int64_t)p[i] << 8) | p[i + 1];
-    i += 2;
-    if (n - i < xlen) return DCMP_UNEXPECTED_END_OF_INPUT;
-    i += xlen;
-  }
-  uint32_t crc = crc32_fast(0, p, 10);
-  for (int bit = 8; bit <= 16; bit <<= 1) { // FNAME, then FCOMMENT: zero-terminated
-    if (!(flg & bit)) continue;
-    int64_t j = i;
-    while (j < n && p[j] != 0) j++;
-    if (j >= n) return DCMP_UNEXPECTED_END_OF_INPUT;
-    crc = crc32_fast(crc, p + i, j + 1 - i);
-    i = j + 1;
-  }
-  if (flg & 2) {
-    if (n - i < 2) return DCMP_UNEXPECTED_END_OF_INPUT;
-    uint32_t have = ((uint32_t)p[i] << 8) | p[i + 1];
-    if ((crc >> 16) != have) return DCMP_INVALID_GZIP_HEADER_CHECKSUM;
-    i += 2;
-  }
-  *hdr_len = i;
-  return DCMP_OK;
-}
-
 int dcmp_inflate_batch(dcmp_engine *e, int fmt, int64_t n, const uint8_t *src_base, const int64_t *src_off,
                        const int64_t *src_len, uint8_t *dst_base, const int64_t *dst_off, const int64_t *dst_cap,
                        int64_t *consumed, int64_t *produced, int32_t *status) {
-  if (fmt == DCMP_FMT_RAW || fmt == DCMP_FMT_ZLIB)
-    return host_batch(e, dcmp_inflate_batch_device, fmt, n, src_base, src_off, src_len, dst_base, dst_off, dst_cap,
-                      consumed, produced, status);
-  if (fmt != DCMP_FMT_GZIP) return DCMP_API_INVALID_ARGUMENT;
-  // One gzip member per unit (Gz.Inf returns `End after one member, lib/gz.ml:344-356): header and trailer
-  // are handled here on the host, the DEFLATE body goes to the device as a raw stream.
-  if (n < 0) return DCMP_API_INVALID_ARGUMENT;
-  if (n == 0) return DCMP_API_OK;
-  if (!src_off || !src_len || !dst_off || !dst_cap || !consumed || !produced || !status || !src_base)
-    return DCMP_API_INVALID_ARGUMENT;
-  std::vector<int64_t> so((size_t)n), sl((size_t)n), hdr((size_t)n, 0);
-  std::vector<int32_t> pre((size_t)n);
-  for (int64_t k = 0; k < n; k++) {
-    if (src_len[k] < 0 || src_off[k] < 0) return DCMP_API_INVALID_ARGUMENT;
-    pre[k] = gz_parse_header(src_base + src_off[k], src_len[k], &hdr[k]);
-    so[k] = src_off[k] + (pre[k] == DCMP_OK ? hdr[k] : 0);
-    sl[k] = pre[k] == DCMP_OK ? src_len[k] - hdr[k] : 0;
-  }
-  int rc = host_batch(e, dcmp_inflate_batch_device, DCMP_FMT_RAW, n, src_base, so.data(), sl.data(), dst_base, dst_off,
-                      dst_cap, consumed, produced, status);
-  if (rc != DCMP_API_OK) return rc;
-  for (int64_t k = 0; k < n; k++) {
-    if (pre[k] != DCMP_OK) { status[k] = pre[k]; consumed[k] = 0; produced[k] = 0; continue; }
-    if (status[k] != DCMP_OK) continue;
-    const uint8_t *t = src_base + so[k] + consumed[k];
-    if (sl[k] - consumed[k] < 8) { status[k] = DCMP_UNEXPECTED_END_OF_INPUT; continue; }
-    const uint32_t crc = (uint32_t)t[0] | ((uint32_t)t[1] << 8) | ((uint32_t)t[2] << 16) | ((uint32_t)t[3] << 24);
-    const uint32_t isize = (uint32_t)t[4] | ((uint32_t)t[5] << 8) | ((uint32_t)t[6] << 16) | ((uint32_t)t[7] << 24);
-    const uint32_t got = crc32_fast(0, dst_base + dst_off[k], produced[k]);
-    if (got != crc) status[k] = DCMP_INVALID_CHECKSUM;             // lib/gz.ml:352-354: the checksum is compared first
-    else if ((uint32_t)produced[k] != isize) status[k] = DCMP_INVALID_INPUT_SIZE;
-    else consumed[k] += hdr[k] + 8;
-  }
-  return DCMP_API_OK;
+  if (fmt != DCMP_FMT_RAW && fmt != DCMP_FMT_ZLIB && fmt != DCMP_FMT_GZIP) return DCMP_API_INVALID_ARGUMENT;
+  return host_batch(e, dcmp_inflate_batch_device, fmt, n, src_base, src_off, src_len, dst_base, dst_off, dst_cap,
+                    consumed, produced, status);
 }
 
 int dcmp_lzo_uncompress_batch_device(dcmp_engine *e, int mode, int64_t n, const uint8_t *d_src_base,

@@ -1,0 +1,167 @@
+// decompress_b200/csrc/gzip_frame.cu — gzip member framing on the device, so that a batch of members can be
+// verified without the inflated bytes ever visiting the host.
+//
+// Replaces, for one member per unit, Gz.Inf's header / trailer handling (lib/gz.ml:463-492 header, 358-461
+// FEXTRA / FNAME / FCOMMENT / FHCRC, 344-356 CRC-32 + ISIZE) and the Checkseum.Crc32 folds of lib/gz.ml:503-513.
+// once inflate runs at tens of GB/s a host CRC-32 (1-3 GB/s per core) is the end-to-end
+// bottleneck, and CRC-32 is parallel-reducible (crc(A||B) = crc(A) * x^(8|B|) + crc(B) over GF(2)).
+//   gzip_header_kernel   one thread per member: parse the header exactly as gz.ml does (only the magic is checked;
+//                        XLEN is read big-endian, gz.ml:455; FHCRC covers the 10 fixed bytes + FNAME + FCOMMENT),
+//                        hand the DEFLATE body to the raw inflate kernels through rebased offset tables;
+//   gzip_trailer_kernel  one warp per member: every lane folds a contiguous slice of the inflated bytes through
+//                        a shared-memory table, the 32 partial CRCs are combined with carry-less multiplications
+//                        by x^(8*len) mod P, then CRC-32 and ISIZE are compared (the checksum first, gz.ml:352-354).
+#include "simt.cuh"
+#include "../../include/dcmp.h"
+
+namespace dcmp {
+
+constexpr uint32_t CRC_POLY = 0xedb88320u;
+
+// (a * b) mod P over GF(2), reflected representation (bit 31 = x^0), as zlib's multmodp
+__device__ __forceinline__ uint32_t gf2_mulmod(uint32_t a, uint32_t b) {
+  uint32_t p = 0;
+#pragma unroll 4
+  for (int i = 31; i >= 0; i--) {
+    if ((a >> i) & 1u) p ^= b;
+    b = (b & 1u) ? (b >> 1) ^ CRC_POLY : b >> 1;
+  }
+  return p;
+}
+// x^(8 * nbytes) mod P by square-and-multiply
+__device__ uint32_t gf2_xpow8n(uint64_t nbytes) {
+  uint32_t sq = 0x00800000u; // x^8: bit (31 - 8)
+  uint32_t p = 0x80000000u;  // x^0
+  while (nbytes) {
+    if (nbytes & 1ull) p = gf2_mulmod(sq, p);
+    sq = gf2_mulmod(sq, sq);
+    nbytes >>= 1;
+  }
+  return p;
+}
+
+__device__ uint32_t crc_bytes(const uint32_t *T, uint32_t c, const uint8_t *p, int64_t n) {
+  for (int64_t i = 0; i < n; i++) c = T[(c ^ p[i]) & 0xffu] ^ (c >> 8);
+  return c;
+}
+
+// one thread per member
+__global__ void gzip_header_kernel(int64_t n, const uint8_t *src_base, const int64_t *src_off, const int64_t *src_len,
+                                   int64_t *body_off, int64_t *body_len, int32_t *pre_status) {
+  __shared__ uint32_t T[256];
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) {
+    uint32_t c = (uint32_t)i;
+    for (int k = 0; k < 8; k++) c = (c & 1u) ? CRC_POLY ^ (c >> 1) : c >> 1;
+    T[i] = c;
+  }
+  __syncthreads();
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const uint8_t *p = src_base + src_off[k];
+  const int64_t len = src_len[k];
+  int st = DCMP_OK;
+  int64_t i = 10;
+  if (len < 10) st = DCMP_UNEXPECTED_END_OF_INPUT;
+  else if (p[0] != 0x1f || p[1] != 0x8b) st = DCMP_INVALID_GZIP_HEADER;
+  else {
+    const int flg = p[3];
+    if (flg & 4) {
+      if (len - i < 2) st = DCMP_UNEXPECTED_END_OF_INPUT;
+      else {
+        const int64_t xlen = ((int64_t)p[i] << 8) | p[i + 1];
+        i += 2;
+        if (len - i < xlen) st = DCMP_UNEXPECTED_END_OF_INPUT;
+        else i += xlen;
+      }
+    }
+    uint32_t crc = ~crc_bytes(T, 0xffffffffu, p, 10);
+    for (int bit = 8; bit <= 16 && st == DCMP_OK; bit <<= 1) { // FNAME, then FCOMMENT: zero-terminated
+      if (!(flg & bit)) continue;
+      int64_t j = i;
+      while (j < len && p[j] != 0) j++;
+      if (j >= len) { st = DCMP_UNEXPECTED_END_OF_INPUT; break; }
+      crc = ~crc_bytes(T, ~crc, p + i, j + 1 - i);
+      i = j + 1;
+    }
+    if (st == DCMP_OK && (flg & 2)) {
+      if (len - i < 2) st = DCMP_UNEXPECTED_END_OF_INPUT;
+      else {
+        const uint32_t have = ((uint32_t)p[i] << 8) | p[i + 1];
+        if ((crc >> 16) != have) st = DCMP_INVALID_GZIP_HEADER_CHECKSUM;
+        i += 2;
+      }
+    }
+  }
+  pre_status[k] = st;
+  body_off[k] = src_off[k] + (st == DCMP_OK ? i : 0);
+  body_len[k] = st == DCMP_OK ? len - i : 0;
+}
+
+// one warp per member
+__global__ void __launch_bounds__(128)
+gzip_trailer_kernel(int64_t n, const uint8_t *src_base, const int64_t *src_off, const int64_t *body_off, const int64_t *body_len,
+                    const int32_t *pre_status, const uint8_t *dst_base, const int64_t *dst_off, int64_t *consumed,
+                    int64_t *produced, int32_t *status) {
+  __shared__ uint32_t T[256];
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) {
+    uint32_t c = (uint32_t)i;
+    for (int k = 0; k < 8; k++) c = (c & 1u) ? CRC_POLY ^ (c >> 1) : c >> 1;
+    T[i] = c;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int64_t k = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (k >= n) return;
+  const int pre = pre_status[k];
+  int st = status[k];
+  if (pre != DCMP_OK) {
+    if (lane == 0) { status[k] = pre; consumed[k] = 0; produced[k] = 0; }
+    return;
+  }
+  if (st != DCMP_OK) return; // the inflate error stands (its consumed / produced too)
+  const int64_t prod = produced[k], cons = consumed[k];
+  // CRC-32 of dst[0..prod): contiguous slices, raw remainders (no pre/post conditioning), combined left to right
+  const uint8_t *o = dst_base + dst_off[k];
+  const int64_t per = (prod + 31) / 32;
+  const int64_t lo = per * lane < prod ? per * lane : prod, hi = lo + per < prod ? lo + per : prod;
+  uint32_t c = crc_bytes(T, lane == 0 ? 0xffffffffu : 0u, o + lo, hi - lo);
+  // tree combine: at step s, lane l (l % 2^(s+1) == 0) absorbs lane l + 2^s, whose span is known from lo/hi
+  for (int s = 1; s < 32; s <<= 1) {
+    const uint32_t right = __shfl_down_sync(0xffffffffu, c, s);
+    const int64_t right_lo = __shfl_down_sync(0xffffffffu, lo, s);
+    int64_t span_end = per * (lane + 2 * s) < prod ? per * (lane + 2 * s) : prod; // end of the absorbed lanes' range
+    if (lane + s < 32 && (lane & (2 * s - 1)) == 0) {
+      const int64_t rlen = span_end - right_lo;
+      c = rlen > 0 ? gf2_mulmod(gf2_xpow8n((uint64_t)rlen), c) ^ right : c;
+    }
+  }
+  if (lane == 0) {
+    const uint32_t crc = ~c;
+    const int64_t blen = body_len[k];
+    if (blen - cons < 8) st = DCMP_UNEXPECTED_END_OF_INPUT;
+    else {
+      const uint8_t *t = src_base + body_off[k] + cons;
+      const uint32_t want = (uint32_t)t[0] | ((uint32_t)t[1] << 8) | ((uint32_t)t[2] << 16) | ((uint32_t)t[3] << 24);
+      const uint32_t isize = (uint32_t)t[4] | ((uint32_t)t[5] << 8) | ((uint32_t)t[6] << 16) | ((uint32_t)t[7] << 24);
+      if (crc != want) st = DCMP_INVALID_CHECKSUM; // lib/gz.ml:352-354: the checksum is compared first
+      else if ((uint32_t)prod != isize) st = DCMP_INVALID_INPUT_SIZE;
+      else consumed[k] = cons + (body_off[k] - src_off[k]) + 8;
+    }
+    status[k] = st;
+  }
+}
+
+#ifndef DCMP_EMU
+void launch_gzip_header(int64_t n, const uint8_t *src_base, const int64_t *src_off, const int64_t *src_len, int64_t *body_off,
+                        int64_t *body_len, int32_t *pre_status, cudaStream_t stream) {
+  gzip_header_kernel<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(n, src_base, src_off, src_len, body_off, body_len, pre_status);
+}
+void launch_gzip_trailer(int64_t n, const uint8_t *src_base, const int64_t *src_off, const int64_t *body_off, const int64_t *body_len,
+                         const int32_t *pre_status, const uint8_t *dst_base, const int64_t *dst_off, int64_t *consumed,
+                         int64_t *produced, int32_t *status, cudaStream_t stream) {
+  gzip_trailer_kernel<<<(unsigned)((n + 3) / 4), 128, 0, stream>>>(n, src_base, src_off, body_off, body_len, pre_status, dst_base,
+                                                                  dst_off, consumed, produced, status);
+}
+#endif
+
+} // namespace dcmp

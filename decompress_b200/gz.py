@@ -2,8 +2,8 @@
 
 The reference's Gz.Inf is a streaming decoder that answers `End after ONE member (lib/gz.ml:344-356) and has no
 one-shot (Ns) form; the batched equivalent here takes one gzip member per unit: header parsing (lib/gz.ml:463-492,
-including the big-endian XLEN and the FHCRC coverage quirks), the DEFLATE body on the GPU, then CRC-32 and ISIZE
-(lib/gz.ml:344-356) — framing and checksum on the host, as in the reference's layering.
+including the big-endian XLEN and the FHCRC coverage quirks), the DEFLATE body, then CRC-32 and ISIZE
+(lib/gz.ml:344-356) — all on the device (csrc/gzip_frame.cu), so verified output never has to visit the host.
 """
 import ctypes as C
 

@@ -71,7 +71,8 @@ enum {
 enum {
   DCMP_FMT_RAW = 0,   /* RFC1951, De.Inf.Ns.inflate (lib/de.ml:1807-1822) */
   DCMP_FMT_ZLIB = 1,  /* RFC1950, Zl.Inf.Ns.inflate (lib/zl.ml:400-417) */
-  DCMP_FMT_GZIP = 2   /* RFC1952 single member, Gz.Inf (lib/gz.ml:463-531) */
+  DCMP_FMT_GZIP = 2   /* RFC1952, one member per unit: Gz.Inf header + CRC-32/ISIZE trailer (lib/gz.ml:463-531, 344-356),
+                         parsed and checked on the device */
 };
 
 typedef struct dcmp_engine dcmp_engine;
