@@ -80,6 +80,19 @@ constexpr int WIN_BYTES = (WIN_WORDS * 4 + 15) & ~15;
 constexpr int HDR_BYTES = 1024 + 16;      // staged input for a block header
 constexpr int LIT_ROOT = 10;
 constexpr int DIST_ROOT = 9;
+constexpr int LIT_SUB = 512;              // second-level entries (codes longer than the root); a code set that needs
+constexpr int DIST_SUB = 128;             // more goes to the general kernel
+// Decode-table entry of this kernel: one shared-memory load per code, fields placed for the hot loop.
+//  [4:0]   bits to drop: code length + extra bits     [8:5]  code length (LINK: index bits of the sub-table)
+//  [12:9]  number of extra bits                         [27:13] base: literal byte | match length base (3..258) |
+//                                                               distance base (1..24577) | LINK: sub-table offset
+//  [28] LINK  [29] EOB  [30] match length  [31] rare: EOB, LINK or an unassigned slot — one sign test takes all
+//  three off the hot path
+constexpr uint32_t PE_RARE = 1u << 31, PE_LEN = 1u << 30, PE_EOB = 1u << 29, PE_LINK = 1u << 28;
+constexpr uint32_t PE_INVALID = PE_RARE;
+__host__ __device__ constexpr uint32_t pe_make(uint32_t base, uint32_t extra, uint32_t len) {
+  return (base << 13) | (extra << 9) | (len << 5) | (len + extra);
+}
 constexpr int DCMP_INTERNAL_RETRY = 0x7f; // never leaves the library
 static_assert(SUB_WORDS % 2 == 1, "odd lane stride keeps the window reads conflict-free");
 static_assert(PT % 32 == 0 && PT <= 1024, "");
@@ -133,15 +146,22 @@ __device__ __forceinline__ void batch_put(uint4 &b, int k, uint32_t t) {
   if (k == 2) b.z = t;
   if (k == 3) b.w = t;
 }
+// A batch is filled as a shift register (newest token in .w): three moves per token, no indexing.
+__device__ __forceinline__ void batch_push(uint4 &b, uint32_t t) { b.x = b.y; b.y = b.z; b.z = b.w; b.w = t; }
+// bring the last r (1..3) tokens of a partial batch to the front
+__device__ __forceinline__ void batch_front(uint4 &b, int r) {
+  if (r == 1) b.x = b.w;
+  if (r == 2) { b.x = b.z; b.y = b.w; }
+  if (r == 3) { b.x = b.y; b.y = b.z; b.z = b.w; }
+}
 __device__ __forceinline__ uint32_t batch_get(const uint4 &b, int k) {
   uint32_t lo = (k & 1) ? b.y : b.x, hi = (k & 1) ? b.w : b.z;
   return (k & 2) ? hi : lo;
 }
 
-struct HuffMeta {      // canonical-code description for codes longer than the root table
+struct HuffMeta {      // canonical-code description of one alphabet
   uint16_t first[16];  // first code (MSB-first) of each length
   uint16_t cnt[16];
-  uint16_t offs[16];   // index of the first symbol of each length in sorted[]
   int root, maxl;
 };
 
@@ -151,12 +171,10 @@ struct ParSmem {
   __align__(16) uint8_t ring[HIST];        // last 32 KiB of output, indexed by (global address & HIST_MASK)
 #endif
   __align__(16) uint32_t win[WIN_BYTES / 4 + 4]; // staged compressed input (TMA destination)
-  uint32_t lit[1 << LIT_ROOT];
-  uint32_t dist[1 << DIST_ROOT];
+  uint32_t lit[(1 << LIT_ROOT) + LIT_SUB];   // root table, then the sub-tables of codes longer than the root
+  uint32_t dist[(1 << DIST_ROOT) + DIST_SUB];
   uint32_t codes[CODES_TABLE_SIZE];
   uint32_t code_of[MAX_LENS];    // table build scratch: bit-reversed code | len << 16 per symbol
-  uint16_t sorted_l[288];
-  uint16_t sorted_d[32];
   uint8_t lens[MAX_LENS];
   HuffMeta ml, md;
   uint32_t run_cnt[16];
@@ -169,12 +187,12 @@ struct ParSmem {
   uint32_t m_owner[NWARP];       // lanes whose own head decode counts (not covered by an earlier lane's head)
   int pass_owner;                // lane whose head ran past the end of the window (-1: none)
   int pass_pos;                  // its exit (own sub-chunk coordinates)
-  int last_clean;
   uint32_t warp_c[NWARP];
   unsigned long long adl_s[NWARP];
   long long adl_b[NWARP];
-  uint32_t hdr_hlit, hdr_hdist, tbl_ok;
-  int first_bad, first_term, first_over;
+  uint32_t hdr_hlit, hdr_hdist, tbl_ok, sub_alloc;
+  int first_bad, first_term;
+  uint32_t slice_end;
   // stream state (CTA-uniform)
   int64_t stream;                // index of the stream being decoded, -1 = none
   const uint8_t *src; int64_t src_len;  // raw deflate bytes
@@ -190,109 +208,100 @@ struct ParSmem {
   int abort_round;               // a lane met an invalid distance: the general kernel reports it
   __align__(8) uint64_t mbar;
 };
-#if DCMP_HIST_GLOBAL
-static_assert(sizeof(ParSmem) <= 74 * 1024, "three CTAs per SM need <= ~74.6 KiB each");
-#else
-static_assert(sizeof(ParSmem) <= 112 * 1024, "two CTAs per SM need <= ~113 KiB each");
+#ifndef DCMP_CTAS_PER_SM
+#define DCMP_CTAS_PER_SM (DCMP_HIST_GLOBAL ? 3 : 2)
 #endif
+// 227 KiB of shared memory per SM, 1 KiB reserved per resident CTA
+static_assert(sizeof(ParSmem) + 128 + 1024 <= 227 * 1024 / DCMP_CTAS_PER_SM, "shared memory per CTA for the intended residency");
 
 // ------------------------------------------------------------------------------------------
 // bit cursor over a lane's sub-chunk inside the staged window
 struct LaneBits {
   uint64_t hold;
-  int nbits; // valid bits in hold
-  int wi;    // next word (relative to the lane's first word) to load
-  int sh;    // bit offset of the sub-chunk inside its first word
-  const uint32_t *w; // the lane's first word
-  __device__ __forceinline__ void init(const uint32_t *lane_words, int sh_, int p0) {
-    w = lane_words;
-    sh = sh_;
-    int b = p0 + sh;
-    wi = b >> 5;
-    int skip = b & 31;
-    hold = (uint64_t)(w[wi] >> skip);
+  int nbits;            // valid bits in hold
+  const uint32_t *wp;   // next word to load
+  int p;                // bits consumed, in the lane's sub-chunk coordinates
+  __device__ __forceinline__ void init(const uint32_t *lane_words, int sh, int p0) {
+    const int b = p0 + sh; // sh: bit offset of the sub-chunk inside its first word
+    wp = lane_words + (b >> 5);
+    const int skip = b & 31;
+    hold = (uint64_t)(*wp++ >> skip);
     nbits = 32 - skip;
-    wi++;
+    p = p0;
   }
-  __device__ __forceinline__ void refill() {
-    if (nbits <= 32) {
-      hold |= (uint64_t)w[wi] << nbits; // the window is padded: wi never leaves it
+  __device__ __forceinline__ void refill() { // at least 32 valid bits afterwards
+    if (nbits < 32) {
+      hold |= (uint64_t)(*wp++) << nbits; // the window is padded: wp never leaves it
       nbits += 32;
-      wi++;
     }
   }
-  __device__ __forceinline__ int pos() const { return 32 * wi - nbits - sh; }
-  __device__ __forceinline__ void drop(int k) { hold >>= k; nbits -= k; }
-  __device__ __forceinline__ uint32_t pop(int k) {
-    uint32_t v = (uint32_t)hold & ((1u << k) - 1u);
-    drop(k);
-    return v;
-  }
+  __device__ __forceinline__ int pos() const { return p; }
+  __device__ __forceinline__ void drop(uint32_t k) { hold >>= k; nbits -= (int)k; p += (int)k; }
 };
-
-// canonical decode for codes longer than the root table (rare): de.ml's second-level
-// tables (de.ml:614-636) are replaced by a first-code comparison per length.
-__device__ __noinline__ uint32_t slow_symbol(const HuffMeta &m, const uint16_t *sorted, uint32_t bits_lsb_first, int *len_out) {
-  uint32_t rev = __brev(bits_lsb_first);
-  for (int l = m.root + 1; l <= m.maxl; l++) {
-    uint32_t c = rev >> (32 - l);
-    uint32_t idx = c - m.first[l];
-    if (c >= m.first[l] && idx < m.cnt[l]) {
-      *len_out = l;
-      return sorted[m.offs[l] + idx];
-    }
-  }
-  *len_out = m.maxl; // unreachable for a complete code
-  return 0;
-}
 
 enum : int { T_TOKEN = 0, T_EOB = 1, T_ERR = 2 };
 
 // Decode one literal / match at the cursor.  *tok gets the token, *nout its byte count.
-__device__ __forceinline__ int decode_token(ParSmem &S, LaneBits &lb, uint32_t lmask, uint32_t dmask,
+__device__ __forceinline__ uint32_t pe_value(uint32_t e, uint32_t lo) { // base + extra bits
+  return ((e >> 13) & 0x7fffu) + ((lo >> ((e >> 5) & 15u)) & ~(~0u << ((e >> 9) & 15u)));
+}
+__device__ __forceinline__ int decode_token(ParSmem &S, LaneBits &lb, uint32_t lmask, uint32_t dmask, int lroot, int droot,
                                             uint32_t *tok, uint32_t *nout) {
   lb.refill();
-  uint32_t e = S.lit[(uint32_t)lb.hold & lmask];
-  if (e_kind(e) == K_LINK) {
-    int l;
-    uint32_t sym = slow_symbol(S.ml, S.sorted_l, (uint32_t)lb.hold, &l);
-    e = lit_symbol_entry((int)sym) | (uint32_t)l;
+  uint32_t lo = (uint32_t)lb.hold;
+  uint32_t e = S.lit[lo & lmask];
+  if ((int32_t)e < 0) { // rare: end of block, a code longer than the root table, an unassigned slot
+    if (e & PE_EOB) { lb.drop(e & 31u); return T_EOB; }
+    if (!(e & PE_LINK)) return T_ERR;
+    e = S.lit[((e >> 13) & 0x7fffu) + ((lo >> lroot) & ~(~0u << ((e >> 5) & 15u)))];
+    if ((int32_t)e < 0) {
+      if (e & PE_EOB) { lb.drop(e & 31u); return T_EOB; }
+      return T_ERR;
+    }
   }
-  lb.drop(e_len(e));
-  uint32_t kind = e_kind(e);
-  if (kind == K_LIT) {
-    *tok = e_base(e);
+  if (!(e & PE_LEN)) {
+    lb.drop(e & 31u);
+    *tok = (e >> 13) & 0xffu;
     *nout = 1;
     return T_TOKEN;
   }
-  if (kind == K_EOB) return T_EOB;
-  if (kind != K_LEN) return T_ERR; // K_INVALID: unfilled slot of an incomplete code set
-  uint32_t len = e_base(e) + lb.pop(e_extra(e));
+  const uint32_t len = pe_value(e, lo);
+  lb.drop(e & 31u);
   lb.refill();
-  uint32_t d = S.dist[(uint32_t)lb.hold & dmask];
-  if (e_kind(d) == K_LINK) {
-    int l;
-    uint32_t sym = slow_symbol(S.md, S.sorted_d, (uint32_t)lb.hold, &l);
-    d = dist_symbol_entry((int)sym) | (uint32_t)l;
+  lo = (uint32_t)lb.hold;
+  uint32_t d = S.dist[lo & dmask];
+  if ((int32_t)d < 0) { // longer than the root, or unassigned (empty / incomplete set, symbols 30/31: general kernel)
+    if (!(d & PE_LINK)) return T_ERR;
+    d = S.dist[((d >> 13) & 0x7fffu) + ((lo >> droot) & ~(~0u << ((d >> 5) & 15u)))];
+    if ((int32_t)d < 0) return T_ERR;
   }
-  if (e_kind(d) != K_LIT) return T_ERR; // empty / incomplete distance code set: general kernel
-  lb.drop(e_len(d));
-  uint32_t db = e_base(d);
-  uint32_t dd = db + lb.pop(e_extra(d));
-  if (db == 0) return T_ERR; // distance symbols 30/31: "Invalid distance code" (de.ml:321-325,1699)
+  const uint32_t dd = pe_value(d, lo);
+  lb.drop(d & 31u);
   *tok = (1u << 23) | ((dd - 1u) << 8) | (len - 3u);
   *nout = len;
   return T_TOKEN;
 }
 
 // ------------------------------------------------------------------------------------------
-// Parallel construction of the root decode table + canonical metadata from code lengths.
-// Accepts complete codes (Kraft sum exactly 1) and, for the literal/length and distance
-// alphabets, the two incomplete shapes the reference accepts (de.ml:544-550): no code at all
-// and a single 1-bit code; their unassigned slots are K_INVALID, which sends a stream that
-// really uses them to the general kernel.  Returns false (CTA-uniform) otherwise.
-__device__ bool build_fast_table(ParSmem &S, int kind, const uint8_t *lens, int n, uint32_t *tbl, int root_max,
-                                 HuffMeta &m, uint16_t *sorted, int tid) {
+// Parallel construction of a two-level decode table from code lengths (the shape of Inf.huffman,
+// de.ml:523-638: a root table indexed by the next `root` bits, sub-tables for longer codes; here the
+// root is wider and every entry carries what the hot loop needs).  Accepts complete codes (Kraft sum
+// exactly 1) and, for the literal/length and distance alphabets, the two incomplete shapes the
+// reference accepts (de.ml:544-550): no code at all and a single 1-bit code; their unassigned slots
+// are PE_INVALID, which sends a stream that really uses them to the general kernel.  Returns false
+// (CTA-uniform) otherwise, or when the sub-tables do not fit.  `scratch`: 1 << root_max words.
+__device__ __forceinline__ uint32_t pe_symbol(int kind, int s, uint32_t l) {
+  if (kind == KIND_DISTS) {
+    const uint32_t b = c_dist_base[s & 31];
+    return b ? pe_make(b, c_dist_extra[s & 31], l) : PE_INVALID; // symbols 30/31: "Invalid distance code" (de.ml:321-325)
+  }
+  if (s < 256) return pe_make((uint32_t)s, 0, l);
+  if (s == 256) return PE_RARE | PE_EOB | pe_make(0, 0, l);
+  const int i = (s - 257) & 31; // 286/287 decode as a length-3 match (de.ml:293-311)
+  return PE_LEN | pe_make(c_len_base[i], c_len_extra[i], l);
+}
+__device__ bool build_fast_table(ParSmem &S, int kind, const uint8_t *lens, int n, uint32_t *tbl, int root_max, int sub_cap,
+                                 HuffMeta &m, uint32_t *scratch, int tid) {
   __syncthreads();
   if (tid < 16) S.run_cnt[tid] = 0;
   __syncthreads();
@@ -303,15 +312,13 @@ __device__ bool build_fast_table(ParSmem &S, int kind, const uint8_t *lens, int 
   __syncthreads();
   if (tid == 0) {
     int left = 1, maxl = 0;
-    uint32_t code = 0, off = 0;
-    m.cnt[0] = 0; m.first[0] = 0; m.offs[0] = 0;
+    uint32_t code = 0;
+    m.cnt[0] = 0; m.first[0] = 0;
     for (int l = 1; l <= 15; l++) {
       uint32_t c = S.run_cnt[l];
       code = (code + (l > 1 ? S.run_cnt[l - 1] : 0)) << 1;
       m.first[l] = (uint16_t)code;
       m.cnt[l] = (uint16_t)c;
-      m.offs[l] = (uint16_t)off;
-      off += c;
       left = (left << 1) - (int)c;
       if (left < 0) left = -100000; // over-subscribed
       if (c) maxl = l;
@@ -324,12 +331,14 @@ __device__ bool build_fast_table(ParSmem &S, int kind, const uint8_t *lens, int 
     m.maxl = maxl;
     m.root = maxl < root_max ? maxl : root_max;
     S.tbl_ok = ok ? 1u : 0u;
+    S.sub_alloc = 0;
   }
   __syncthreads();
   if (!S.tbl_ok) return false;
   if (tid < 16) S.run_cnt[tid] = 0;
   const int root = m.root;
-  for (int i = tid; i < (1 << root); i += PT) tbl[i] = mk_entry(K_INVALID, 0, 0, 0);
+  const uint32_t rmask = (1u << root) - 1u;
+  for (int i = tid; i < (1 << root); i += PT) { tbl[i] = PE_INVALID; scratch[i] = 0; }
   __syncthreads();
   // canonical rank of every symbol among the symbols of its length (by symbol index):
   // warp 0 walks the alphabet 32 symbols at a time, __match_any_sync groups equal lengths.
@@ -345,10 +354,10 @@ __device__ bool build_fast_table(ParSmem &S, int kind, const uint8_t *lens, int 
       __syncwarp();
       if (s < n) {
         if (l) {
-          uint32_t r = before + rank;
-          uint32_t code = (uint32_t)m.first[l] + r;
-          S.code_of[s] = (__brev(code) >> (32 - l)) | (l << 16);
-          sorted[m.offs[l] + r] = (uint16_t)s;
+          uint32_t code = (uint32_t)m.first[l] + before + rank;
+          uint32_t r = __brev(code) >> (32 - l);
+          S.code_of[s] = r | (l << 16);
+          if ((int)l > root) atomicMax(&scratch[r & rmask], l - (uint32_t)root); // index bits its sub-table needs
         } else {
           S.code_of[s] = 0;
         }
@@ -356,16 +365,34 @@ __device__ bool build_fast_table(ParSmem &S, int kind, const uint8_t *lens, int 
     }
   }
   __syncthreads();
+  // place the sub-tables (any order) and link them from the root
+  for (int i = tid; i < (1 << root); i += PT) {
+    const uint32_t bits = scratch[i];
+    if (bits) {
+      const uint32_t off = atomicAdd(&S.sub_alloc, 1u << bits);
+      if (off + (1u << bits) > (uint32_t)sub_cap) S.tbl_ok = 0;
+      else {
+        const uint32_t at = (1u << root) + off;
+        tbl[i] = PE_RARE | PE_LINK | (at << 13) | (bits << 5);
+        scratch[i] = at | (bits << 16);
+        for (uint32_t j = 0; j < (1u << bits); j++) tbl[at + j] = PE_INVALID;
+      }
+    }
+  }
+  __syncthreads();
+  if (!S.tbl_ok) return false;
   for (int s = tid; s < n; s += PT) {
-    uint32_t co = S.code_of[s];
-    int l = (int)(co >> 16);
+    const uint32_t co = S.code_of[s];
+    const uint32_t l = co >> 16;
     if (!l) continue;
-    uint32_t r = co & 0xffffu;
-    if (l <= root) {
-      uint32_t entry = symbol_entry(kind, s) | (uint32_t)l;
+    const uint32_t r = co & 0xffffu;
+    const uint32_t entry = pe_symbol(kind, s, l);
+    if ((int)l <= root) {
       for (uint32_t i = r; i < (1u << root); i += (1u << l)) tbl[i] = entry;
     } else {
-      tbl[r & ((1u << root) - 1u)] = mk_entry(K_LINK, 0, 0, 0);
+      const uint32_t sc = scratch[r & rmask];
+      const uint32_t at = sc & 0xffffu, bits = sc >> 16;
+      for (uint32_t j = r >> root; j < (1u << bits); j += (1u << (l - (uint32_t)root))) tbl[at + j] = entry;
     }
   }
   __syncthreads();
@@ -502,43 +529,11 @@ __device__ void stage_window(ParSmem &S, const uint8_t *g, int bytes, int valid,
   __syncthreads();
 }
 
-// ---- E: resolve markers, drain to HBM (and to the history ring), fold Adler-32.  All threads call.
-__device__ __forceinline__ void phase_e_drain(ParSmem &S, const int fmt, uint8_t *const G0, const uint32_t g0_low,
-                                              const uint32_t bias, const uint32_t E, const uint32_t out0,
-                                              const uint32_t round_out, const int tid, const int lane, const int warp) {
-        const uint32_t nchunks = (E + 15u) >> 4;
-        unsigned long long s_sum = 0;
-        long long b_sum = 0;
-        for (uint32_t c = (uint32_t)tid; c < nchunks; c += PT) {
-          const uint32_t i0 = c << 4;
-          uint4 qa = *(const uint4 *)(S.sym + i0);
-          uint4 qb = *(const uint4 *)(S.sym + i0 + 8);
-          uint32_t pr[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
-          uint32_t wv[4];
-          const bool any_marker = ((qa.x | qa.y | qa.z | qa.w | qb.x | qb.y | qb.z | qb.w) & 0xff00ff00u) != 0u;
-          if (any_marker) {
-            // chase in rounds: every unresolved symbol of the chunk hops once per round, so up to 16 independent
-            // shared-memory loads are in flight instead of one dependent chain per symbol
-            bool pending = true;
-            while (pending) {
-              uint32_t acc = 0;
-#pragma unroll
-              for (int q = 0; q < 8; q++) {
-                uint32_t lo = pr[q] & 0xffffu, hi = pr[q] >> 16;
-                if (lo >= 256u) { lo = S.sym[lo - 256u]; STAT(g_stats.chase_hops++;) }
-                if (hi >= 256u) { hi = S.sym[hi - 256u]; STAT(g_stats.chase_hops++;) }
-                pr[q] = lo | (hi << 16);
-                acc |= pr[q];
-              }
-              pending = (acc & 0xff00ff00u) != 0u;
-            }
-            // path compression: later chases that land here stop after one hop (a racing reader sees
-            // either the old marker or the final literal — both lead to the same byte)
-            *(uint4 *)(S.sym + i0) = make_uint4(pr[0], pr[1], pr[2], pr[3]);
-            *(uint4 *)(S.sym + i0 + 8) = make_uint4(pr[4], pr[5], pr[6], pr[7]);
-          }
-#pragma unroll
-          for (int k = 0; k < 4; k++) wv[k] = __byte_perm(pr[2 * k], pr[2 * k + 1], 0x6420);
+// One 16-symbol chunk (symbol indices [i0, i0 + 16), packed into four words) leaves for HBM — one aligned 128-bit
+// store, byte-wise at the ragged ends of the segment [bias, E) — and is folded into the Adler-32 partial sums.
+__device__ __forceinline__ void emit_chunk16(ParSmem &S, const int fmt, uint8_t *const G0, const uint32_t g0_low,
+                                             const uint32_t bias, const uint32_t E, const uint32_t i0, uint32_t (&wv)[4],
+                                             unsigned long long &s_sum, long long &b_sum) {
           const bool full = i0 >= bias && i0 + 16u <= E;
           if (full) {
             uint4 q = make_uint4(wv[0], wv[1], wv[2], wv[3]);
@@ -579,7 +574,13 @@ __device__ __forceinline__ void phase_e_drain(ParSmem &S, const int fmt, uint8_t
             s_sum += sb;
             b_sum += (long long)bb + (long long)sb * after;
           }
-        }
+}
+
+// Close a segment of seg_out bytes that started at stream position out0: reduce the Adler-32 partial sums over the
+// CTA, append them to the stream's running (A, B) and advance the output cursor.  All threads call.
+__device__ __forceinline__ void segment_finish(ParSmem &S, const int fmt, const uint32_t out0, const uint32_t round_out,
+                                               unsigned long long s_sum, long long b_sum, const int tid, const int lane,
+                                               const int warp) {
         if (fmt == DCMP_FMT_ZLIB) {
           for (int o = 16; o > 0; o >>= 1) {
             s_sum += __shfl_xor_sync(0xffffffffu, s_sum, o);
@@ -608,8 +609,100 @@ __device__ __forceinline__ void phase_e_drain(ParSmem &S, const int fmt, uint8_t
         __syncthreads();
 }
 
+// ---- E: resolve markers, drain to HBM (and to the history ring), fold Adler-32.  All threads call.
+__device__ __forceinline__ void phase_e_drain(ParSmem &S, const int fmt, uint8_t *const G0, const uint32_t g0_low,
+                                              const uint32_t bias, const uint32_t E, const uint32_t out0,
+                                              const uint32_t round_out, const int tid, const int lane, const int warp) {
+        const uint32_t nchunks = (E + 15u) >> 4;
+        unsigned long long s_sum = 0;
+        long long b_sum = 0;
+        for (uint32_t c = (uint32_t)tid; c < nchunks; c += PT) {
+          const uint32_t i0 = c << 4;
+          uint4 qa = *(const uint4 *)(S.sym + i0);
+          uint4 qb = *(const uint4 *)(S.sym + i0 + 8);
+          uint32_t pr[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
+          uint32_t wv[4];
+          const bool any_marker = ((qa.x | qa.y | qa.z | qa.w | qb.x | qb.y | qb.z | qb.w) & 0xff00ff00u) != 0u;
+          if (any_marker) {
+            // chase in rounds: every unresolved symbol of the chunk hops once per round, so up to 16 independent
+            // shared-memory loads are in flight instead of one dependent chain per symbol
+            bool pending = true;
+            while (pending) {
+              uint32_t acc = 0;
+#pragma unroll
+              for (int q = 0; q < 8; q++) {
+                uint32_t lo = pr[q] & 0xffffu, hi = pr[q] >> 16;
+                if (lo >= 256u) { lo = S.sym[lo - 256u]; STAT(g_stats.chase_hops++;) }
+                if (hi >= 256u) { hi = S.sym[hi - 256u]; STAT(g_stats.chase_hops++;) }
+                pr[q] = lo | (hi << 16);
+                acc |= pr[q];
+              }
+              pending = (acc & 0xff00ff00u) != 0u;
+            }
+            // path compression: later chases that land here stop after one hop (a racing reader sees
+            // either the old marker or the final literal — both lead to the same byte)
+            *(uint4 *)(S.sym + i0) = make_uint4(pr[0], pr[1], pr[2], pr[3]);
+            *(uint4 *)(S.sym + i0 + 8) = make_uint4(pr[4], pr[5], pr[6], pr[7]);
+          }
+#pragma unroll
+          for (int k = 0; k < 4; k++) wv[k] = __byte_perm(pr[2 * k], pr[2 * k + 1], 0x6420);
+          emit_chunk16(S, fmt, G0, g0_low, bias, E, i0, wv, s_sum, b_sum);
+        }
+        segment_finish(S, fmt, out0, round_out, s_sum, b_sum, tid, lane, warp);
+}
+
+// Stored payload (de.ml:837-865, one-shot form 1613-1627): n bytes straight from the input to the output with
+// 128-bit loads and stores.  The bytes pass through registers once — re-aligned with funnel shifts, Adler-32
+// folded on the way — and never touch shared memory.  All threads call.
+__device__ __forceinline__ void stored_copy(ParSmem &S, const int fmt, const uint8_t *sp, const uint32_t n,
+                                            const uint32_t out0, const int tid, const int lane, const int warp) {
+  uint8_t *const dp = S.dst + out0;
+  const uint32_t bias = (uint32_t)((uintptr_t)dp & 15);
+  uint8_t *const G0 = dp - bias;
+  const uint32_t g0_low = (uint32_t)((uintptr_t)G0 & HIST_MASK);
+  const uint32_t E = bias + n;
+  const uint32_t nchunks = (E + 15u) >> 4;
+  // symbol index i <-> source address SA + i; the 16-byte granules that hold a byte of the stream may be read
+  const uintptr_t SA = (uintptr_t)sp - bias;
+  const uint32_t a = (uint32_t)(SA & 15);
+  const uintptr_t AB = SA - a;
+  const uintptr_t lo_ok = (uintptr_t)S.src & ~(uintptr_t)15, hi_ok = (uintptr_t)S.src + (uintptr_t)S.src_len;
+  const uint32_t q = a >> 2, r8 = 8u * (a & 3u);
+  unsigned long long s_sum = 0;
+  long long b_sum = 0;
+  constexpr int U = 4; // chunks in flight per thread
+  for (uint32_t c0 = 0; c0 < nchunks; c0 += U * PT) {
+    uint4 L0[U], L1[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const uint32_t c = c0 + (uint32_t)u * PT + (uint32_t)tid;
+      const uintptr_t g = AB + 16ull * c;
+      L0[u] = make_uint4(0, 0, 0, 0);
+      L1[u] = make_uint4(0, 0, 0, 0);
+      if (c < nchunks) {
+        if (g >= lo_ok && g < hi_ok) L0[u] = __ldcs(reinterpret_cast<const uint4 *>(g));
+        if (a != 0u && g + 16 >= lo_ok && g + 16 < hi_ok) L1[u] = __ldcs(reinterpret_cast<const uint4 *>(g + 16));
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const uint32_t c = c0 + (uint32_t)u * PT + (uint32_t)tid;
+      if (c >= nchunks) continue;
+      const uint32_t w[8] = {L0[u].x, L0[u].y, L0[u].z, L0[u].w, L1[u].x, L1[u].y, L1[u].z, L1[u].w};
+      uint32_t x[5];
+#pragma unroll
+      for (int k = 0; k < 5; k++) x[k] = q == 0 ? w[k] : q == 1 ? w[k + 1] : q == 2 ? w[k + 2] : w[(k + 3) & 7];
+      uint32_t wv[4];
+#pragma unroll
+      for (int k = 0; k < 4; k++) wv[k] = __funnelshift_r(x[k], x[k + 1], r8);
+      emit_chunk16(S, fmt, G0, g0_low, bias, E, c << 4, wv, s_sum, b_sum);
+    }
+  }
+  segment_finish(S, fmt, out0, n, s_sum, b_sum, tid, lane, warp);
+}
+
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(PT, DCMP_HIST_GLOBAL ? 3 : 2)
+__global__ void __launch_bounds__(PT, DCMP_CTAS_PER_SM)
 inflate_parallel_kernel(int fmt, int64_t nstreams, const uint8_t *src_base, const int64_t *src_off,
                         const int64_t *src_len, uint8_t *dst_base, const int64_t *dst_off, const int64_t *dst_cap,
                         int64_t *consumed, int64_t *produced, int32_t *status, unsigned long long *work_counter,
@@ -737,8 +830,9 @@ inflate_parallel_kernel(int fmt, int64_t nstreams, const uint8_t *src_base, cons
         if (S.next == NEXT_RETRY) break;
         if (S.next != NEXT_CONTINUE) continue; // stored block (or an empty one): no tables to build
         const int hlit = (int)S.hdr_hlit, hdist = (int)S.hdr_hdist;
-        bool ok = build_fast_table(S, KIND_LENS, S.lens, hlit, S.lit, LIT_ROOT, S.ml, S.sorted_l, tid);
-        ok = ok && build_fast_table(S, KIND_DISTS, S.lens + hlit, hdist, S.dist, DIST_ROOT, S.md, S.sorted_d, tid);
+        // (the symbol buffer is idle between rounds: it lends the builder its scratch words)
+        bool ok = build_fast_table(S, KIND_LENS, S.lens, hlit, S.lit, LIT_ROOT, LIT_SUB, S.ml, reinterpret_cast<uint32_t *>(S.sym), tid);
+        ok = ok && build_fast_table(S, KIND_DISTS, S.lens + hlit, hdist, S.dist, DIST_ROOT, DIST_SUB, S.md, reinterpret_cast<uint32_t *>(S.sym), tid);
         if (!ok) {
           __syncthreads();
           if (tid == 0) S.next = NEXT_RETRY;
@@ -749,32 +843,20 @@ inflate_parallel_kernel(int fmt, int64_t nstreams, const uint8_t *src_base, cons
       }
 
       if (S.next == NEXT_STORED) {
-        // ------------------------------------------------------------ stored payload: the bytes become literal
-        // symbols and leave through the same drain (128-bit stores, Adler-32) as a decoded round
+        // ------------------------------------------------------------ stored payload: straight copy
         const uint32_t out0 = S.out_pos;
-        const uint32_t n = umin32(S.stored_rem, (uint32_t)RSYM);
+        const uint32_t n = S.stored_rem;
         if ((int64_t)out0 + n > S.dst_cap) {
           __syncthreads();
           if (tid == 0) S.next = NEXT_RETRY; // Unexpected_end_of_output: exact point needed
           __syncthreads();
           break;
         }
-        const uint32_t bias = (uint32_t)((uintptr_t)(S.dst + out0) & 15);
-        uint8_t *const G0 = S.dst + out0 - bias;
-        const uint32_t g0_low = (uint32_t)((uintptr_t)G0 & HIST_MASK);
-        const uint32_t E = bias + n;
-        const uint8_t *sp = S.src + (base_bit >> 3);
-        if (tid < 16) {
-          if ((uint32_t)tid < bias) S.sym[tid] = 0;
-          S.sym[E + tid] = 0;
-        }
-        for (uint32_t j = (uint32_t)tid; j < n; j += PT) S.sym[bias + j] = sp[j];
-        __syncthreads();
-        phase_e_drain(S, fmt, G0, g0_low, bias, E, out0, n, tid, lane, warp);
+        stored_copy(S, fmt, S.src + (base_bit >> 3), n, out0, tid, lane, warp);
         if (tid == 0) {
-          S.stored_rem -= n;
+          S.stored_rem = 0;
           S.base_bit = base_bit + 8 * (int64_t)n;
-          if (S.stored_rem == 0) S.next = S.last_block ? NEXT_FINISH : NEXT_HEADER;
+          S.next = S.last_block ? NEXT_FINISH : NEXT_HEADER;
         }
         __syncthreads();
         continue;
@@ -787,7 +869,8 @@ inflate_parallel_kernel(int fmt, int64_t nstreams, const uint8_t *src_base, cons
       }
       const int sh = bit0 & 31;
       const uint32_t *lane_words = S.win + (bit0 >> 5) + SUB_WORDS * tid;
-      const uint32_t lmask = (1u << S.ml.root) - 1u, dmask = (1u << S.md.root) - 1u;
+      const int lroot = S.ml.root, droot = S.md.root;
+      const uint32_t lmask = (1u << lroot) - 1u, dmask = (1u << droot) - 1u;
       // this lane's token slots in the L2-resident scratch: [HEAD_CAP head tokens | SPEC_CAP speculative tokens],
       // written and read back as 128-bit batches of four
       uint4 *tok_lane = reinterpret_cast<uint4 *>(tok_scratch + ((size_t)blockIdx.x * PT + tid) * TOK_SLOTS);
@@ -814,22 +897,22 @@ inflate_parallel_kernel(int fmt, int64_t nstreams, const uint8_t *src_base, cons
             last_ck = ck;
           }
           uint32_t tok, no;
-          int r = decode_token(S, lb, lmask, dmask, &tok, &no);
+          int r = decode_token(S, lb, lmask, dmask, lroot, droot, &tok, &no);
           if (r == T_EOB) { xkind = X_EOB; xpos = lb.pos(); break; }
           if (r == T_ERR) { xkind = X_ERR; xpos = p; break; }
-          batch_put(tbuf, ns & 3, tok);
+          batch_push(tbuf, tok);
           if ((ns & 3) == 3) tok_spec[ns >> 2] = tbuf;
           ns++;
           out_s += no;
         }
-        if (ns & 3) tok_spec[ns >> 2] = tbuf;
+        if (ns & 3) { batch_front(tbuf, ns & 3); tok_spec[ns >> 2] = tbuf; }
       }
       S.exit_pos[tid] = (uint16_t)xpos;
       S.exit_kind[tid] = (uint8_t)xkind;
       S.last_ck[tid] = (int8_t)last_ck;
       S.spec_ns[tid] = (uint8_t)ns;
       S.spec_out[tid] = (uint16_t)out_s;
-      if (tid == 0) { S.first_bad = PT; S.first_term = PT; S.first_over = PT; S.abort_round = 0; S.pass_owner = -1; S.last_clean = -1; }
+      if (tid == 0) { S.first_bad = PT; S.first_term = PT; S.abort_round = 0; S.pass_owner = -1; }
       __syncthreads();
       // ---- B: re-synchronise with the true entry point handed over by the previous lane.
       // Lane t assumes that lane t-1's true sequence ends in that lane's speculative sequence
@@ -883,15 +966,15 @@ inflate_parallel_kernel(int fmt, int64_t nstreams, const uint8_t *src_base, cons
               }
               if (nh == HEAD_CAP || out_h > (uint32_t)(LANE_BYTE_CAP - 258)) { hcat = H_TERM; hkind = X_CAP; hpos = p; break; }
               uint32_t tok, no;
-              const int r = decode_token(S, lb, lmask, dmask, &tok, &no);
+              const int r = decode_token(S, lb, lmask, dmask, lroot, droot, &tok, &no);
               if (r == T_EOB) { hcat = H_TERM; hkind = X_EOB; hpos = lb.pos(); break; }
               if (r == T_ERR) { hcat = H_TERM; hkind = X_ERR; hpos = p; break; }
-              batch_put(tbuf, nh & 3, tok);
+              batch_push(tbuf, tok);
               if ((nh & 3) == 3) tok_head[nh >> 2] = tbuf;
               nh++;
               out_h += no;
             }
-            if (nh & 3) tok_head[nh >> 2] = tbuf;
+            if (nh & 3) { batch_front(tbuf, nh & 3); tok_head[nh >> 2] = tbuf; }
           }
         }
         STAT(if (hcat != H_BAD && tid > 0) { if (hcat == H_MERGE && ncross == 0) g_stats.hist_nh[nh < 47 ? nh : 47]++; else if (hcat != H_TERM) g_stats.nosync_lanes++; })
@@ -991,17 +1074,7 @@ inflate_parallel_kernel(int fmt, int64_t nstreams, const uint8_t *src_base, cons
           if (w < warp) woff += S.warp_c[w];
         incl += woff;
       }
-      // output budget of the symbol buffer: first lane whose inclusive sum exceeds it
-      if (tid < n_valid && incl > (uint32_t)RSYM) atomicMin(&S.first_over, tid);
-      __syncthreads();
-      const bool cut_by_budget = S.first_over < n_valid;
-      // a round can only be cut where the position of the true sequence is known: behind a lane that
-      // ends in its own speculative sequence
-      if (cut_by_budget && clean && tid < S.first_over) atomicMax(&S.last_clean, tid);
-      __syncthreads();
-      if (cut_by_budget) n_valid = S.last_clean + 1;
       const uint32_t out0 = S.out_pos;
-      const uint32_t my_off = out0 + incl - out_valid; // only meaningful for tid < n_valid
       if (n_valid == 0) {
         if (tid == 0) S.next = NEXT_RETRY; // truncated input: the general kernel reports what the reference does
       } else if (tid == n_valid - 1) {
@@ -1010,7 +1083,7 @@ inflate_parallel_kernel(int fmt, int64_t nstreams, const uint8_t *src_base, cons
         S.round_out = round_out;
         int nx = NEXT_CONTINUE;
         int64_t nb = t_next;
-        if (!cut_by_budget && first_term < first_bad) {
+        if (first_term < first_bad) {
           // closed by this lane's own exit
           if (tkind == X_EOB) nx = S.last_block ? NEXT_FINISH : NEXT_HEADER;
           else if (tkind == X_ERR) nx = NEXT_RETRY;
@@ -1021,24 +1094,40 @@ inflate_parallel_kernel(int fmt, int64_t nstreams, const uint8_t *src_base, cons
           if (x < 0) nx = NEXT_RETRY; // cannot happen
           else nb = base_bit + (int64_t)SUB_BITS * x + S.pass_pos;
         }
-        // otherwise the next lane could not be chained (or did not fit the budget): it opens the next
-        // round at this lane's (normal) exit
+        // otherwise the next lane could not be chained: it opens the next round at this lane's (normal) exit
         if ((int64_t)out0 + round_out > S.dst_cap) nx = NEXT_RETRY; // Unexpected_end_of_output: exact point needed
         S.base_bit = nb;
         S.next = nx;
         S.n_valid = n_valid;
         STAT(g_stats.rounds++; g_stats.valid_lanes += n_valid;
-             if (cut_by_budget) g_stats.cut_budget++; else if (first_term < first_bad) g_stats.cut_term[tkind]++; else g_stats.cut_bad++;)
+             if (first_term < first_bad) g_stats.cut_term[tkind]++; else g_stats.cut_bad++;)
       }
       __syncthreads();
       if (S.next == NEXT_RETRY) break;
-      const uint32_t round_out = S.round_out;
-      // Symbol-buffer coordinates: index i <-> stream position out0 + (i - bias) <-> global address G0 + i,
-      // G0 = (dst + out0) rounded down to 16 bytes, so that 16-symbol chunks are aligned 16-byte stores.
-      const uint32_t bias = (uint32_t)((uintptr_t)(S.dst + out0) & 15);
-      uint8_t *const G0 = S.dst + out0 - bias;
+      const uint32_t round_total = S.round_out;
+      // The round's output leaves in slices of whole lanes that fit the symbol buffer (RSYM symbols; one
+      // slice is the rule).  A back-reference from a later slice into an earlier one is history: those
+      // bytes are already in HBM/L2.  From here on the round metadata (which overlays the symbol buffer)
+      // is dead; what a lane replays sits in its registers.
+      const uint32_t my_end = incl, my_start = incl - out_valid; // round-relative byte range of this lane
+      uint32_t s0 = 0;
+      bool round_failed = false;
+      while (s0 < round_total) {
+      if (tid == 0) S.slice_end = s0;
+      __syncthreads();
+      if (tid < n_valid && my_end <= s0 + (uint32_t)RSYM) atomicMax(&S.slice_end, my_end); // a prefix of the lanes
+      __syncthreads();
+      const uint32_t s1 = S.slice_end;
+      if (s1 == s0) { round_failed = true; break; } // cannot happen: one lane's output always fits
+      const bool in_slice = tid < n_valid && my_start >= s0 && my_end <= s1 && out_valid > 0u;
+      const uint32_t slice_out0 = out0 + s0;   // stream position of the slice's first byte
+      const uint32_t round_out = s1 - s0;      // bytes of this slice
+      // Symbol-buffer coordinates: index i <-> stream position slice_out0 + (i - bias) <-> global address G0 + i,
+      // G0 = (dst + slice_out0) rounded down to 16 bytes, so that 16-symbol chunks are aligned 16-byte stores.
+      const uint32_t bias = (uint32_t)((uintptr_t)(S.dst + slice_out0) & 15);
+      uint8_t *const G0 = S.dst + slice_out0 - bias;
       const uint32_t g0_low = (uint32_t)((uintptr_t)G0 & HIST_MASK);
-      const uint32_t E = bias + round_out; // one past the last symbol of the round
+      const uint32_t E = bias + round_out; // one past the last symbol of the slice
       // ---- D: replay tokens into symbols
       if (tid < 16) {
         if ((uint32_t)tid < bias) S.sym[tid] = 0;
@@ -1051,10 +1140,10 @@ inflate_parallel_kernel(int fmt, int64_t nstreams, const uint8_t *src_base, cons
         //   inside this round (any lane, this one included): markers 256 + source index, no load at all
         //   entirely in earlier rounds: bytes of the history ring
         //   straddling the start of the round, or overlapping itself inside the group: per symbol
-        const int total_tok = tid < n_valid ? d_nh + (d_spec ? ns - d_k : 0) : 0;
+        const int total_tok = in_slice ? d_nh + (d_spec ? ns - d_k : 0) : 0;
         const int delta = HEAD_CAP + d_k - d_nh; // token index -> slot for the speculative part
         const uint4 *head_lane = reinterpret_cast<const uint4 *>(tok_scratch + ((size_t)blockIdx.x * PT + d_owner) * TOK_SLOTS);
-        STAT(if (tid < n_valid) { g_stats.head_tokens += d_nh; g_stats.used_tokens += total_tok; } long iters = 0;)
+        STAT(if (in_slice) { g_stats.head_tokens += d_nh; g_stats.used_tokens += total_tok; } long iters = 0;)
 #if DCMP_HIST_GLOBAL
         // history = the stream's own output in HBM/L2; symbol index s <-> address G0 + s.  L2-coherent loads
         // (.cg): the bytes were stored by this CTA in earlier rounds, a barrier ago at least.
@@ -1063,7 +1152,7 @@ inflate_parallel_kernel(int fmt, int64_t nstreams, const uint8_t *src_base, cons
         const uint32_t *ring32 = reinterpret_cast<const uint32_t *>(S.ring);
 #endif
         int ti = 0;
-        int32_t i = (int32_t)(my_off - out0 + bias); // next symbol to write
+        int32_t i = (int32_t)(my_start - s0 + bias); // next symbol to write
         int32_t s = 0;                // next source symbol of the pending match
         uint32_t rem = 0;             // symbols the pending match still owes
         uint32_t dist = 0;
@@ -1109,7 +1198,7 @@ inflate_parallel_kernel(int fmt, int64_t nstreams, const uint8_t *src_base, cons
             dist = ((t >> 8) & 0x7fffu) + 1u;
             rem = (t & 0xffu) + 3u;
             s = i - (int32_t)dist;
-            if (dist > out0 + (uint32_t)(i - (int32_t)bias)) { // Invalid distance (de.ml:1700): the general kernel reports it
+            if (dist > slice_out0 + (uint32_t)(i - (int32_t)bias)) { // Invalid distance (de.ml:1700): the general kernel reports it
               S.abort_round = 1;
               active = false;
               rem = 0;
@@ -1176,16 +1265,18 @@ inflate_parallel_kernel(int fmt, int64_t nstreams, const uint8_t *src_base, cons
         }
         STAT(g_stats.d_iters += iters; if (iters > g_stats.d_lane_max_iters) g_stats.d_lane_max_iters = iters;)
       }
-      STAT(if (tid == 0) g_stats.spec_tokens += 0;)
-      STAT(g_stats.spec_tokens += ns;)
       __syncthreads();
-      if (S.abort_round) {
+      if (S.abort_round) { round_failed = true; break; }
+      phase_e_drain(S, fmt, G0, g0_low, bias, E, slice_out0, round_out, tid, lane, warp);
+      s0 = s1;
+      } // slices
+      STAT(g_stats.spec_tokens += ns;)
+      if (round_failed) {
         __syncthreads();
         if (tid == 0) S.next = NEXT_RETRY;
         __syncthreads();
         break;
       }
-      phase_e_drain(S, fmt, G0, g0_low, bias, E, out0, round_out, tid, lane, warp);
     } // rounds
 
     // ---------------------------------------------------------------- finish the stream
@@ -1218,7 +1309,7 @@ inflate_parallel_kernel(int fmt, int64_t nstreams, const uint8_t *src_base, cons
 }
 
 size_t inflate_parallel_smem_bytes() { return sizeof(ParSmem) + 128; }
-int inflate_parallel_ctas_per_sm() { return DCMP_HIST_GLOBAL ? 3 : 2; }
+int inflate_parallel_ctas_per_sm() { return DCMP_CTAS_PER_SM; }
 // bytes of token scratch one CTA needs (global memory, stays L2-resident)
 size_t inflate_parallel_scratch_bytes_per_cta() { return (size_t)TOK_SLOTS * PT * sizeof(uint32_t) + 64; }
 

@@ -228,6 +228,7 @@ inline unsigned __dp4a(unsigned a, unsigned b, unsigned c) {
 }
 template <class T> inline T __ldg(const T *p) { return *p; }
 template <class T> inline T __ldcg(const T *p) { return *p; }
+template <class T> inline T __ldcs(const T *p) { return *p; }
 inline void __threadfence_block() {}
 inline void __threadfence() {}
 inline void __nanosleep(unsigned) {}
