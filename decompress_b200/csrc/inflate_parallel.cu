@@ -71,7 +71,7 @@ constexpr int HIST_MASK = HIST - 1;
 #define DCMP_HIST_GLOBAL 1                // 1: read the history from the output buffer in HBM/L2 instead of a shared ring
 #endif
 #ifndef DCMP_RSYM_K
-#define DCMP_RSYM_K 26
+#define DCMP_RSYM_K 25
 #endif
 constexpr int RSYM = DCMP_RSYM_K * 1024;  // symbols one round may produce (+ up to 15 of alignment bias)
 constexpr int SYM_SLOTS = RSYM + 32;
@@ -165,6 +165,18 @@ struct HuffMeta {      // canonical-code description of one alphabet
   int root, maxl;
 };
 
+struct Prefetch {          // the stream this CTA decodes next, claimed and opened ahead of time by one warp
+  int64_t stream;          // claimed index (>= nstreams: none left); -2: nothing claimed
+  const uint8_t *src; int64_t src_len; uint8_t *dst; int64_t dst_cap; int st;
+  int hdr;                 // 1: its first block is dynamic and the header is parsed: lens, hlit, hdist, last_block, base_bit
+  int last_block;
+  uint32_t hlit, hdist;
+  int64_t base_bit;
+  uint32_t codes[CODES_TABLE_SIZE];
+  uint8_t lens[MAX_LENS];
+  __align__(16) uint8_t win[HDR_BYTES];
+};
+
 struct ParSmem {
   __align__(16) uint16_t sym[SYM_SLOTS];   // phase D/E: symbols of the round; phase A/B: checkpoints [NCKPT][PT] u32
 #if !DCMP_HIST_GLOBAL
@@ -206,6 +218,9 @@ struct ParSmem {
   uint32_t adler_a, adler_b;
   uint32_t mbar_phase;
   int abort_round;               // a lane met an invalid distance: the general kernel reports it
+  int hdr_ready;                 // the first header of this stream was parsed ahead (S.pf)
+  int pf_done;                   // the next stream has been claimed during this one
+  Prefetch pf;
   __align__(8) uint64_t mbar;
 };
 #ifndef DCMP_CTAS_PER_SM
@@ -435,7 +450,7 @@ struct HdrBits {
 
 // thread 0 only.  Returns the bit position after the header (>0) or -1 to give the stream to the
 // general kernel.
-__device__ int parse_dynamic_header(ParSmem &S, HdrBits &hb, int64_t bits_avail, int *hlit_out, int *hdist_out) {
+__device__ int parse_dynamic_header(uint32_t *codes, uint8_t *lens, HdrBits &hb, int64_t bits_avail, int *hlit_out, int *hdist_out) {
   hb.refill();
   if (bits_avail - hb.pos() < 14) return -1;
   int hlit = (int)hb.pop(5) + 257, hdist = (int)hb.pop(5) + 1, hclen = (int)hb.pop(4) + 4;
@@ -465,17 +480,17 @@ __device__ int parse_dynamic_header(ParSmem &S, HdrBits &hb, int64_t bits_avail,
     if (!l) continue;
     uint32_t c = first[l]++;
     uint32_t r = __brev(c) >> (32 - l);
-    for (uint32_t i = r; i < 128u; i += (1u << l)) S.codes[i] = mk_entry(K_LIT, (uint32_t)s, 0, (uint32_t)l);
+    for (uint32_t i = r; i < 128u; i += (1u << l)) codes[i] = mk_entry(K_LIT, (uint32_t)s, 0, (uint32_t)l);
   }
   const int total = hlit + hdist;
   int i = 0, prev = 0;
   while (i < total) {
     hb.refill();
-    uint32_t e = S.codes[(uint32_t)hb.hold & 127u];
+    uint32_t e = codes[(uint32_t)hb.hold & 127u];
     hb.pop((int)e_len(e));
     int v = (int)e_base(e);
     if (v < 16) {
-      S.lens[i++] = (uint8_t)v;
+      lens[i++] = (uint8_t)v;
       prev = v;
       continue;
     }
@@ -489,12 +504,12 @@ __device__ int parse_dynamic_header(ParSmem &S, HdrBits &hb, int64_t bits_avail,
       rep = 11 + (int)hb.pop(7); fill = 0;
     }
     if (i + rep > total) return -1;
-    for (int x = 0; x < rep; x++) S.lens[i + x] = (uint8_t)fill;
+    for (int x = 0; x < rep; x++) lens[i + x] = (uint8_t)fill;
     prev = fill;
     i += rep;
   }
   if (bits_avail - hb.pos() < 0) return -1; // header ran past the end of the input
-  if (S.lens[256] == 0) return -1;
+  if (lens[256] == 0) return -1;
   *hlit_out = hlit;
   *hdist_out = hdist;
   return hb.pos();
@@ -701,6 +716,85 @@ __device__ __forceinline__ void stored_copy(ParSmem &S, const int fmt, const uin
   segment_finish(S, fmt, out0, n, s_sum, b_sum, tid, lane, warp);
 }
 
+// Resolve stream k: where its raw DEFLATE bytes and its output window are, and whether this kernel takes it.
+__device__ __forceinline__ int open_stream(int fmt, int64_t k, const uint8_t *src_base, const int64_t *src_off,
+                                           const int64_t *src_len, uint8_t *dst_base, const int64_t *dst_off,
+                                           const int64_t *dst_cap, const uint8_t **src_out, int64_t *len_out,
+                                           uint8_t **dst_out, int64_t *cap_out) {
+  const uint8_t *p = src_base + src_off[k];
+  int64_t n = src_len[k];
+  int st = DCMP_OK;
+  if (fmt == DCMP_FMT_ZLIB) {
+    // Zl.Inf.Ns.inflate, lib/zl.ml:391-417: anything odd goes to the general kernel
+    if (n < 6) st = DCMP_INTERNAL_RETRY;
+    else {
+      uint32_t cmf = p[0], flg = p[1];
+      if (((cmf << 8) + flg) % 31 != 0 || (cmf & 15) != 8) st = DCMP_INTERNAL_RETRY;
+      p += 2;
+      n -= 6;
+    }
+  }
+  *src_out = p;
+  *len_out = n;
+  *dst_out = dst_base + dst_off[k];
+  *cap_out = dst_cap[k];
+  if (*cap_out > 0xfff00000LL || n > 0x0fffffffLL) st = DCMP_INTERNAL_RETRY; // 32-bit positions in the kernel
+  return st;
+}
+
+// One warp claims the CTA's next stream and parses the header of its first block while the other warps are
+// still busy with the current stream: the serial part of a dynamic header (the Huffman-coded code lengths,
+// de.ml:1733-1769) then costs the CTA nothing.  All 32 lanes call.
+__device__ void prefetch_next_stream(ParSmem &S, int fmt, int64_t nstreams, const uint8_t *src_base, const int64_t *src_off,
+                                     const int64_t *src_len, uint8_t *dst_base, const int64_t *dst_off,
+                                     const int64_t *dst_cap, unsigned long long *work_counter, int lane) {
+  Prefetch &P = S.pf;
+  unsigned long long k = 0;
+  if (lane == 0) {
+    k = atomicAdd(work_counter, 1ull);
+    P.stream = (int64_t)k;
+    P.hdr = 0;
+    P.st = DCMP_OK;
+    S.pf_done = 1;
+    if (k < (unsigned long long)nstreams)
+      P.st = open_stream(fmt, (int64_t)k, src_base, src_off, src_len, dst_base, dst_off, dst_cap, &P.src, &P.src_len, &P.dst, &P.dst_cap);
+  }
+  k = __shfl_sync(0xffffffffu, k, 0);
+  __syncwarp();
+  if (k >= (unsigned long long)nstreams || P.st != DCMP_OK || P.src_len <= 0) return;
+  const uint32_t A = (uint32_t)((uintptr_t)P.src & 15);
+  const uint8_t *g = P.src - A;
+  const int64_t vend = ((int64_t)A + P.src_len + 15) & ~(int64_t)15; // one past the last granule that holds input
+  for (int i = lane * 16; i < HDR_BYTES; i += 512) {
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (i < vend) v = __ldcs(reinterpret_cast<const uint4 *>(g + i));
+    *reinterpret_cast<uint4 *>(P.win + i) = v;
+  }
+  __syncwarp();
+  if (lane == 0) {
+    const int bit0 = 8 * (int)A;
+    HdrBits hb;
+    hb.init(P.win, bit0, HDR_BYTES);
+    const int64_t avail = 8 * P.src_len + bit0; // valid bits measured in window coordinates
+    hb.refill();
+    if (avail - hb.pos() >= 3) {
+      const int last = (int)hb.pop(1);
+      if (hb.pop(2) == 2u) {
+        int hlit = 0, hdist = 0;
+        const int used = parse_dynamic_header(P.codes, P.lens, hb, avail, &hlit, &hdist);
+        if (used >= 0) {
+          P.last_block = last;
+          P.hlit = (uint32_t)hlit;
+          P.hdist = (uint32_t)hdist;
+          P.base_bit = used - bit0;
+          P.hdr = 1;
+        }
+      }
+    }
+  }
+  __syncwarp();
+}
+
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(PT, DCMP_CTAS_PER_SM)
 inflate_parallel_kernel(int fmt, int64_t nstreams, const uint8_t *src_base, const int64_t *src_off,
@@ -719,6 +813,7 @@ inflate_parallel_kernel(int fmt, int64_t nstreams, const uint8_t *src_base, cons
     mbar_init(&S.mbar, 1);
     fence_mbar_init();
     S.mbar_phase = 0;
+    S.pf.stream = -2;
   }
   __syncthreads();
 
@@ -726,27 +821,14 @@ inflate_parallel_kernel(int fmt, int64_t nstreams, const uint8_t *src_base, cons
     // ---------------------------------------------------------------- fetch a stream
     __syncthreads();
     if (tid == 0) {
-      unsigned long long k = atomicAdd(work_counter, 1ull);
+      const bool claimed = S.pf.stream != -2; // claimed (and opened) during the previous stream
+      const unsigned long long k = claimed ? (unsigned long long)S.pf.stream : atomicAdd(work_counter, 1ull);
       S.stream = k < (unsigned long long)nstreams ? (int64_t)k : -1;
       if (S.stream >= 0) {
-        const uint8_t *p = src_base + src_off[k];
-        int64_t n = src_len[k];
-        int st = DCMP_OK;
-        if (fmt == DCMP_FMT_ZLIB) {
-          // Zl.Inf.Ns.inflate, lib/zl.ml:391-417: anything odd goes to the general kernel
-          if (n < 6) st = DCMP_INTERNAL_RETRY;
-          else {
-            uint32_t cmf = p[0], flg = p[1];
-            if (((cmf << 8) + flg) % 31 != 0 || (cmf & 15) != 8) st = DCMP_INTERNAL_RETRY;
-            p += 2;
-            n -= 6;
-          }
-        }
-        S.src = p;
-        S.src_len = n;
-        S.dst = dst_base + dst_off[k];
-        S.dst_cap = dst_cap[k];
-        if (S.dst_cap > 0xfff00000LL || n > 0x0fffffffLL) st = DCMP_INTERNAL_RETRY; // 32-bit positions below
+        int st;
+        if (claimed) { S.src = S.pf.src; S.src_len = S.pf.src_len; S.dst = S.pf.dst; S.dst_cap = S.pf.dst_cap; st = S.pf.st; }
+        else st = open_stream(fmt, (int64_t)k, src_base, src_off, src_len, dst_base, dst_off, dst_cap, &S.src, &S.src_len, &S.dst, &S.dst_cap);
+        S.hdr_ready = claimed && st == DCMP_OK && S.pf.hdr;
         S.base_bit = 0;
         S.out_pos = 0;
         S.last_block = 0;
@@ -755,6 +837,8 @@ inflate_parallel_kernel(int fmt, int64_t nstreams, const uint8_t *src_base, cons
         S.adler_a = 1;
         S.adler_b = 0;
       }
+      S.pf.stream = -2;
+      S.pf_done = 0;
     }
     __syncthreads();
     if (S.stream < 0) break;
@@ -776,8 +860,20 @@ inflate_parallel_kernel(int fmt, int64_t nstreams, const uint8_t *src_base, cons
       }
       if (S.next == NEXT_HEADER) {
         // ------------------------------------------------------------ block header
-        stage_window(S, g0, HDR_BYTES, (int)(vend - v0 > HDR_BYTES ? HDR_BYTES : vend - v0), tid);
-        if (tid == 0) {
+        const bool ahead = S.hdr_ready != 0; // parsed while the previous stream was being decoded
+        __syncthreads();
+        if (ahead) {
+          for (int i = tid; i < MAX_LENS; i += PT) S.lens[i] = S.pf.lens[i];
+          if (tid == 0) {
+            S.last_block = S.pf.last_block;
+            S.hdr_hlit = S.pf.hlit;
+            S.hdr_hdist = S.pf.hdist;
+            S.base_bit = S.pf.base_bit;
+            S.hdr_ready = 0;
+            S.next = NEXT_CONTINUE;
+          }
+        } else stage_window(S, g0, HDR_BYTES, (int)(vend - v0 > HDR_BYTES ? HDR_BYTES : vend - v0), tid);
+        if (tid == 0 && !ahead) {
           STAT(g_stats.hdr_rounds++;)
           HdrBits hb;
           hb.init((const uint8_t *)S.win, bit0, HDR_BYTES);
@@ -790,7 +886,7 @@ inflate_parallel_kernel(int fmt, int64_t nstreams, const uint8_t *src_base, cons
             uint32_t type = hb.pop(2);
             if (type == 2) {
               int hlit = 0, hdist = 0;
-              int used = parse_dynamic_header(S, hb, avail, &hlit, &hdist);
+              int used = parse_dynamic_header(S.codes, S.lens, hb, avail, &hlit, &hdist);
               if (used < 0) nx = NEXT_RETRY;
               else {
                 S.hdr_hlit = (uint32_t)hlit;
@@ -978,6 +1074,11 @@ inflate_parallel_kernel(int fmt, int64_t nstreams, const uint8_t *src_base, cons
           }
         }
         STAT(if (hcat != H_BAD && tid > 0) { if (hcat == H_MERGE && ncross == 0) g_stats.hist_nh[nh < 47 ? nh : 47]++; else if (hcat != H_TERM) g_stats.nosync_lanes++; })
+        // the last warp, once its own heads are done, opens the CTA's next stream (the others are still in their tails)
+        if (warp == NWARP - 1 && !S.pf_done) {
+          __syncwarp();
+          prefetch_next_stream(S, fmt, nstreams, src_base, src_off, src_len, dst_base, dst_off, dst_cap, work_counter, lane);
+        }
         // the lane after the ones this head covers is the next one whose own head counts
         int last = tid + ncross;           // lane in which the head ended
         if (last > PT - 1) last = PT - 1;  // (H_PASS)
@@ -1156,22 +1257,15 @@ inflate_parallel_kernel(int fmt, int64_t nstreams, const uint8_t *src_base, cons
         int32_t s = 0;                // next source symbol of the pending match
         uint32_t rem = 0;             // symbols the pending match still owes
         uint32_t dist = 0;
-        // token batches (four tokens, 128 bits) are fetched two batches ahead of their use
-        uint4 cur = make_uint4(0, 0, 0, 0), nx1 = make_uint4(0, 0, 0, 0), nx2 = make_uint4(0, 0, 0, 0);
-        int cur_b = -1;
+        // tokens are fetched three ahead of their use (scalar L2 loads: the lists were written as 128-bit batches)
+        const uint32_t *head32 = tok_scratch + ((size_t)blockIdx.x * PT + d_owner) * TOK_SLOTS + d_h0;
+        const uint32_t *spec32 = tok_scratch + ((size_t)blockIdx.x * PT + tid) * TOK_SLOTS + delta;
+        auto tok_at = [&](int t) { return __ldcg((t < d_nh ? head32 : spec32) + t); };
+        uint32_t q0 = 0, q1 = 0, q2 = 0;
+        if (0 < total_tok) q0 = tok_at(0);
+        if (1 < total_tok) q1 = tok_at(1);
+        if (2 < total_tok) q2 = tok_at(2);
         bool active = total_tok > 0;
-        auto slot_of = [&](int t) { return t < d_nh ? t + d_h0 : t + delta; };
-        auto load_batch = [&](int t) { return t < d_nh ? head_lane[(t + d_h0) >> 2] : tok_lane[(t + delta) >> 2]; };
-        auto next_batch_start = [&](int t) { // first token of the batch after the one that holds token t
-          int t2 = t + 4 - (slot_of(t) & 3);
-          if (t < d_nh && t2 > d_nh) t2 = d_nh;
-          return t2;
-        };
-        if (active) {
-          nx1 = load_batch(0);
-          const int t1 = next_batch_start(0);
-          if (t1 < total_tok) nx2 = load_batch(t1);
-        }
         while (__any_sync(0xffffffffu, active)) {
           STAT(if (active) iters++;)
           // -- next token, for the lanes that finished the previous one
@@ -1179,18 +1273,10 @@ inflate_parallel_kernel(int fmt, int64_t nstreams, const uint8_t *src_base, cons
           if (fetch && ti == total_tok) { active = false; fetch = false; }
           uint32_t t = 0;
           if (fetch) {
-            const int slot = slot_of(ti);
-            if ((slot >> 2) != cur_b) {
-              cur = nx1;
-              nx1 = nx2;
-              cur_b = slot >> 2;
-              const int ta = next_batch_start(ti);
-              if (ta < total_tok) {
-                const int tb = next_batch_start(ta);
-                if (tb < total_tok) nx2 = load_batch(tb);
-              }
-            }
-            t = batch_get(cur, slot & 3);
+            t = q0;
+            q0 = q1;
+            q1 = q2;
+            if (ti + 3 < total_tok) q2 = tok_at(ti + 3);
             ti++;
           }
           const bool new_match = fetch && tok_is_match(t);
