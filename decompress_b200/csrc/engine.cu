@@ -29,7 +29,10 @@ void launch_gzip_trailer(int64_t n, const uint8_t *src_base, const int64_t *src_
                          int64_t *produced, int32_t *status, cudaStream_t stream);
 void launch_lzo_decode(int mode, int64_t n, const uint8_t *src_base, const int64_t *src_off, const int64_t *src_len,
                        uint8_t *dst_base, const int64_t *dst_off, const int64_t *dst_cap, int64_t *consumed,
-                       int64_t *produced, int32_t *status, cudaStream_t stream);
+                       int64_t *produced, int32_t *status, int only_status, cudaStream_t stream);
+int launch_lzo_parallel(int mode, int64_t n, const uint8_t *src_base, const int64_t *src_off, const int64_t *src_len,
+                        uint8_t *dst_base, const int64_t *dst_off, const int64_t *dst_cap, int64_t *consumed,
+                        int64_t *produced, int32_t *status, cudaStream_t stream);
 int launch_deflate(int level, int fmt, int64_t nstreams, int64_t nchunks, const uint8_t *src_base, const void *chunks,
                    const int64_t *first_chunk, void *outs, uint8_t *slots, int64_t *chunk_dst, uint32_t *tok_scratch,
                    unsigned long long *work_counter, int ctas, uint8_t *dst_base, const int64_t *dst_off,
@@ -373,9 +376,22 @@ int dcmp_lzo_uncompress_batch_device(dcmp_engine *e, int mode, int64_t n, const 
   if (!e || n < 0 || (mode != 0 && mode != 1)) return DCMP_API_INVALID_ARGUMENT;
   if (n == 0) return DCMP_API_OK;
   CU(cudaSetDevice(e->device));
-  dcmp::launch_lzo_decode(mode, n, d_src_base, d_src_off, d_src_len, d_dst_base, d_dst_off, d_dst_cap, d_consumed,
-                          d_produced, d_status, (cudaStream_t)cuda_stream);
-  e->launches += 1;
+  if (e->mode == 0) {
+    // stage 1: one CTA per block (serial opcode parse, CTA-wide copies); stage 2: the one-warp-per-block
+    // kernel on exactly the blocks stage 1 gave up (malformed input, short output window, ...)
+    int rc = dcmp::launch_lzo_parallel(mode, n, d_src_base, d_src_off, d_src_len, d_dst_base, d_dst_off, d_dst_cap, d_consumed,
+                                       d_produced, d_status, (cudaStream_t)cuda_stream);
+    if (rc != 0) { set_err("launch_lzo_parallel", (cudaError_t)rc); return DCMP_API_CUDA_ERROR; }
+    static const bool no_fallback = getenv("DCMP_LZO_NO_FALLBACK") != nullptr; // debugging aid: given-up blocks keep status 0x7f
+    if (!no_fallback)
+      dcmp::launch_lzo_decode(mode, n, d_src_base, d_src_off, d_src_len, d_dst_base, d_dst_off, d_dst_cap, d_consumed,
+                              d_produced, d_status, dcmp::INTERNAL_RETRY, (cudaStream_t)cuda_stream);
+    e->launches += 2;
+  } else {
+    dcmp::launch_lzo_decode(mode, n, d_src_base, d_src_off, d_src_len, d_dst_base, d_dst_off, d_dst_cap, d_consumed,
+                            d_produced, d_status, -1, (cudaStream_t)cuda_stream);
+    e->launches += 1;
+  }
   CU(cudaGetLastError());
   return DCMP_API_OK;
 }

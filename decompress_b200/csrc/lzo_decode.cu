@@ -245,12 +245,14 @@ __device__ int lzo_run(LzoWarp<P> &w) {
 __global__ void __launch_bounds__(LZO_WARPS * 32)
 lzo_decode_kernel(int mode, int64_t nblocks, const uint8_t *src_base, const int64_t *src_off, const int64_t *src_len,
                   uint8_t *dst_base, const int64_t *dst_off, const int64_t *dst_cap, int64_t *consumed,
-                  int64_t *produced, int32_t *status) {
+                  int64_t *produced, int32_t *status, int only_status) {
   DCMP_DYN_SMEM(smem_raw);
   uint8_t(*cache)[LZO_CACHE] = reinterpret_cast<uint8_t(*)[LZO_CACHE]>(smem_raw + (size_t)LZO_WARPS * LZO_RING);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t k = (int64_t)blockIdx.x * LZO_WARPS + warp;
   if (k >= nblocks) return;
+  // second stage of the dispatcher: only the blocks the CTA-per-block kernel (lzo_parallel.cu) gave up
+  if (only_status >= 0 && status[k] != only_status) return;
   const int64_t n_in = src_len[k], n_out = dst_cap[k];
   int r;
   int64_t cons, prod;
@@ -287,7 +289,7 @@ lzo_decode_kernel(int mode, int64_t nblocks, const uint8_t *src_base, const int6
 #ifndef DCMP_EMU
 void launch_lzo_decode(int mode, int64_t n, const uint8_t *src_base, const int64_t *src_off, const int64_t *src_len,
                        uint8_t *dst_base, const int64_t *dst_off, const int64_t *dst_cap, int64_t *consumed,
-                       int64_t *produced, int32_t *status, cudaStream_t stream) {
+                       int64_t *produced, int32_t *status, int only_status, cudaStream_t stream) {
   if (n <= 0) return;
   const int64_t blocks = (n + LZO_WARPS - 1) / LZO_WARPS;
   const size_t smem = (size_t)LZO_WARPS * (LZO_RING + LZO_CACHE);
@@ -297,7 +299,7 @@ void launch_lzo_decode(int mode, int64_t n, const uint8_t *src_base, const int64
     configured = true;
   }
   lzo_decode_kernel<<<(unsigned)blocks, LZO_WARPS * 32, smem, stream>>>(mode, n, src_base, src_off, src_len, dst_base,
-                                                                    dst_off, dst_cap, consumed, produced, status);
+                                                                    dst_off, dst_cap, consumed, produced, status, only_status);
 }
 #endif
 

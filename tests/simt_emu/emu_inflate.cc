@@ -6,6 +6,7 @@
 #include "../../decompress_b200/csrc/inflate_serial.cu"
 #include "../../decompress_b200/csrc/inflate_parallel.cu"
 #include "../../decompress_b200/csrc/lzo_decode.cu"
+#include "../../decompress_b200/csrc/lzo_parallel.cu"
 #include "../../decompress_b200/csrc/deflate.cu"
 
 extern "C" {
@@ -38,13 +39,27 @@ int emu_inflate_batch(int mode, int fmt, int64_t n, const uint8_t *src, const in
   return retried;
 }
 
+// lzo_mode: 0 = Lzo.uncompress, 1 = uncompress_with_buffer; which: 0 = CTA-per-block kernel then the general one on
+// the blocks it gave up (like engine.cu), 2 = general kernel only.  Returns the number of blocks given up.
+int emu_lzo_batch2(int lzo_mode, int which, int64_t n, const uint8_t *src, const int64_t *soff, const int64_t *slen, uint8_t *dst,
+                   const int64_t *doff, const int64_t *dcap, int64_t *cons, int64_t *prod, int32_t *status) {
+  using namespace dcmp;
+  int retried = 0;
+  if (which != 2) {
+    simt::launch(simt::dim3((unsigned)n), simt::dim3(LZP_PT), lzo_parallel_smem_bytes(), [&]() {
+      lzo_parallel_kernel(lzo_mode, n, src, soff, slen, dst, doff, dcap, cons, prod, status);
+    });
+    for (int64_t k = 0; k < n; k++) retried += status[k] == LZP_RETRY;
+    if (!retried) return 0;
+  }
+  simt::launch(simt::dim3((unsigned)((n + LZO_WARPS - 1) / LZO_WARPS)), simt::dim3(LZO_WARPS * 32), (size_t)LZO_WARPS * (LZO_RING + LZO_CACHE), [&]() {
+    lzo_decode_kernel(lzo_mode, n, src, soff, slen, dst, doff, dcap, cons, prod, status, which == 2 ? -1 : LZP_RETRY);
+  });
+  return retried;
+}
 int emu_lzo_batch(int mode, int64_t n, const uint8_t *src, const int64_t *soff, const int64_t *slen, uint8_t *dst,
                   const int64_t *doff, const int64_t *dcap, int64_t *cons, int64_t *prod, int32_t *status) {
-  using namespace dcmp;
-  simt::launch(simt::dim3((unsigned)((n + LZO_WARPS - 1) / LZO_WARPS)), simt::dim3(LZO_WARPS * 32), (size_t)LZO_WARPS * (LZO_RING + LZO_CACHE), [&]() {
-    lzo_decode_kernel(mode, n, src, soff, slen, dst, doff, dcap, cons, prod, status);
-  });
-  return 0;
+  return emu_lzo_batch2(mode, 0, n, src, soff, slen, dst, doff, dcap, cons, prod, status);
 }
 
 int emu_deflate_batch(int level, int fmt, int64_t n, const uint8_t *src, const int64_t *soff, const int64_t *slen, uint8_t *dst,
