@@ -34,18 +34,18 @@ constexpr int LZP_RSYM = 20 * 1024;      // output symbols per round (+ up to 15
 constexpr int LZP_WIN = 16 * 1024;       // input bytes staged per round
 constexpr int LZP_DEC = 8 * 1024;        // window positions decoded as candidates (instructions may extend beyond)
 constexpr int LZP_MAXI = 4096;           // instructions per round
-constexpr int LZP_PER = LZP_MAXI / LZP_PT; // instructions one thread scans / replays
 constexpr int LZP_MAXZ = 80;            // zero bytes of a length extension a candidate decode follows (255 bytes each)
 constexpr int LZP_RETRY = 0x7f;          // never leaves the library
-constexpr uint32_t LZP_END = 0x7ffd, LZP_BAD = 0x7ffe, LZP_OUT = 0x7fff; // next[] codes above any window position
-static_assert(LZP_WIN < (int)LZP_END && LZP_DEC <= (1 << 13), "");
+constexpr uint32_t LZP_FAR = 0x7ffb, LZP_STEP = 0x7ffc, LZP_END = 0x7ffd, LZP_BAD = 0x7ffe, LZP_OUT = 0x7fff; // next[] codes above any index
+constexpr uint32_t LZP_FIRST = 0x4000;   // visited[]: the block's first byte (state class 2)
+static_assert(LZP_DEC == (1 << 13) && 2 * LZP_DEC * 2 <= LZP_RSYM * 2, "next2 overlays the symbol buffer");
 
 struct LzpSmem {
   static constexpr int THREADS = LZP_PT;
   __align__(16) uint16_t sym[LZP_RSYM + 64];
   __align__(16) uint8_t win[LZP_WIN + 32];
-  uint16_t next[2][LZP_DEC];   // [14:0] next window position or LZP_*, [15] next state class
-  uint16_t visited[LZP_MAXI];  // [12:0] window position, [14:13] state class (2: first byte of the block)
+  uint16_t next[2 * LZP_DEC];  // index = state class << 13 | window position; value = index of the next instruction, or LZP_*
+  uint16_t visited[LZP_MAXI];  // index of every instruction of the round (| LZP_FIRST)
   uint32_t part[LZP_PT];       // scan partials
   unsigned long long adl_s[LZP_PT / 32];
   long long adl_b[LZP_PT / 32];
@@ -193,32 +193,46 @@ lzo_parallel_kernel(int mode, int64_t nblocks, const uint8_t *src_base, const in
       if (tid == 0 && valid > 0) S.mbar_phase ^= 1u;
     }
     // ---- 1: every position as a candidate instruction start, in both state classes
-    for (int c = 0; c < 2; c++)
-      for (int p = tid; p < LZP_DEC; p += LZP_PT) {
-        const LzpInst r = lzp_decode(S.win, p, c, wlim, at_end);
-        const uint32_t nx = r.kind ? r.kind : (uint32_t)(p + r.hdr + r.lit + r.trail);
-        S.next[c][p] = (uint16_t)(nx | ((uint32_t)r.ncls << 15));
-      }
+    auto link = [&](const LzpInst &r, int p) -> uint32_t { // where the instruction at p leads
+      if (r.kind) return r.kind;
+      const int np = p + r.hdr + r.lit + r.trail;
+      return np < LZP_DEC ? (uint32_t)np | ((uint32_t)r.ncls << 13) : LZP_FAR;
+    };
+    for (int x = tid; x < 2 * LZP_DEC; x += LZP_PT) {
+      const int p = x & (LZP_DEC - 1);
+      S.next[x] = (uint16_t)link(lzp_decode(S.win, p, x >> 13, wlim, at_end), p);
+    }
     __syncthreads();
-    // ---- 2: the chain of real instructions
+    // two instructions ahead (the symbol buffer is idle until the replay: it lends the space)
+    uint16_t *next2 = S.sym;
+    for (int x = tid; x < 2 * LZP_DEC; x += LZP_PT) {
+      const uint32_t e1 = S.next[x];
+      uint32_t e2 = LZP_STEP;
+      if (e1 < 2u * LZP_DEC) {
+        e2 = S.next[e1];
+        if (e2 >= 2u * LZP_DEC) e2 = LZP_STEP;
+      }
+      next2[x] = (uint16_t)e2;
+    }
+    __syncthreads();
+    // ---- 2: the chain of real instructions: two per shared-memory round trip
     const uint32_t out0 = S.out_pos;
     if (tid == 0) {
-      int p = (int)(ip0 - w_lo), cls = cls0, n = 0;
+      const int p0 = (int)(ip0 - w_lo);
+      uint32_t x = (uint32_t)p0 | ((uint32_t)(cls0 & 1) << 13);
+      int n = 0;
       int64_t bulk = 0;
-      while (n < LZP_MAXI && p < LZP_DEC) {
-        uint32_t e;
-        if (cls == 2) {
-          const LzpInst r = lzp_decode(S.win, p, 2, wlim, at_end);
-          e = (r.kind ? r.kind : (uint32_t)(p + r.hdr + r.lit + r.trail)) | ((uint32_t)r.ncls << 15);
-        } else e = S.next[cls][p];
-        const uint32_t v = e & 0x7fffu;
-        if (v == LZP_OUT || v == LZP_BAD) {
+      bool stop = false;
+      int64_t ip_after = -1;
+      int cls_after = 0;
+      auto single = [&](uint32_t e, uint32_t vis) { // one instruction whose link is e; returns false when the chain stops
+        if (e == LZP_OUT || e == LZP_BAD) {
           if (n == 0) {
             // the round's first instruction does not fit the window: a long literal run is moved directly
             // (its header is re-read from global memory byte-wise, the zero run of its length may be long)
             S.give_up = 1;
-            if (v == LZP_OUT && cls != 1) { // (the block's first byte, if it is 0, opens an ordinary literal run)
-              int64_t q = w_lo + p;
+            if (e == LZP_OUT && cls0 != 1) { // (the block's first byte, if it is 0, opens an ordinary literal run)
+              int64_t q = w_lo + p0;
               const int chr = in[q++];
               if (chr == 0) {
                 int64_t z = 0;
@@ -234,23 +248,38 @@ lzo_parallel_kernel(int mode, int64_t nblocks, const uint8_t *src_base, const in
               }
             }
           }
-          break;
+          return false;
         }
-        S.visited[n++] = (uint16_t)((uint32_t)p | ((uint32_t)cls << 13));
-        if (v == LZP_END) {
-          const LzpInst r = lzp_decode(S.win, p, cls, wlim, at_end);
-          S.ended = 1;
-          S.ip_end = w_lo + p + r.hdr;
-          n--; // the terminator produces nothing
-          break;
+        if (e == LZP_END || e == LZP_FAR) {
+          const LzpInst r = lzp_decode(S.win, (int)(vis & (LZP_DEC - 1)), (vis & LZP_FIRST) ? 2 : (int)((vis >> 13) & 1), wlim, at_end);
+          if (e == LZP_END) {
+            S.ended = 1;
+            S.ip_end = w_lo + (int64_t)(vis & (LZP_DEC - 1)) + r.hdr; // the terminator produces nothing: not listed
+          } else {
+            S.visited[n++] = (uint16_t)vis;
+            ip_after = w_lo + (int64_t)(vis & (LZP_DEC - 1)) + r.hdr + r.lit + r.trail;
+            cls_after = r.ncls;
+          }
+          return false;
         }
-        p = (int)v;
-        cls = (int)(e >> 15);
+        S.visited[n++] = (uint16_t)vis;
+        x = e;
+        return true;
+      };
+      if (cls0 == 2) stop = !single(link(lzp_decode(S.win, p0, 2, wlim, at_end), p0), (uint32_t)p0 | LZP_FIRST);
+      while (!stop && n + 2 <= LZP_MAXI) {
+        const uint32_t e1 = S.next[x], e2 = next2[x];
+        if (e2 >= 2u * LZP_DEC) break;
+        S.visited[n] = (uint16_t)x;
+        S.visited[n + 1] = (uint16_t)e1;
+        n += 2;
+        x = e2;
       }
+      while (!stop && n < LZP_MAXI) stop = !single(S.next[x], x);
       S.nvis = n;
       S.bulk_len = bulk;
-      S.ip_after = w_lo + p;
-      S.cls_after = cls;
+      S.ip_after = ip_after >= 0 ? ip_after : w_lo + (int64_t)(x & (LZP_DEC - 1));
+      S.cls_after = ip_after >= 0 ? cls_after : (int)(x >> 13);
       if (n == 0 && !bulk && !S.ended) S.give_up = 1; // no progress: cannot happen on the happy path
     }
     __syncthreads();
@@ -271,13 +300,14 @@ lzo_parallel_kernel(int mode, int64_t nblocks, const uint8_t *src_base, const in
       __syncthreads();
       continue;
     }
-    // ---- 3: output lengths, scan, cut at the budget, validity (a thread owns LZP_PER consecutive instructions and
+    // ---- 3: output lengths, scan, cut at the budget, validity (a thread owns `per` consecutive instructions and
     // decodes them again in every pass: cheaper than keeping them)
     const int n = S.nvis;
-    const int j0 = tid * LZP_PER;
+    const int per = (n + LZP_PT - 1) / LZP_PT; // consecutive instructions per thread
+    const int j0 = tid * per;
     auto inst = [&](int j) {
       const uint32_t vv = S.visited[j];
-      return lzp_decode(S.win, (int)(vv & 0x1fffu), (int)(vv >> 13), wlim, at_end);
+      return lzp_decode(S.win, (int)(vv & (LZP_DEC - 1)), (vv & LZP_FIRST) ? 2 : (int)((vv >> 13) & 1), wlim, at_end);
     };
     auto out_len = [](const LzpInst &r) {
       const uint32_t ol = (uint32_t)(r.lit + r.mlen + r.trail);
@@ -285,7 +315,7 @@ lzo_parallel_kernel(int mode, int64_t nblocks, const uint8_t *src_base, const in
     };
     uint32_t len_sum = 0;
 #pragma unroll 1
-    for (int j = j0; j < j0 + LZP_PER && j < n; j++) len_sum += out_len(inst(j));
+    for (int j = j0; j < j0 + per && j < n; j++) len_sum += out_len(inst(j));
     uint32_t incl = len_sum;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -301,7 +331,7 @@ lzo_parallel_kernel(int mode, int64_t nblocks, const uint8_t *src_base, const in
     {
       uint32_t o = base;
 #pragma unroll 1
-      for (int j = j0; j < j0 + LZP_PER && j < n && o <= (uint32_t)LZP_RSYM; j++) {
+      for (int j = j0; j < j0 + per && j < n && o <= (uint32_t)LZP_RSYM; j++) {
         const uint32_t ol = out_len(inst(j));
         if (o + ol > (uint32_t)LZP_RSYM) atomicMin(&S.cut, j);
         o += ol;
@@ -318,7 +348,7 @@ lzo_parallel_kernel(int mode, int64_t nblocks, const uint8_t *src_base, const in
     {
       uint32_t o = base;
 #pragma unroll 1
-      for (int j = j0; j < j0 + LZP_PER && j < ncut; j++) {
+      for (int j = j0; j < j0 + per && j < ncut; j++) {
         const LzpInst r = inst(j);
         const int64_t o_abs = (int64_t)out0 + o;
         const uint32_t ol = (uint32_t)(r.lit + r.mlen + r.trail);
@@ -342,9 +372,9 @@ lzo_parallel_kernel(int mode, int64_t nblocks, const uint8_t *src_base, const in
     {
       int32_t i = (int32_t)(bias + base);
 #pragma unroll 1
-      for (int j = j0; j < j0 + LZP_PER && j < ncut; j++) {
+      for (int j = j0; j < j0 + per && j < ncut; j++) {
         const LzpInst r = inst(j);
-        const uint8_t *pay = S.win + (S.visited[j] & 0x1fffu) + r.hdr; // literal bytes follow the header
+        const uint8_t *pay = S.win + (S.visited[j] & (LZP_DEC - 1)) + r.hdr; // literal bytes follow the header
         if (r.mlen) {
           const int32_t s = i - (int32_t)r.dist; // symbol index of the first source byte (below bias: earlier rounds)
           const uint32_t len = (uint32_t)r.mlen, dist = r.dist;
@@ -367,8 +397,8 @@ lzo_parallel_kernel(int mode, int64_t nblocks, const uint8_t *src_base, const in
     if (tid == 0) {
       if (ncut < n) { // cut by the budget: the next round starts at the first instruction left out
         const uint32_t vv = S.visited[ncut];
-        S.ip = w_lo + (int64_t)(vv & 0x1fffu);
-        S.cls = (int)(vv >> 13);
+        S.ip = w_lo + (int64_t)(vv & (LZP_DEC - 1));
+        S.cls = (int)((vv >> 13) & 1);
         S.ended = 0;
       } else {
         S.ip = S.ip_after;
