@@ -66,7 +66,7 @@ constexpr int LANE_BYTE_CAP = 4096;       // bytes a lane may produce per pass (
 constexpr int CKPT_SHIFT = 5;             // one checkpoint per 32-bit window of the sub-chunk
 constexpr int NCKPT = (SUB_BITS >> CKPT_SHIFT) + 1;
 #ifndef DCMP_RSYM_K
-#define DCMP_RSYM_K 25
+#define DCMP_RSYM_K 26
 #endif
 constexpr int RSYM = DCMP_RSYM_K * 1024;  // symbols one round may produce (+ up to 15 of alignment bias)
 constexpr int SYM_SLOTS = RSYM + 32;
@@ -184,8 +184,6 @@ struct ParSmem {
   __align__(16) uint32_t win[WIN_BYTES / 4 + 4]; // staged compressed input (TMA destination)
   uint32_t lit[(1 << LIT_ROOT) + LIT_SUB];   // root table, then the sub-tables of codes longer than the root
   uint32_t dist[(1 << DIST_ROOT) + DIST_SUB];
-  uint32_t codes[CODES_TABLE_SIZE];
-  uint32_t code_of[MAX_LENS];    // table build scratch: bit-reversed code | len << 16 per symbol
   uint8_t lens[MAX_LENS];
   HuffMeta ml, md;
   uint32_t run_cnt[16];
@@ -303,7 +301,7 @@ __device__ __forceinline__ int decode_token(ParSmem &S, LaneBits &lb, uint32_t l
 // exactly 1) and, for the literal/length and distance alphabets, the two incomplete shapes the
 // reference accepts (de.ml:544-550): no code at all and a single 1-bit code; their unassigned slots
 // are PE_INVALID, which sends a stream that really uses them to the general kernel.  Returns false
-// (CTA-uniform) otherwise, or when the sub-tables do not fit.  `scratch`: 1 << root_max words.
+// (CTA-uniform) otherwise, or when the sub-tables do not fit.  `scratch`: (1 << root_max) + MAX_LENS words.
 __device__ __forceinline__ uint32_t pe_symbol(int kind, int s, uint32_t l) {
   if (kind == KIND_DISTS) {
     const uint32_t b = c_dist_base[s & 31];
@@ -316,6 +314,7 @@ __device__ __forceinline__ uint32_t pe_symbol(int kind, int s, uint32_t l) {
 }
 __device__ bool build_fast_table(ParSmem &S, int kind, const uint8_t *lens, int n, uint32_t *tbl, int root_max, int sub_cap,
                                  HuffMeta &m, uint32_t *scratch, int tid) {
+  uint32_t *const code_of = scratch + (1 << root_max); // per symbol: bit-reversed code | len << 16
   __syncthreads();
   if (tid < 16) S.run_cnt[tid] = 0;
   __syncthreads();
@@ -370,10 +369,10 @@ __device__ bool build_fast_table(ParSmem &S, int kind, const uint8_t *lens, int 
         if (l) {
           uint32_t code = (uint32_t)m.first[l] + before + rank;
           uint32_t r = __brev(code) >> (32 - l);
-          S.code_of[s] = r | (l << 16);
+          code_of[s] = r | (l << 16);
           if ((int)l > root) atomicMax(&scratch[r & rmask], l - (uint32_t)root); // index bits its sub-table needs
         } else {
-          S.code_of[s] = 0;
+          code_of[s] = 0;
         }
       }
     }
@@ -396,7 +395,7 @@ __device__ bool build_fast_table(ParSmem &S, int kind, const uint8_t *lens, int 
   __syncthreads();
   if (!S.tbl_ok) return false;
   for (int s = tid; s < n; s += PT) {
-    const uint32_t co = S.code_of[s];
+    const uint32_t co = code_of[s];
     const uint32_t l = co >> 16;
     if (!l) continue;
     const uint32_t r = co & 0xffffu;
@@ -713,7 +712,7 @@ inflate_parallel_kernel(int fmt, int64_t nstreams, const uint8_t *src_base, cons
             uint32_t type = hb.pop(2);
             if (type == 2) {
               int hlit = 0, hdist = 0;
-              int used = parse_dynamic_header(S.codes, S.lens, hb, avail, &hlit, &hdist);
+              int used = parse_dynamic_header(S.pf.codes, S.lens, hb, avail, &hlit, &hdist); // (pf.codes is scratch: the two parses never overlap)
               if (used < 0) nx = NEXT_RETRY;
               else {
                 S.hdr_hlit = (uint32_t)hlit;

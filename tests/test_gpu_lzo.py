@@ -134,3 +134,33 @@ def test_single_call_mirrors(eng):
     assert lzo.uncompress(comp, np.zeros(10, dtype=np.uint8), engine=eng) == Error("Invalid_argument")
     assert lzo.uncompress_with_buffer(comp, chunk=16, engine=eng) == Ok(b"againandagainandagain" * 50)
     assert lzo.uncompress_with_buffer(b"\x10\x00\x00", engine=eng) == Error("Malformed")
+
+
+def test_cta_per_block_kernel_paths(eng):
+    """Shapes that steer the CTA-per-block kernel (lzo_parallel.cu) through every branch: literal runs longer
+    than its 16 KiB input window (moved by raw_copy), matches longer than a round's symbol budget (given to the
+    warp-per-block kernel), rounds cut by the budget (highly compressible input), blocks spanning many
+    rounds, odd source/destination alignment inside the slabs."""
+    rng = np.random.default_rng(17)
+    noise = lambda n: rng.integers(0, 256, n, dtype=np.uint8).tobytes()
+    txt = workloads.text(700000, 41)
+    plains = [
+        noise(20000), noise(300000),                           # one literal run each
+        txt[:1000] + noise(70000) + txt[1000:3000],            # a long run between ordinary instructions
+        bytes(200000), b"ab" * 150000, (b"0123456789abcdef" * 64 + b"x") * 300,   # long / periodic matches
+        txt, txt[:333333] + bytes(5000) + txt[400000:500000],
+        b"".join(txt[i * 3000:i * 3000 + 700] + noise(40) for i in range(150)),
+    ]
+    comps = [workloads.lzo1x_1_compress(p) for p in plains]
+    for mode in (0, 1):
+        res = lzo.uncompress_batch(comps, [len(p) for p in plains], mode=mode, engine=eng)
+        for k, (st, cons, prod, out) in enumerate(res):
+            assert (st, cons, prod) == (0, len(comps[k]), len(plains[k])), (mode, k)
+            assert out == plains[k], (mode, k)
+    # every alignment of the block inside the slabs (the input window and the drain are 16-byte machines)
+    small = [workloads.lzo1x_1_compress(txt[o:o + 5000 + o]) for o in range(17)]
+    res = lzo.uncompress_batch(small, [5000 + o for o in range(17)], engine=eng)
+    for o, (st, cons, prod, out) in enumerate(res):
+        assert (st, cons, prod, out) == (0, len(small[o]), 5000 + o, txt[o:o + 5000 + o]), o
+    _check(comps, [len(p) - 1 for p in plains], 0, eng)
+    _check(comps, [len(p) // 2 for p in plains], 1, eng)
