@@ -33,12 +33,14 @@ constexpr int LZP_PT = 256;
 constexpr int LZP_RSYM = 20 * 1024;      // output symbols per round (+ up to 15 of alignment bias)
 constexpr int LZP_WIN = 16 * 1024;       // input bytes staged per round
 constexpr int LZP_DEC = 8 * 1024;        // window positions decoded as candidates (instructions may extend beyond)
-constexpr int LZP_MAXI = 4096;           // instructions per round
+constexpr int LZP_MAXI = 4096 + 8;       // instructions per round (an instruction is at least two bytes long)
+constexpr int LZP_MAXMS = 1024;          // milestones of the serial walk
+constexpr int LZP_JUMP_PASSES = 3;       // doublings of the jump table: a milestone every 8..27 instructions
 constexpr int LZP_MAXZ = 80;            // zero bytes of a length extension a candidate decode follows (255 bytes each)
 constexpr int LZP_RETRY = 0x7f;          // never leaves the library
 constexpr uint32_t LZP_FAR = 0x7ffb, LZP_STEP = 0x7ffc, LZP_END = 0x7ffd, LZP_BAD = 0x7ffe, LZP_OUT = 0x7fff; // next[] codes above any index
 constexpr uint32_t LZP_FIRST = 0x4000;   // visited[]: the block's first byte (state class 2)
-static_assert(LZP_DEC == (1 << 13) && 2 * LZP_DEC * 2 <= LZP_RSYM * 2, "next2 overlays the symbol buffer");
+static_assert(LZP_DEC == (1 << 13) && 2 * LZP_DEC * 2 <= LZP_RSYM * 2, "the jump table overlays the symbol buffer");
 
 struct LzpSmem {
   static constexpr int THREADS = LZP_PT;
@@ -46,6 +48,8 @@ struct LzpSmem {
   __align__(16) uint8_t win[LZP_WIN + 32];
   uint16_t next[2 * LZP_DEC];  // index = state class << 13 | window position; value = index of the next instruction, or LZP_*
   uint16_t visited[LZP_MAXI];  // index of every instruction of the round (| LZP_FIRST)
+  uint16_t ms[LZP_MAXMS];      // every few instructions: what the serial walk visits
+  int nms, npre;
   uint32_t part[LZP_PT];       // scan partials
   unsigned long long adl_s[LZP_PT / 32];
   long long adl_b[LZP_PT / 32];
@@ -203,84 +207,132 @@ lzo_parallel_kernel(int mode, int64_t nblocks, const uint8_t *src_base, const in
       S.next[x] = (uint16_t)link(lzp_decode(S.win, p, x >> 13, wlim, at_end), p);
     }
     __syncthreads();
-    // two instructions ahead (the symbol buffer is idle until the replay: it lends the space)
-    uint16_t *next2 = S.sym;
+    // jump table: J[x] = an instruction some steps ahead on x's chain (LZP_STEP: x's link is not an ordinary one).
+    // Built by doubling in place — racy on purpose: whatever a thread reads still points ahead on the same chain —
+    // in the symbol buffer, which is idle until the replay.
+    uint16_t *J = S.sym;
     for (int x = tid; x < 2 * LZP_DEC; x += LZP_PT) {
       const uint32_t e1 = S.next[x];
-      uint32_t e2 = LZP_STEP;
-      if (e1 < 2u * LZP_DEC) {
-        e2 = S.next[e1];
-        if (e2 >= 2u * LZP_DEC) e2 = LZP_STEP;
-      }
-      next2[x] = (uint16_t)e2;
+      J[x] = (uint16_t)(e1 < 2u * LZP_DEC ? e1 : LZP_STEP);
     }
     __syncthreads();
-    // ---- 2: the chain of real instructions: two per shared-memory round trip
+    for (int pass = 0; pass < LZP_JUMP_PASSES; pass++) {
+      for (int x = tid; x < 2 * LZP_DEC; x += LZP_PT) {
+        const uint32_t j = J[x];
+        if (j < 2u * LZP_DEC) {
+          const uint32_t jj = J[j];
+          if (jj < 2u * LZP_DEC) J[x] = (uint16_t)jj;
+        }
+      }
+      __syncthreads();
+    }
+    // ---- 2: the chain of real instructions.  One thread walks the milestones, all threads fill in between.
     const uint32_t out0 = S.out_pos;
-    if (tid == 0) {
-      const int p0 = (int)(ip0 - w_lo);
-      uint32_t x = (uint32_t)p0 | ((uint32_t)(cls0 & 1) << 13);
-      int n = 0;
-      int64_t bulk = 0;
-      bool stop = false;
-      int64_t ip_after = -1;
-      int cls_after = 0;
-      auto single = [&](uint32_t e, uint32_t vis) { // one instruction whose link is e; returns false when the chain stops
-        if (e == LZP_OUT || e == LZP_BAD) {
-          if (n == 0) {
-            // the round's first instruction does not fit the window: a long literal run is moved directly
-            // (its header is re-read from global memory byte-wise, the zero run of its length may be long)
-            S.give_up = 1;
-            if (e == LZP_OUT && cls0 != 1) { // (the block's first byte, if it is 0, opens an ordinary literal run)
-              int64_t q = w_lo + p0;
-              const int chr = in[q++];
-              if (chr == 0) {
-                int64_t z = 0;
-                while (q < ilen && in[q] == 0) { q++; z++; }
-                if (q < ilen) {
-                  const int64_t lit = 18 + z * 255 + in[q++];
-                  if (q < ilen && lit <= ilen - q && (int64_t)out0 + lit <= olen) {
-                    bulk = lit;
-                    S.ip = q;            // payload start; the round after continues behind it
-                    S.give_up = 0;
-                  }
+    const int p0 = (int)(ip0 - w_lo);
+    int64_t bulk = 0, ip_after = -1;
+    int cls_after = 0, nlist = 0; // (thread 0) instructions listed so far
+    uint32_t xcur = 0;
+    auto single = [&](uint32_t e, uint32_t vis) { // (thread 0) one instruction whose link is e; returns false when the chain stops
+      if (e == LZP_OUT || e == LZP_BAD) {
+        if (nlist == 0) {
+          // the round's first instruction does not fit the window: a long literal run is moved directly
+          // (its header is re-read from global memory byte-wise, the zero run of its length may be long)
+          S.give_up = 1;
+          if (e == LZP_OUT && cls0 != 1) { // (the block's first byte, if it is 0, opens an ordinary literal run)
+            int64_t q = w_lo + p0;
+            const int chr = in[q++];
+            if (chr == 0) {
+              int64_t z = 0;
+              while (q < ilen && in[q] == 0) { q++; z++; }
+              if (q < ilen) {
+                const int64_t lit = 18 + z * 255 + in[q++];
+                if (q < ilen && lit <= ilen - q && (int64_t)out0 + lit <= olen) {
+                  bulk = lit;
+                  S.ip = q;            // payload start; the round after continues behind it
+                  S.give_up = 0;
                 }
               }
             }
           }
-          return false;
         }
-        if (e == LZP_END || e == LZP_FAR) {
-          const LzpInst r = lzp_decode(S.win, (int)(vis & (LZP_DEC - 1)), (vis & LZP_FIRST) ? 2 : (int)((vis >> 13) & 1), wlim, at_end);
-          if (e == LZP_END) {
-            S.ended = 1;
-            S.ip_end = w_lo + (int64_t)(vis & (LZP_DEC - 1)) + r.hdr; // the terminator produces nothing: not listed
-          } else {
-            S.visited[n++] = (uint16_t)vis;
-            ip_after = w_lo + (int64_t)(vis & (LZP_DEC - 1)) + r.hdr + r.lit + r.trail;
-            cls_after = r.ncls;
-          }
-          return false;
-        }
-        S.visited[n++] = (uint16_t)vis;
-        x = e;
-        return true;
-      };
-      if (cls0 == 2) stop = !single(link(lzp_decode(S.win, p0, 2, wlim, at_end), p0), (uint32_t)p0 | LZP_FIRST);
-      while (!stop && n + 2 <= LZP_MAXI) {
-        const uint32_t e1 = S.next[x], e2 = next2[x];
-        if (e2 >= 2u * LZP_DEC) break;
-        S.visited[n] = (uint16_t)x;
-        S.visited[n + 1] = (uint16_t)e1;
-        n += 2;
-        x = e2;
+        return false;
       }
-      while (!stop && n < LZP_MAXI) stop = !single(S.next[x], x);
-      S.nvis = n;
-      S.bulk_len = bulk;
-      S.ip_after = ip_after >= 0 ? ip_after : w_lo + (int64_t)(x & (LZP_DEC - 1));
-      S.cls_after = ip_after >= 0 ? cls_after : (int)(x >> 13);
-      if (n == 0 && !bulk && !S.ended) S.give_up = 1; // no progress: cannot happen on the happy path
+      if (e == LZP_END || e == LZP_FAR) {
+        const LzpInst r = lzp_decode(S.win, (int)(vis & (LZP_DEC - 1)), (vis & LZP_FIRST) ? 2 : (int)((vis >> 13) & 1), wlim, at_end);
+        if (e == LZP_END) {
+          S.ended = 1;
+          S.ip_end = w_lo + (int64_t)(vis & (LZP_DEC - 1)) + r.hdr; // the terminator produces nothing: not listed
+        } else {
+          S.visited[nlist++] = (uint16_t)vis;
+          ip_after = w_lo + (int64_t)(vis & (LZP_DEC - 1)) + r.hdr + r.lit + r.trail;
+          cls_after = r.ncls;
+        }
+        return false;
+      }
+      S.visited[nlist++] = (uint16_t)vis;
+      xcur = e;
+      return true;
+    };
+    if (tid == 0) {
+      xcur = (uint32_t)p0 | ((uint32_t)(cls0 & 1) << 13);
+      bool stop = false;
+      if (cls0 == 2) stop = !single(link(lzp_decode(S.win, p0, 2, wlim, at_end), p0), (uint32_t)p0 | LZP_FIRST);
+      int m = 0;
+      if (!stop) {
+        for (;;) {
+          S.ms[m++] = (uint16_t)xcur;
+          const uint32_t j = J[xcur];
+          if (j >= 2u * LZP_DEC || m == LZP_MAXMS) break;
+          xcur = j;
+        }
+      }
+      S.nms = m;
+      S.npre = nlist;
+    }
+    __syncthreads();
+    {
+      // between two milestones: count, scan, list
+      const int m = S.nms, npre = S.npre;
+      const int nseg = m > 0 ? m - 1 : 0;
+      const int per = (nseg + LZP_PT - 1) / LZP_PT;
+      const int i0 = tid * per;
+      uint32_t cnt = 0;
+      for (int i = i0; i < i0 + per && i < nseg; i++) {
+        const uint32_t stop_at = S.ms[i + 1];
+        for (uint32_t y = S.ms[i]; y != stop_at && y < 2u * LZP_DEC && cnt <= (uint32_t)LZP_MAXI; y = S.next[y]) cnt++;
+      }
+      uint32_t incl = cnt;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t u = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += u;
+      }
+      if (lane == 31) S.part[warp] = incl;
+      __syncthreads();
+      uint32_t at = (uint32_t)npre + incl - cnt;
+      uint32_t total = 0;
+      for (int w2 = 0; w2 < LZP_PT / 32; w2++) { if (w2 < warp) at += S.part[w2]; total += S.part[w2]; }
+      for (int i = i0; i < i0 + per && i < nseg; i++) {
+        const uint32_t stop_at = S.ms[i + 1];
+        for (uint32_t y = S.ms[i]; y != stop_at && y < 2u * LZP_DEC && at < (uint32_t)LZP_MAXI; y = S.next[y]) S.visited[at++] = (uint16_t)y;
+      }
+      if (tid == 0) {
+        nlist = npre + (int)total;
+        if (nlist >= LZP_MAXI) { nlist = 0; S.give_up = 1; } // cannot happen: an instruction is at least two bytes long
+        if (m > 0) {
+          const uint32_t xl = S.ms[m - 1]; // the last milestone: its link ends the chain, unless the milestone list was full
+          xcur = xl;
+          if (J[xl] >= 2u * LZP_DEC) {
+            // (its link may still be an ordinary one when a doubling raced: then walk on, instruction by instruction)
+            while (nlist < LZP_MAXI - 1 && single(S.next[xcur], xcur)) {}
+          }
+        }
+        S.nvis = nlist;
+        S.bulk_len = bulk;
+        S.ip_after = ip_after >= 0 ? ip_after : w_lo + (int64_t)(xcur & (LZP_DEC - 1));
+        S.cls_after = ip_after >= 0 ? cls_after : (int)(xcur >> 13);
+        if (nlist == 0 && !bulk && !S.ended) S.give_up = 1; // no progress: cannot happen on the happy path
+      }
     }
     __syncthreads();
     if (S.give_up) break;
