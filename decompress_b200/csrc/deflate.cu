@@ -35,7 +35,8 @@ namespace dcmp {
 
 constexpr int DF_CHUNK = 65536;
 constexpr int DF_WARPS = 4;
-constexpr int DF_HASH_BITS = 12;
+constexpr int DF_HASH_BITS_FAST = 11;     // levels 1..6: 8 KiB of hash table per warp, four CTAs per SM
+constexpr int DF_HASH_BITS_BEST = 12;     // levels 7..12: 16 KiB, two CTAs per SM, ~2 % smaller output
 constexpr int DF_SLOT = DF_CHUNK + 64;   // bytes of scratch output per chunk (stored worst case: len + 15)
 constexpr int DF_WIN = 256;              // words of the output bit window (ring)
 constexpr int DF_MIN_MATCH = 4;          // 3-byte matches only when close (zlib's TOO_FAR idea, de.ml:4102)
@@ -60,9 +61,11 @@ struct DfTree {            // Huffman construction scratch; only alive after tok
   uint32_t weight[2 * 288];
   uint16_t parent[2 * 288];
 };
-struct DfSmem {
+template <int HB>
+struct DfSmemT {
+  static constexpr int HASH_BITS = HB;
   union {
-    uint32_t head[1 << DF_HASH_BITS];   // two most recent positions per hash: [15:0] newest, [31:16] the one before
+    uint32_t head[1 << HB];   // two most recent positions per hash: [15:0] newest, [31:16] the one before
     DfTree tree;
   };
   uint32_t freq_l[288];
@@ -81,7 +84,7 @@ struct DfSmem {
   int n_rle;
   int hlit, hdist;
 };
-static_assert(sizeof(DfTree) <= sizeof(uint32_t) * (1 << DF_HASH_BITS), "tree scratch overlays the hash table");
+static_assert(sizeof(DfTree) <= sizeof(uint32_t) * (1 << DF_HASH_BITS_FAST), "tree scratch overlays the hash table");
 
 __device__ __constant__ uint8_t c_bl_order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15}; // de.ml:237
 
@@ -152,7 +155,8 @@ struct DfBits {
 // ---- Huffman code construction (one warp) ------------------------------------------------------
 // freq[0..n) -> len[0..n) (<= max_bits) and bit-reversed canonical codes.  Follows the shape of
 // De.T.make / zlib build_tree (de.ml:2013-2068): at least two codes, overflow repair as in gen_bitlen.
-__device__ void df_build_code(DfSmem &S, const uint32_t *freq, int n, int max_bits, uint8_t *len, uint16_t *code, int lane) {
+template <class SM>
+__device__ void df_build_code(SM &S, const uint32_t *freq, int n, int max_bits, uint8_t *len, uint16_t *code, int lane) {
   __syncwarp();
   // keys (freq << 9 | sym) of the used symbols, padded for the sorting network
   for (int i = lane; i < 512; i += 32) S.tree.sortbuf[i] = 0xffffffffu;
@@ -253,7 +257,8 @@ __device__ void df_adler_partials(const uint8_t *p, int n, int lane, uint32_t *s
 }
 
 // ---- one chunk ----------------------------------------------------------------------------------
-__device__ void df_compress_chunk(DfSmem &S, const uint8_t *d, int len, bool last, int level, uint32_t *tok,
+template <class SM>
+__device__ void df_compress_chunk(SM &S, const uint8_t *d, int len, bool last, int level, uint32_t *tok,
                                   uint8_t *slot, DfChunkOut *res, bool want_adler, int lane) {
   uint32_t sum_a = 0, sum_b = 0;
   if (want_adler) df_adler_partials(d, len, lane, &sum_a, &sum_b);
@@ -262,7 +267,7 @@ __device__ void df_compress_chunk(DfSmem &S, const uint8_t *d, int len, bool las
   int ntok = 0;
   bool stored = level == 0 || len < 16;
   if (!stored) {
-    for (int i = lane; i < (1 << DF_HASH_BITS); i += 32) S.head[i] = 0;
+    for (int i = lane; i < (1 << SM::HASH_BITS); i += 32) S.head[i] = 0;
     for (int i = lane; i < 288; i += 32) S.freq_l[i] = 0;
     if (lane < 32) S.freq_d[lane] = 0;
     if (lane == 0) S.extra_bits = 0;
@@ -277,7 +282,7 @@ __device__ void df_compress_chunk(DfSmem &S, const uint8_t *d, int len, bool las
       uint32_t h = 0xffffffffu; // lanes that cannot start a match do not take part in the hash table
       if (maxlen >= DF_MIN_MATCH) {
         const uint32_t v = (uint32_t)d[p] | ((uint32_t)d[p + 1] << 8) | ((uint32_t)d[p + 2] << 16) | ((uint32_t)d[p + 3] << 24);
-        h = (v * 0x9e3779b1u) >> (32 - DF_HASH_BITS);
+        h = (v * 0x9e3779b1u) >> (32 - SM::HASH_BITS);
       }
       const uint32_t same = __match_any_sync(0xffffffffu, h);
       int cand0 = -1, cand1 = -1; // the two most recent earlier positions with this hash
@@ -495,10 +500,12 @@ __device__ void df_compress_chunk(DfSmem &S, const uint8_t *d, int len, bool las
   }
 }
 
+template <int HB>
 __global__ void __launch_bounds__(DF_WARPS * 32)
 deflate_chunk_kernel(int level, int want_adler, int64_t nchunks, const uint8_t *src_base, const DfChunk *chunks,
                      DfChunkOut *outs, uint8_t *slots, uint32_t *tok_scratch, unsigned long long *work_counter) {
   DCMP_DYN_SMEM(smem_raw);
+  typedef DfSmemT<HB> DfSmem;
   DfSmem *SS = reinterpret_cast<DfSmem *>(smem_raw);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   DfSmem &S = SS[warp];
@@ -582,12 +589,25 @@ deflate_gather_kernel(const DfChunk *chunks, const DfChunkOut *outs, const uint8
   for (uint32_t i = headn + body + threadIdx.x; i < n; i += blockDim.x) o[i] = s[i];
 }
 
-size_t deflate_smem_bytes() { return sizeof(DfSmem) * DF_WARPS + 128; }
+inline int deflate_hash_bits(int level) { return level >= 7 ? DF_HASH_BITS_BEST : DF_HASH_BITS_FAST; }
+size_t deflate_smem_bytes(int level) {
+  return (deflate_hash_bits(level) == DF_HASH_BITS_BEST ? sizeof(DfSmemT<DF_HASH_BITS_BEST>) : sizeof(DfSmemT<DF_HASH_BITS_FAST>)) * DF_WARPS + 128;
+}
 size_t deflate_tok_bytes_per_cta() { return (size_t)DF_WARPS * DF_CHUNK * sizeof(uint32_t); }
+#ifndef DCMP_EMU
+// resident CTAs of the chunk kernel per SM at its smallest footprint (the persistent grid and its scratch are sized with it)
+int deflate_ctas_per_sm() {
+  int n = 0;
+  const size_t smem = deflate_smem_bytes(1);
+  cudaFuncSetAttribute(deflate_chunk_kernel<DF_HASH_BITS_FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, deflate_chunk_kernel<DF_HASH_BITS_FAST>, DF_WARPS * 32, smem) != cudaSuccess || n < 1) n = 2;
+  return n;
+}
+#endif
 size_t deflate_chunk_desc_bytes() { return sizeof(DfChunk); }
 size_t deflate_chunk_out_bytes() { return sizeof(DfChunkOut); }
-int deflate_chunk_size() { return DF_CHUNK; }
 size_t deflate_slot_bytes() { return DF_SLOT; }
+int deflate_chunk_size() { return DF_CHUNK; }
 
 #ifndef DCMP_EMU
 int launch_deflate(int level, int fmt, int64_t nstreams, int64_t nchunks, const uint8_t *src_base, const void *chunks,
@@ -595,18 +615,24 @@ int launch_deflate(int level, int fmt, int64_t nstreams, int64_t nchunks, const 
                    unsigned long long *work_counter, int ctas, uint8_t *dst_base, const int64_t *dst_off,
                    const int64_t *dst_cap, int64_t *written, int32_t *status, cudaStream_t stream) {
   static bool configured = false;
-  const size_t smem = deflate_smem_bytes();
+  const size_t smem = deflate_smem_bytes(level);
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(deflate_chunk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(deflate_chunk_kernel<DF_HASH_BITS_FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)deflate_smem_bytes(1));
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(deflate_chunk_kernel<DF_HASH_BITS_BEST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)deflate_smem_bytes(9));
     if (e != cudaSuccess) return (int)e;
     configured = true;
   }
   if (nchunks > 0) {
     int64_t want = (nchunks + DF_WARPS - 1) / DF_WARPS;
     if (ctas > want) ctas = (int)want;
-    deflate_chunk_kernel<<<(unsigned)ctas, DF_WARPS * 32, smem, stream>>>(level, fmt == DCMP_FMT_ZLIB ? 1 : 0, nchunks, src_base,
-                                                                         (const DfChunk *)chunks, (DfChunkOut *)outs, slots,
-                                                                         tok_scratch, work_counter);
+    if (deflate_hash_bits(level) == DF_HASH_BITS_BEST)
+      deflate_chunk_kernel<DF_HASH_BITS_BEST><<<(unsigned)ctas, DF_WARPS * 32, smem, stream>>>(
+          level, fmt == DCMP_FMT_ZLIB ? 1 : 0, nchunks, src_base, (const DfChunk *)chunks, (DfChunkOut *)outs, slots, tok_scratch, work_counter);
+    else
+      deflate_chunk_kernel<DF_HASH_BITS_FAST><<<(unsigned)ctas, DF_WARPS * 32, smem, stream>>>(
+          level, fmt == DCMP_FMT_ZLIB ? 1 : 0, nchunks, src_base, (const DfChunk *)chunks, (DfChunkOut *)outs, slots, tok_scratch, work_counter);
   }
   deflate_plan_kernel<<<(unsigned)((nstreams + 127) / 128), 128, 0, stream>>>(fmt, level, nstreams, first_chunk, (const DfChunkOut *)outs,
                                                                               (const DfChunk *)chunks, dst_base, dst_off, dst_cap,

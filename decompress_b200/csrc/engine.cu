@@ -38,6 +38,7 @@ int launch_deflate(int level, int fmt, int64_t nstreams, int64_t nchunks, const 
                    unsigned long long *work_counter, int ctas, uint8_t *dst_base, const int64_t *dst_off,
                    const int64_t *dst_cap, int64_t *written, int32_t *status, cudaStream_t stream);
 size_t deflate_tok_bytes_per_cta();
+int deflate_ctas_per_sm();
 size_t deflate_slot_bytes();
 int deflate_chunk_size();
 struct DfChunkHost { int64_t src_off; int32_t len; int32_t stream; int32_t flags; int32_t pad; }; // = deflate.cu's DfChunk
@@ -472,7 +473,7 @@ int dcmp_deflate_batch_device(dcmp_engine *e, int level, int fmt, int64_t n, con
   first[n] = (int64_t)chunks.size();
   const int64_t nc = (int64_t)chunks.size();
   if (!e->d_def_scratch) {
-    e->def_ctas = 3 * (e->sm_count > 0 ? e->sm_count : 148);
+    e->def_ctas = dcmp::deflate_ctas_per_sm() * (e->sm_count > 0 ? e->sm_count : 148);
     CU(cudaMalloc(&e->d_def_scratch, 256 + (size_t)e->def_ctas * dcmp::deflate_tok_bytes_per_cta()));
   }
   const size_t slot = dcmp::deflate_slot_bytes();
