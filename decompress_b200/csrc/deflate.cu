@@ -522,33 +522,69 @@ deflate_chunk_kernel(int level, int want_adler, int64_t nchunks, const uint8_t *
   }
 }
 
-// One thread per stream: where every chunk goes, the framing, the result.
+// One warp per stream: where every chunk goes (exclusive scan of the chunk sizes), the Adler-32 of the whole
+// input from the per-chunk partial sums, the framing, the result.
 // first_chunk[k] .. first_chunk[k+1] are stream k's chunks.
 __global__ void deflate_plan_kernel(int fmt, int level, int64_t nstreams, const int64_t *first_chunk, const DfChunkOut *outs,
                                     const DfChunk *chunks, uint8_t *dst_base, const int64_t *dst_off, const int64_t *dst_cap,
                                     int64_t *chunk_dst, int64_t *written, int32_t *status) {
-  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const int64_t k = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (k >= nstreams) return;
   const int64_t c0 = first_chunk[k], c1 = first_chunk[k + 1];
   const int64_t cap = dst_cap[k];
   int64_t total = fmt == DCMP_FMT_ZLIB ? 2 : 0;
-  unsigned long long A = 1, B = 0;
-  for (int64_t c = c0; c < c1; c++) {
-    chunk_dst[c] = total;
-    total += outs[c].bytes;
-    const unsigned long long n = (unsigned long long)chunks[c].len;
-    B = (B + (n % 65521ull) * A + outs[c].sum_b) % 65521ull;
-    A = (A + outs[c].sum_a) % 65521ull;
+  const unsigned long long M = 65521ull;
+  unsigned long long A = 1, B = 0; // Adler-32 state after the chunks seen so far
+  for (int64_t base = c0; base < c1; base += 32) {
+    const int64_t c = base + lane;
+    const bool have = c < c1;
+    // a chunk as an Adler segment (a, b, n): appended to a state (A, B) it gives (A + a, B + n*A + b)
+    unsigned long long a = 0, bq = 0, n = 0;
+    int64_t bytes = 0;
+    if (have) {
+      bytes = outs[c].bytes;
+      a = outs[c].sum_a % M;
+      bq = outs[c].sum_b % M;
+      n = (unsigned long long)chunks[c].len % M;
+    }
+    int64_t incl = bytes;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int64_t u = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += u;
+    }
+    if (have) chunk_dst[c] = total + incl - bytes;
+    total += __shfl_sync(0xffffffffu, incl, 31);
+    // ordered reduction of the 32 segments: (a1, b1, n1) then (a2, b2, n2) = (a1 + a2, b1 + b2 + n2*a1, n1 + n2)
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned long long a2 = __shfl_down_sync(0xffffffffu, a, o), b2 = __shfl_down_sync(0xffffffffu, bq, o),
+                               n2 = __shfl_down_sync(0xffffffffu, n, o);
+      if (lane + o < 32) {
+        bq = (bq + b2 + (n2 * a) % M) % M;
+        a = (a + a2) % M;
+        n = (n + n2) % M;
+      }
+    }
+    a = __shfl_sync(0xffffffffu, a, 0);
+    bq = __shfl_sync(0xffffffffu, bq, 0);
+    n = __shfl_sync(0xffffffffu, n, 0);
+    B = (B + (n * A) % M + bq) % M;
+    A = (A + a) % M;
   }
   if (fmt == DCMP_FMT_ZLIB) total += 4;
   // De.Def.Ns.deflate needs _end_padding = 8 bytes of dst (de.ml:3998-4001) and reports a dst that is too
   // small as Unexpected_end_of_output
   if (total > cap) {
-    for (int64_t c = c0; c < c1; c++) chunk_dst[c] = -1;
-    written[k] = 0;
-    status[k] = DCMP_UNEXPECTED_END_OF_OUTPUT;
+    for (int64_t c = c0 + lane; c < c1; c += 32) chunk_dst[c] = -1;
+    if (lane == 0) {
+      written[k] = 0;
+      status[k] = DCMP_UNEXPECTED_END_OF_OUTPUT;
+    }
     return;
   }
+  if (lane != 0) return;
   uint8_t *o = dst_base + dst_off[k];
   if (fmt == DCMP_FMT_ZLIB) {
     // Zl.Def.Ns.header (lib/zl.ml:600-608)
@@ -634,7 +670,7 @@ int launch_deflate(int level, int fmt, int64_t nstreams, int64_t nchunks, const 
       deflate_chunk_kernel<DF_HASH_BITS_FAST><<<(unsigned)ctas, DF_WARPS * 32, smem, stream>>>(
           level, fmt == DCMP_FMT_ZLIB ? 1 : 0, nchunks, src_base, (const DfChunk *)chunks, (DfChunkOut *)outs, slots, tok_scratch, work_counter);
   }
-  deflate_plan_kernel<<<(unsigned)((nstreams + 127) / 128), 128, 0, stream>>>(fmt, level, nstreams, first_chunk, (const DfChunkOut *)outs,
+  deflate_plan_kernel<<<(unsigned)((nstreams + 3) / 4), 128, 0, stream>>>(fmt, level, nstreams, first_chunk, (const DfChunkOut *)outs,
                                                                               (const DfChunk *)chunks, dst_base, dst_off, dst_cap,
                                                                               chunk_dst, written, status);
   if (nchunks > 0)

@@ -63,7 +63,12 @@ constexpr int SPEC_CAP = ((SUB_BITS / 3) + 3) & ~3; // tokens a lane may produce
 constexpr int HEAD_CAP = 96;              // tokens a lane may produce while re-synchronising (p99 of the distance is ~55 on text)
 constexpr int TOK_SLOTS = SPEC_CAP + HEAD_CAP; // per lane, in the global scratch
 constexpr int LANE_BYTE_CAP = 4096;       // bytes a lane may produce per pass (checkpoint field: 19 bits)
-constexpr int CKPT_SHIFT = 5;             // one checkpoint per 32-bit window of the sub-chunk
+#ifndef DCMP_CKPT_SHIFT
+#define DCMP_CKPT_SHIFT 4
+#endif
+constexpr int CKPT_SHIFT = DCMP_CKPT_SHIFT; // one checkpoint per 2^CKPT_SHIFT-bit window of the sub-chunk
+constexpr uint32_t CKPT_NONE = 0x80000000u; // no token of the speculative pass starts in this window (a long match can skip one)
+static_assert(CKPT_SHIFT >= 3 && CKPT_SHIFT <= 5, "");
 constexpr int NCKPT = (SUB_BITS >> CKPT_SHIFT) + 1;
 #ifndef DCMP_RSYM_K
 #define DCMP_RSYM_K 26
@@ -135,8 +140,8 @@ enum : int { X_NORMAL = 0, X_EOB = 1, X_CAP = 2, X_ERR = 3, X_NOSYNC = 4 };
 enum : int { NEXT_CONTINUE = 0, NEXT_HEADER = 1, NEXT_FINISH = 2, NEXT_RETRY = 3, NEXT_STORED = 4 };
 
 // token: [23] match flag; match: [22:8] distance-1, [7:0] length-3;  literal: [7:0] byte
-// checkpoint: [4:0] bit offset of the first token start inside the 32-bit window,
-//             [12:5] index of that token, [31:13] bytes emitted before it
+// checkpoint: [4:0] low bits of the position of the first token start inside the window,
+//             [12:5] index of that token, [30:13] bytes emitted before it, [31] none
 __device__ __forceinline__ bool tok_is_match(uint32_t t) { return (t >> 23) & 1u; }
 __device__ __forceinline__ void batch_put(uint4 &b, int k, uint32_t t) {
   if (k == 0) b.x = t;
@@ -806,6 +811,8 @@ inflate_parallel_kernel(int fmt, int64_t nstreams, const uint8_t *src_base, cons
       int xkind = X_ERR, xpos = 0;
       int last_ck = -1;
       if (lane_has_input) {
+#pragma unroll
+        for (int c = 0; c < NCKPT; c++) ckpt[c][tid] = CKPT_NONE; // (the buffer held symbols, or an older round's checkpoints)
         LaneBits lb;
         lb.init(lane_words, sh, 0);
         uint4 tbuf = make_uint4(0, 0, 0, 0);
@@ -880,7 +887,7 @@ inflate_parallel_kernel(int fmt, int64_t nstreams, const uint8_t *src_base, cons
                 seen_ck = ck;
                 if (ck <= lck) { // the speculative pass of lane u left a checkpoint for this window
                   const uint32_t c = ckpt[ck][u];
-                  if ((int)(c & 31u) == (pl & 31)) { mk = (int)((c >> 5) & 255u); mskip = c >> 13; hcat = H_MERGE; break; }
+                  if ((c & (CKPT_NONE | 31u)) == (uint32_t)(pl & 31)) { mk = (int)((c >> 5) & 255u); mskip = c >> 13; hcat = H_MERGE; break; }
                 }
               }
               if (xk_u == X_CAP && pl == xp_u) { // met that pass where its token buffer filled up

@@ -88,7 +88,7 @@ int emu_deflate_batch(int level, int fmt, int64_t n, const uint8_t *src, const i
     if (level >= 7) deflate_chunk_kernel<DF_HASH_BITS_BEST>(level, fmt == DCMP_FMT_ZLIB, nc, src, chunks.data(), outs.data(), slots.data(), tok.data(), &counter);
     else deflate_chunk_kernel<DF_HASH_BITS_FAST>(level, fmt == DCMP_FMT_ZLIB, nc, src, chunks.data(), outs.data(), slots.data(), tok.data(), &counter);
   });
-  simt::launch(simt::dim3((unsigned)((n + 127) / 128)), simt::dim3(128), 0, [&]() {
+  simt::launch(simt::dim3((unsigned)((n + 3) / 4)), simt::dim3(128), 0, [&]() {
     deflate_plan_kernel(fmt, level, n, first.data(), outs.data(), chunks.data(), dst, doff, dcap, cdst.data(), written, status);
   });
   simt::launch(simt::dim3((unsigned)nc), simt::dim3(256), 0, [&]() {
