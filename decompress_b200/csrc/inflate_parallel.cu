@@ -63,6 +63,10 @@ constexpr int SPEC_CAP = ((SUB_BITS / 3) + 3) & ~3; // tokens a lane may produce
 constexpr int HEAD_CAP = 96;              // tokens a lane may produce while re-synchronising (p99 of the distance is ~55 on text)
 constexpr int TOK_SLOTS = SPEC_CAP + HEAD_CAP; // per lane, in the global scratch
 constexpr int LANE_BYTE_CAP = 4096;       // bytes a lane may produce per pass (checkpoint field: 19 bits)
+#ifndef DCMP_WARMUP_BITS
+#define DCMP_WARMUP_BITS 384
+#endif
+constexpr int WARMUP_BITS = DCMP_WARMUP_BITS; // a lane's speculative pass starts this far inside the previous sub-chunk
 #ifndef DCMP_CKPT_SHIFT
 #define DCMP_CKPT_SHIFT 4
 #endif
@@ -814,7 +818,13 @@ inflate_parallel_kernel(int fmt, int64_t nstreams, const uint8_t *src_base, cons
 #pragma unroll
         for (int c = 0; c < NCKPT; c++) ckpt[c][tid] = CKPT_NONE; // (the buffer held symbols, or an older round's checkpoints)
         LaneBits lb;
-        lb.init(lane_words, sh, 0);
+        // Warm-up: the pass starts WARMUP_BITS before the sub-chunk and throws away what it decodes there, so that it
+        // has often found the true token boundaries by the time its own bits begin (lane 0 starts on one).
+        lb.init(lane_words, sh, -imin(WARMUP_BITS, tid * SUB_BITS)); // (never before lane 0's start, which is a token boundary)
+        while (lb.pos() < 0) {
+          uint32_t tok, no;
+          if (decode_token(S, lb, lmask, dmask, lroot, droot, &tok, &no) != T_TOKEN) { lb.init(lane_words, sh, 0); break; }
+        }
         uint4 tbuf = make_uint4(0, 0, 0, 0);
         for (;;) {
           int p = lb.pos();
@@ -859,8 +869,8 @@ inflate_parallel_kernel(int fmt, int64_t nstreams, const uint8_t *src_base, cons
         int entry = 0;
         if (tid > 0) entry = S.exit_kind[tid - 1] == X_NORMAL ? (int)S.exit_pos[tid - 1] - SUB_BITS : ENTRY_NONE;
         if (lane_has_input && entry != ENTRY_NONE) {
-          if (entry == 0 && ns > 0) {
-            hcat = H_MERGE; // the speculative pass started at the true position
+          if (tid == 0 && ns > 0) {
+            hcat = H_MERGE; // lane 0's speculative pass started at the true position
           } else {
             LaneBits lb;
             lb.init(lane_words, sh, entry);
