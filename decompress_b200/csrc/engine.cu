@@ -76,14 +76,15 @@ struct dcmp_engine {
   uint8_t *d_def_arena = nullptr;
   size_t def_arena_cap = 0;
   // host-facing calls: three-stage pipeline (H2D | kernels | D2H) over slices of the batch
-  static const int MAX_SLICES = 8;
-  cudaStream_t s_kernel = nullptr, s_out = nullptr;
+  static const int MAX_SLICES = 16;
+  cudaStream_t s_kernel = nullptr, s_out = nullptr, s_meta = nullptr;
   cudaEvent_t ev_in[MAX_SLICES] = {}, ev_k[MAX_SLICES] = {}, ev_meta[MAX_SLICES] = {};
   bool pipeline_ready = false;
   int ensure_pipeline() {
     if (pipeline_ready) return DCMP_API_OK;
     CU(cudaStreamCreateWithFlags(&s_kernel, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&s_meta, cudaStreamNonBlocking));
     for (int i = 0; i < MAX_SLICES; i++) {
       CU(cudaEventCreateWithFlags(&ev_in[i], cudaEventDisableTiming));
       CU(cudaEventCreateWithFlags(&ev_k[i], cudaEventDisableTiming));
@@ -176,6 +177,7 @@ void dcmp_engine_destroy(dcmp_engine *e) {
     for (int i = 0; i < dcmp_engine::MAX_SLICES; i++) { cudaEventDestroy(e->ev_in[i]); cudaEventDestroy(e->ev_k[i]); cudaEventDestroy(e->ev_meta[i]); }
     cudaStreamDestroy(e->s_kernel);
     cudaStreamDestroy(e->s_out);
+    cudaStreamDestroy(e->s_meta);
   }
   if (e->stream) cudaStreamDestroy(e->stream);
   delete e;
@@ -295,7 +297,8 @@ static int host_batch(dcmp_engine *e, device_batch_fn launch, int fmt, int64_t n
   // bytes, the kernels, device->host copy of the inflated bytes — in slices of consecutive streams, so
   // that PCIe in both directions and the SMs work at the same time.  A slice's input is the byte span
   // its streams reference; if the caller's layout is not monotonic the batch runs as one slice.
-  int nslice = (int)std::min<int64_t>(dcmp_engine::MAX_SLICES, std::max<int64_t>(1, work / (48ll << 20)));
+  static const int64_t slice_mb = getenv("DCMP_SLICE_MB") ? std::max(1, atoi(getenv("DCMP_SLICE_MB"))) : 48; // tuning knob
+  int nslice = (int)std::min<int64_t>(dcmp_engine::MAX_SLICES, std::max<int64_t>(1, work / (slice_mb << 20)));
   if (n < 4 * nslice) nslice = 1;
   bool monotonic = true;
   for (int64_t k = 1; k < n && monotonic; k++)
@@ -335,12 +338,15 @@ static int host_batch(dcmp_engine *e, device_batch_fn launch, int fmt, int64_t n
   for (int c = 0; c < nslice; c++) {
     int64_t k0 = cut[c], k1 = cut[c + 1], m = k1 - k0;
     if (m <= 0) continue;
-    CU(cudaStreamWaitEvent(s_out, e->ev_k[c], 0));
-    CU(cudaMemcpyAsync(consumed + k0, d_cons + k0, (size_t)m * 8, cudaMemcpyDeviceToHost, s_out));
-    CU(cudaMemcpyAsync(produced + k0, d_prod + k0, (size_t)m * 8, cudaMemcpyDeviceToHost, s_out));
-    CU(cudaMemcpyAsync(status + k0, d_stat + k0, (size_t)m * 4, cudaMemcpyDeviceToHost, s_out));
-    CU(cudaEventRecord(e->ev_meta[c], s_out));
+    // the small result rows travel on their own stream, so that they do not queue behind the previous
+    // slice's payload copy: the host learns what to fetch for slice c while slice c-1 is still leaving
+    CU(cudaStreamWaitEvent(e->s_meta, e->ev_k[c], 0));
+    CU(cudaMemcpyAsync(consumed + k0, d_cons + k0, (size_t)m * 8, cudaMemcpyDeviceToHost, e->s_meta));
+    CU(cudaMemcpyAsync(produced + k0, d_prod + k0, (size_t)m * 8, cudaMemcpyDeviceToHost, e->s_meta));
+    CU(cudaMemcpyAsync(status + k0, d_stat + k0, (size_t)m * 4, cudaMemcpyDeviceToHost, e->s_meta));
+    CU(cudaEventRecord(e->ev_meta[c], e->s_meta));
     CU(cudaEventSynchronize(e->ev_meta[c]));
+    CU(cudaStreamWaitEvent(s_out, e->ev_k[c], 0));
     int64_t run_lo = -1, run_hi = -1;
     for (int64_t k = k0; k <= k1; k++) {
       int64_t lo = 0, hi = 0;

@@ -225,6 +225,10 @@ struct ParSmem {
   uint32_t mbar_phase;
   int abort_round;               // a lane met an invalid distance: the general kernel reports it
   int hdr_ready;                 // the first header of this stream was parsed ahead (S.pf)
+  int nh_ready;                  // the header of the stream's NEXT block was parsed during phases D/E: lens, nh_*
+  int nh_last;
+  uint32_t nh_hlit, nh_hdist;
+  int64_t nh_base_bit;
   int pf_done;                   // the next stream has been claimed during this one
   Prefetch pf;
   __align__(8) uint64_t mbar;
@@ -664,6 +668,7 @@ inflate_parallel_kernel(int fmt, int64_t nstreams, const uint8_t *src_base, cons
         if (claimed) { S.src = S.pf.src; S.src_len = S.pf.src_len; S.dst = S.pf.dst; S.dst_cap = S.pf.dst_cap; st = S.pf.st; }
         else st = open_stream(fmt, (int64_t)k, src_base, src_off, src_len, dst_base, dst_off, dst_cap, &S.src, &S.src_len, &S.dst, &S.dst_cap);
         S.hdr_ready = claimed && st == DCMP_OK && S.pf.hdr;
+        S.nh_ready = 0;
         S.base_bit = 0;
         S.out_pos = 0;
         S.last_block = 0;
@@ -696,8 +701,18 @@ inflate_parallel_kernel(int fmt, int64_t nstreams, const uint8_t *src_base, cons
       if (S.next == NEXT_HEADER) {
         // ------------------------------------------------------------ block header
         const bool ahead = S.hdr_ready != 0; // parsed while the previous stream was being decoded
+        const bool ahead2 = S.nh_ready != 0; // parsed while the previous block's last round was being replayed
         __syncthreads();
-        if (ahead) {
+        if (ahead2) {
+          if (tid == 0) {
+            S.last_block = S.nh_last;
+            S.hdr_hlit = S.nh_hlit;
+            S.hdr_hdist = S.nh_hdist;
+            S.base_bit = S.nh_base_bit;
+            S.nh_ready = 0;
+            S.next = NEXT_CONTINUE;
+          }
+        } else if (ahead) {
           for (int i = tid; i < MAX_LENS; i += PT) S.lens[i] = S.pf.lens[i];
           if (tid == 0) {
             S.last_block = S.pf.last_block;
@@ -708,7 +723,7 @@ inflate_parallel_kernel(int fmt, int64_t nstreams, const uint8_t *src_base, cons
             S.next = NEXT_CONTINUE;
           }
         } else stage_window(S, g0, HDR_BYTES, (int)(vend - v0 > HDR_BYTES ? HDR_BYTES : vend - v0), tid);
-        if (tid == 0 && !ahead) {
+        if (tid == 0 && !ahead && !ahead2) {
           STAT(g_stats.hdr_rounds++;)
           HdrBits hb;
           hb.init((const uint8_t *)S.win, bit0, HDR_BYTES);
@@ -1072,6 +1087,31 @@ inflate_parallel_kernel(int fmt, int64_t nstreams, const uint8_t *src_base, cons
       uint8_t *const G0 = S.dst + slice_out0 - bias;
       const uint32_t g0_low = (uint32_t)((uintptr_t)G0 & HIST_MASK);
       const uint32_t E = bias + round_out; // one past the last symbol of the slice
+      // A block ended in this round and another one follows: the last warp, when the round left it no lanes to
+      // replay, parses the next header out of the staged window while the other warps are in phase D.
+      if (s0 == 0 && S.next == NEXT_HEADER && tid == PT - 32 && n_valid <= PT - 32) {
+        const int64_t staged = 8 * (vend - v0 > WIN_BYTES ? (int64_t)WIN_BYTES : vend - v0); // window bits that hold input
+        const int64_t hbit = bit0 + (S.base_bit - base_bit);                              // where the header starts
+        if (hbit + 64 < staged) {
+          HdrBits hb;
+          hb.init((const uint8_t *)S.win, (int)hbit, WIN_BYTES);
+          int64_t avail = 8 * S.src_len - base_bit + bit0; // valid bits measured in window coordinates
+          if (avail > staged) avail = staged;
+          hb.refill();
+          const int last = (int)hb.pop(1);
+          if (hb.pop(2) == 2u) {
+            int hlit = 0, hdist = 0;
+            const int used = parse_dynamic_header(S.pf.codes, S.lens, hb, avail, &hlit, &hdist);
+            if (used >= 0) {
+              S.nh_last = last;
+              S.nh_hlit = (uint32_t)hlit;
+              S.nh_hdist = (uint32_t)hdist;
+              S.nh_base_bit = S.base_bit + (used - hbit);
+              S.nh_ready = 1;
+            }
+          }
+        }
+      }
       // ---- D: replay tokens into symbols
       if (tid < 16) {
         if ((uint32_t)tid < bias) S.sym[tid] = 0;

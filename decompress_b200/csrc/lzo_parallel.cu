@@ -202,9 +202,11 @@ lzo_parallel_kernel(int mode, int64_t nblocks, const uint8_t *src_base, const in
       const int np = p + r.hdr + r.lit + r.trail;
       return np < LZP_DEC ? (uint32_t)np | ((uint32_t)r.ncls << 13) : LZP_FAR;
     };
-    for (int x = tid; x < 2 * LZP_DEC; x += LZP_PT) {
-      const int p = x & (LZP_DEC - 1);
-      S.next[x] = (uint16_t)link(lzp_decode(S.win, p, x >> 13, wlim, at_end), p);
+    for (int p = tid; p < LZP_DEC; p += LZP_PT) {
+      // the two states differ only in what an opcode below 16 means
+      const uint32_t l0 = link(lzp_decode(S.win, p, 0, wlim, at_end), p);
+      S.next[p] = (uint16_t)l0;
+      S.next[LZP_DEC + p] = (uint16_t)(S.win[p] > 15 ? l0 : link(lzp_decode(S.win, p, 1, wlim, at_end), p));
     }
     __syncthreads();
     // jump table: J[x] = an instruction some steps ahead on x's chain (LZP_STEP: x's link is not an ordinary one).
