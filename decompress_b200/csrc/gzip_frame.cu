@@ -8,8 +8,8 @@
 //   gzip_header_kernel   one thread per member: parse the header exactly as gz.ml does (only the magic is checked;
 //                        XLEN is read big-endian, gz.ml:455; FHCRC covers the 10 fixed bytes + FNAME + FCOMMENT),
 //                        hand the DEFLATE body to the raw inflate kernels through rebased offset tables;
-//   gzip_trailer_kernel  one warp per member: every lane folds a contiguous slice of the inflated bytes through
-//                        a shared-memory table, the 32 partial CRCs are combined with carry-less multiplications
+//   gzip_trailer_kernel  one warp per member: every lane folds a contiguous slice of the inflated bytes, eight
+//                        bytes per step through slicing-by-8 tables in shared memory, the 32 partial CRCs are combined with carry-less multiplications
 //                        by x^(8*len) mod P, then CRC-32 and ISIZE are compared (the checksum first, gz.ml:352-354).
 #include "simt.cuh"
 #include "../../include/dcmp.h"
@@ -42,6 +42,37 @@ __device__ uint32_t gf2_xpow8n(uint64_t nbytes) {
 
 __device__ uint32_t crc_bytes(const uint32_t *T, uint32_t c, const uint8_t *p, int64_t n) {
   for (int64_t i = 0; i < n; i++) c = T[(c ^ p[i]) & 0xffu] ^ (c >> 8);
+  return c;
+}
+
+// Slicing-by-8: T8[k][b] = CRC of byte b followed by k zero bytes, so eight bytes cost eight independent
+// table reads (one shared-memory round trip on the dependency chain) instead of eight dependent ones.
+__device__ __forceinline__ void crc_build_slices(uint32_t (*T8)[256], int tid, int nthreads) {
+  for (int i = tid; i < 256; i += nthreads) {
+    uint32_t c = (uint32_t)i;
+    for (int k = 0; k < 8; k++) c = (c & 1u) ? CRC_POLY ^ (c >> 1) : c >> 1;
+    T8[0][i] = c;
+  }
+  __syncthreads();
+  for (int i = tid; i < 256; i += nthreads) {
+    uint32_t c = T8[0][i];
+    for (int k = 1; k < 8; k++) {
+      c = T8[0][c & 0xffu] ^ (c >> 8);
+      T8[k][i] = c;
+    }
+  }
+  __syncthreads();
+}
+__device__ uint32_t crc_bytes8(const uint32_t (*T8)[256], uint32_t c, const uint8_t *p, int64_t n) {
+  int64_t i = 0;
+  while (i < n && ((uintptr_t)(p + i) & 7)) { c = T8[0][(c ^ p[i]) & 0xffu] ^ (c >> 8); i++; }
+  for (; i + 8 <= n; i += 8) {
+    const uint2 w = *reinterpret_cast<const uint2 *>(p + i);
+    const uint32_t a = w.x ^ c, b = w.y;
+    c = T8[7][a & 0xffu] ^ T8[6][(a >> 8) & 0xffu] ^ T8[5][(a >> 16) & 0xffu] ^ T8[4][a >> 24] ^
+        T8[3][b & 0xffu] ^ T8[2][(b >> 8) & 0xffu] ^ T8[1][(b >> 16) & 0xffu] ^ T8[0][b >> 24];
+  }
+  for (; i < n; i++) c = T8[0][(c ^ p[i]) & 0xffu] ^ (c >> 8);
   return c;
 }
 
@@ -102,13 +133,8 @@ __global__ void __launch_bounds__(128)
 gzip_trailer_kernel(int64_t n, const uint8_t *src_base, const int64_t *src_off, const int64_t *body_off, const int64_t *body_len,
                     const int32_t *pre_status, const uint8_t *dst_base, const int64_t *dst_off, int64_t *consumed,
                     int64_t *produced, int32_t *status) {
-  __shared__ uint32_t T[256];
-  for (int i = threadIdx.x; i < 256; i += blockDim.x) {
-    uint32_t c = (uint32_t)i;
-    for (int k = 0; k < 8; k++) c = (c & 1u) ? CRC_POLY ^ (c >> 1) : c >> 1;
-    T[i] = c;
-  }
-  __syncthreads();
+  __shared__ uint32_t T8[8][256];
+  crc_build_slices(T8, threadIdx.x, blockDim.x);
   const int lane = threadIdx.x & 31;
   const int64_t k = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (k >= n) return;
@@ -124,7 +150,7 @@ gzip_trailer_kernel(int64_t n, const uint8_t *src_base, const int64_t *src_off, 
   const uint8_t *o = dst_base + dst_off[k];
   const int64_t per = (prod + 31) / 32;
   const int64_t lo = per * lane < prod ? per * lane : prod, hi = lo + per < prod ? lo + per : prod;
-  uint32_t c = crc_bytes(T, lane == 0 ? 0xffffffffu : 0u, o + lo, hi - lo);
+  uint32_t c = crc_bytes8(T8, lane == 0 ? 0xffffffffu : 0u, o + lo, hi - lo);
   // tree combine: at step s, lane l (l % 2^(s+1) == 0) absorbs lane l + 2^s, whose span is known from lo/hi
   for (int s = 1; s < 32; s <<= 1) {
     const uint32_t right = __shfl_down_sync(0xffffffffu, c, s);
