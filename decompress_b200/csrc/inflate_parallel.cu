@@ -153,6 +153,16 @@ __device__ __forceinline__ void batch_put(uint4 &b, int k, uint32_t t) {
   if (k == 2) b.z = t;
   if (k == 3) b.w = t;
 }
+// one predicated 16-bit shared-memory store, without a branch
+__device__ __forceinline__ void st_sym_if(bool pred, uint16_t *addr, uint32_t v) {
+#ifdef DCMP_EMU
+  if (pred) *addr = (uint16_t)v;
+#else
+  asm volatile("{\n .reg .pred p;\n setp.ne.u32 p, %0, 0;\n @p st.shared.u16 [%1], %2;\n}\n" ::"r"((uint32_t)pred),
+               "r"((uint32_t)__cvta_generic_to_shared(addr)), "h"((uint16_t)v)
+               : "memory");
+#endif
+}
 // A batch is filled as a shift register (newest token in .w): three moves per token, no indexing.
 __device__ __forceinline__ void batch_push(uint4 &b, uint32_t t) { b.x = b.y; b.y = b.z; b.z = b.w; b.w = t; }
 // bring the last r (1..3) tokens of a partial batch to the front
@@ -1220,14 +1230,16 @@ inflate_parallel_kernel(int fmt, int64_t nstreams, const uint8_t *src_base, cons
               S.sym[i + (int32_t)k] = (uint16_t)v;
             }
           } else {
-            if (n > 0u) S.sym[i] = (uint16_t)p0;
-            if (n > 1u) S.sym[i + 1] = (uint16_t)(p0 >> 16);
-            if (n > 2u) S.sym[i + 2] = (uint16_t)p1;
-            if (n > 3u) S.sym[i + 3] = (uint16_t)(p1 >> 16);
-            if (n > 4u) S.sym[i + 4] = (uint16_t)p2;
-            if (n > 5u) S.sym[i + 5] = (uint16_t)(p2 >> 16);
-            if (n > 6u) S.sym[i + 6] = (uint16_t)p3;
-            if (n > 7u) S.sym[i + 7] = (uint16_t)(p3 >> 16);
+            // eight predicated stores (the compiler turns the plain `if`s into a cascade of eight divergent branches)
+            uint16_t *const at = S.sym + i;
+            st_sym_if(n > 0u, at + 0, p0);
+            st_sym_if(n > 1u, at + 1, p0 >> 16);
+            st_sym_if(n > 2u, at + 2, p1);
+            st_sym_if(n > 3u, at + 3, p1 >> 16);
+            st_sym_if(n > 4u, at + 4, p2);
+            st_sym_if(n > 5u, at + 5, p2 >> 16);
+            st_sym_if(n > 6u, at + 6, p3);
+            st_sym_if(n > 7u, at + 7, p3 >> 16);
           }
           i += (int32_t)n;
           if (rem > 0u) { s += (int32_t)n; rem -= n; }

@@ -29,18 +29,31 @@
 
 namespace dcmp {
 
-constexpr int LZP_PT = 256;
-constexpr int LZP_RSYM = 20 * 1024;      // output symbols per round (+ up to 15 of alignment bias)
-constexpr int LZP_WIN = 16 * 1024;       // input bytes staged per round
-constexpr int LZP_DEC = 8 * 1024;        // window positions decoded as candidates (instructions may extend beyond)
-constexpr int LZP_MAXI = 4096 + 8;       // instructions per round (an instruction is at least two bytes long)
+#ifndef DCMP_LZP_PT
+#define DCMP_LZP_PT 256
+#endif
+#ifndef DCMP_LZP_DEC_BITS
+#define DCMP_LZP_DEC_BITS 13
+#endif
+#ifndef DCMP_LZP_RSYM_K
+#define DCMP_LZP_RSYM_K 20
+#endif
+#ifndef DCMP_LZP_CTAS
+#define DCMP_LZP_CTAS 2
+#endif
+constexpr int LZP_PT = DCMP_LZP_PT;
+constexpr int LZP_RSYM = DCMP_LZP_RSYM_K * 1024;      // output symbols per round (+ up to 15 of alignment bias)
+constexpr int LZP_DEC_BITS = DCMP_LZP_DEC_BITS;
+constexpr int LZP_DEC = 1 << LZP_DEC_BITS; // window positions decoded as candidates (instructions may extend beyond)
+constexpr int LZP_WIN = 2 * LZP_DEC;     // input bytes staged per round
+constexpr int LZP_MAXI = LZP_DEC / 2 + 8;       // instructions per round (an instruction is at least two bytes long)
 constexpr int LZP_MAXMS = 1024;          // milestones of the serial walk
 constexpr int LZP_JUMP_PASSES = 3;       // doublings of the jump table: a milestone every 8..27 instructions
 constexpr int LZP_MAXZ = 80;            // zero bytes of a length extension a candidate decode follows (255 bytes each)
 constexpr int LZP_RETRY = 0x7f;          // never leaves the library
 constexpr uint32_t LZP_FAR = 0x7ffb, LZP_STEP = 0x7ffc, LZP_END = 0x7ffd, LZP_BAD = 0x7ffe, LZP_OUT = 0x7fff; // next[] codes above any index
 constexpr uint32_t LZP_FIRST = 0x4000;   // visited[]: the block's first byte (state class 2)
-static_assert(LZP_DEC == (1 << 13) && 2 * LZP_DEC * 2 <= LZP_RSYM * 2, "the jump table overlays the symbol buffer");
+static_assert(LZP_DEC_BITS <= 13 && 2 * LZP_DEC * 2 <= LZP_RSYM * 2, "the jump table overlays the symbol buffer");
 
 struct LzpSmem {
   static constexpr int THREADS = LZP_PT;
@@ -151,7 +164,7 @@ __device__ __forceinline__ LzpInst lzp_decode(const uint8_t *w, int p, int cls, 
   return r;
 }
 
-__global__ void __launch_bounds__(LZP_PT, 2)
+__global__ void __launch_bounds__(LZP_PT, DCMP_LZP_CTAS)
 lzo_parallel_kernel(int mode, int64_t nblocks, const uint8_t *src_base, const int64_t *src_off, const int64_t *src_len,
                     uint8_t *dst_base, const int64_t *dst_off, const int64_t *dst_cap, int64_t *consumed,
                     int64_t *produced, int32_t *status) {
@@ -200,7 +213,7 @@ lzo_parallel_kernel(int mode, int64_t nblocks, const uint8_t *src_base, const in
     auto link = [&](const LzpInst &r, int p) -> uint32_t { // where the instruction at p leads
       if (r.kind) return r.kind;
       const int np = p + r.hdr + r.lit + r.trail;
-      return np < LZP_DEC ? (uint32_t)np | ((uint32_t)r.ncls << 13) : LZP_FAR;
+      return np < LZP_DEC ? (uint32_t)np | ((uint32_t)r.ncls << LZP_DEC_BITS) : LZP_FAR;
     };
     for (int p = tid; p < LZP_DEC; p += LZP_PT) {
       // the two states differ only in what an opcode below 16 means
@@ -260,7 +273,7 @@ lzo_parallel_kernel(int mode, int64_t nblocks, const uint8_t *src_base, const in
         return false;
       }
       if (e == LZP_END || e == LZP_FAR) {
-        const LzpInst r = lzp_decode(S.win, (int)(vis & (LZP_DEC - 1)), (vis & LZP_FIRST) ? 2 : (int)((vis >> 13) & 1), wlim, at_end);
+        const LzpInst r = lzp_decode(S.win, (int)(vis & (LZP_DEC - 1)), (vis & LZP_FIRST) ? 2 : (int)((vis >> LZP_DEC_BITS) & 1), wlim, at_end);
         if (e == LZP_END) {
           S.ended = 1;
           S.ip_end = w_lo + (int64_t)(vis & (LZP_DEC - 1)) + r.hdr; // the terminator produces nothing: not listed
@@ -276,7 +289,7 @@ lzo_parallel_kernel(int mode, int64_t nblocks, const uint8_t *src_base, const in
       return true;
     };
     if (tid == 0) {
-      xcur = (uint32_t)p0 | ((uint32_t)(cls0 & 1) << 13);
+      xcur = (uint32_t)p0 | ((uint32_t)(cls0 & 1) << LZP_DEC_BITS);
       bool stop = false;
       if (cls0 == 2) stop = !single(link(lzp_decode(S.win, p0, 2, wlim, at_end), p0), (uint32_t)p0 | LZP_FIRST);
       int m = 0;
@@ -332,7 +345,7 @@ lzo_parallel_kernel(int mode, int64_t nblocks, const uint8_t *src_base, const in
         S.nvis = nlist;
         S.bulk_len = bulk;
         S.ip_after = ip_after >= 0 ? ip_after : w_lo + (int64_t)(xcur & (LZP_DEC - 1));
-        S.cls_after = ip_after >= 0 ? cls_after : (int)(xcur >> 13);
+        S.cls_after = ip_after >= 0 ? cls_after : (int)(xcur >> LZP_DEC_BITS);
         if (nlist == 0 && !bulk && !S.ended) S.give_up = 1; // no progress: cannot happen on the happy path
       }
     }
@@ -361,7 +374,7 @@ lzo_parallel_kernel(int mode, int64_t nblocks, const uint8_t *src_base, const in
     const int j0 = tid * per;
     auto inst = [&](int j) {
       const uint32_t vv = S.visited[j];
-      return lzp_decode(S.win, (int)(vv & (LZP_DEC - 1)), (vv & LZP_FIRST) ? 2 : (int)((vv >> 13) & 1), wlim, at_end);
+      return lzp_decode(S.win, (int)(vv & (LZP_DEC - 1)), (vv & LZP_FIRST) ? 2 : (int)((vv >> LZP_DEC_BITS) & 1), wlim, at_end);
     };
     auto out_len = [](const LzpInst &r) {
       const uint32_t ol = (uint32_t)(r.lit + r.mlen + r.trail);
@@ -452,7 +465,7 @@ lzo_parallel_kernel(int mode, int64_t nblocks, const uint8_t *src_base, const in
       if (ncut < n) { // cut by the budget: the next round starts at the first instruction left out
         const uint32_t vv = S.visited[ncut];
         S.ip = w_lo + (int64_t)(vv & (LZP_DEC - 1));
-        S.cls = (int)((vv >> 13) & 1);
+        S.cls = (int)((vv >> LZP_DEC_BITS) & 1);
         S.ended = 0;
       } else {
         S.ip = S.ip_after;
