@@ -77,6 +77,9 @@ struct LzpSmem {
   int cls_after;
   int64_t ip_end;              // input position after the terminator
   int64_t bulk_len;            // a literal run moved by raw_copy instead
+  int64_t bm_len, bm_pay;      // a match longer than the symbol buffer, replicated directly: length, input position of its trailing literals
+  uint32_t bm_dist;
+  int bm_trail;
   uint32_t mbar_phase;
   __align__(8) uint64_t mbar;
 };
@@ -269,6 +272,28 @@ lzo_parallel_kernel(int mode, int64_t nblocks, const uint8_t *src_base, const in
               }
             }
           }
+          if (e == LZP_OUT && S.give_up) {
+            // ... or a match whose length extension is longer than a candidate decode follows (run-length data)
+            int64_t q = w_lo + p0;
+            const int chr = in[q++];
+            const bool m4 = chr >= 16 && chr <= 31 && (chr & 7) == 0, m3 = chr >= 32 && chr <= 63 && (chr & 31) == 0;
+            if (m3 || m4) {
+              int64_t z = 0;
+              while (q < ilen && in[q] == 0) { q++; z++; }
+              if (q + 3 <= ilen) {
+                const int64_t len = (m4 ? 7 : 31) + z * 255 + in[q++];
+                const int s16 = in[q] | (in[q + 1] << 8);
+                q += 2;
+                const int64_t dist = m4 ? 16384 + (((chr & 8) >> 3) << 14) + (s16 >> 2) : (s16 >> 2) + 1;
+                const int trail = s16 & 3;
+                if (!(m4 && dist == 16384) && q < ilen && trail <= ilen - q && dist <= (int64_t)out0 &&
+                    (int64_t)out0 + len + 2 + trail <= olen) {
+                  S.bm_len = len + 2; S.bm_dist = (uint32_t)dist; S.bm_trail = trail; S.bm_pay = q;
+                  S.give_up = 0;
+                }
+              }
+            }
+          }
         }
         return false;
       }
@@ -289,6 +314,7 @@ lzo_parallel_kernel(int mode, int64_t nblocks, const uint8_t *src_base, const in
       return true;
     };
     if (tid == 0) {
+      S.bm_len = 0;
       xcur = (uint32_t)p0 | ((uint32_t)(cls0 & 1) << LZP_DEC_BITS);
       bool stop = false;
       if (cls0 == 2) stop = !single(link(lzp_decode(S.win, p0, 2, wlim, at_end), p0), (uint32_t)p0 | LZP_FIRST);
@@ -346,7 +372,7 @@ lzo_parallel_kernel(int mode, int64_t nblocks, const uint8_t *src_base, const in
         S.bulk_len = bulk;
         S.ip_after = ip_after >= 0 ? ip_after : w_lo + (int64_t)(xcur & (LZP_DEC - 1));
         S.cls_after = ip_after >= 0 ? cls_after : (int)(xcur >> LZP_DEC_BITS);
-        if (nlist == 0 && !bulk && !S.ended) S.give_up = 1; // no progress: cannot happen on the happy path
+        if (nlist == 0 && !bulk && !S.bm_len && !S.ended) S.give_up = 1; // no progress: cannot happen on the happy path
       }
     }
     __syncthreads();
@@ -367,6 +393,28 @@ lzo_parallel_kernel(int mode, int64_t nblocks, const uint8_t *src_base, const in
       __syncthreads();
       continue;
     }
+    auto bulk_match = [&]() {
+      // A match longer than the symbol buffer is replicated output -> output directly: byte k repeats byte k mod dist
+      // of the period in front of it, which is complete, so the copy has no order (lzo.ml:206-216 semantics); then
+      // its trailing literals.  Arguments in S.bm_*; all threads call.
+      const uint32_t o_abs = S.out_pos;
+      uint8_t *const o = out + o_abs;
+      const uint32_t dist = S.bm_dist, mlen = (uint32_t)S.bm_len;
+      const int trail = S.bm_trail;
+      const int64_t pay = S.bm_pay;
+      for (uint32_t kk = (uint32_t)tid; kk < mlen; kk += LZP_PT) o[kk] = __ldcg(o - dist + kk % dist);
+      if (tid < trail) o[mlen + tid] = in[pay + tid];
+      __syncthreads();
+      if (tid == 0) {
+        S.out_pos = o_abs + mlen + (uint32_t)trail;
+        S.ip = pay + trail;
+        S.cls = trail ? 1 : 0;
+        S.ended = 0; // (a terminator seen further down the chain is met again)
+        S.bm_len = 0;
+      }
+      __syncthreads();
+    };
+    if (S.bm_len) { bulk_match(); continue; }
     // ---- 3: output lengths, scan, cut at the budget, validity (a thread owns `per` consecutive instructions and
     // decodes them again in every pass: cheaper than keeping them)
     const int n = S.nvis;
@@ -406,10 +454,21 @@ lzo_parallel_kernel(int mode, int64_t nblocks, const uint8_t *src_base, const in
     }
     __syncthreads();
     const int ncut = S.cut;
-    if (ncut == 0) { // one instruction larger than the symbol buffer (a very long match): the general kernel takes the block
-      if (tid == 0) S.give_up = 1;
+    if (ncut == 0) {
+      // the round's first instruction alone is larger than the symbol buffer: a very long match (run-length data)
+      const LzpInst r = inst(0);
+      const bool ok = !r.kind && r.mlen && (int64_t)r.dist <= (int64_t)out0 && (int64_t)out0 + r.mlen + r.trail <= olen;
       __syncthreads();
-      break;
+      if (tid == 0) {
+        if (ok) {
+          S.bm_len = r.mlen; S.bm_dist = r.dist; S.bm_trail = r.trail;
+          S.bm_pay = w_lo + (int64_t)(S.visited[0] & (LZP_DEC - 1)) + r.hdr;
+        } else S.give_up = 1;
+      }
+      __syncthreads();
+      if (S.give_up) break;
+      bulk_match();
+      continue;
     }
     // validity: distance within the produced output (Invalid_dictionary / Out_of_bound otherwise), output window
     {
