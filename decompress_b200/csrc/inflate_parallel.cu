@@ -962,7 +962,7 @@ inflate_parallel_kernel(int fmt, int64_t nstreams, const uint8_t *src_base, cons
         for (int span = 1; span < PT; span <<= 1) {
           const int j = M.jump[cur][tid];
           if (j < PT) {
-            if (M.mark[tid]) M.mark[j] = 1;
+            if (M.mark[tid]) M.mark[j] = 1; // (racy on purpose: a mark that lands early only marks members of the orbit sooner)
             M.jump[cur ^ 1][tid] = M.jump[cur][j];
           } else {
             M.jump[cur ^ 1][tid] = (uint16_t)PT;
