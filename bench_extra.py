@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """bench_extra.py — the other BASELINE.json configurations (not the driver's headline line; that is bench.py).
 
-    python bench_extra.py [--what c1,c3,c5] [--c3-mib 256] [--c5-blocks 256] [--steps 5]
+    python bench_extra.py [--what c1,c3,c5] [--c3-mib 1024] [--c5-blocks 256] [--steps 5]
 
 One JSON line per configuration: device-resident throughput (CUDA events), algorithmic-bytes roofline fraction,
 and a CPU reference beside it (the oracle port for inflate / LZO; system zlib level 6, the reference's own
@@ -26,7 +26,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--what", default="c1,c3,c4,c5")
     ap.add_argument("--c4-mib", type=int, default=512)
-    ap.add_argument("--c3-mib", type=int, default=256)
+    ap.add_argument("--c3-mib", type=int, default=1024)
     ap.add_argument("--c5-blocks", type=int, default=256)
     ap.add_argument("--steps", type=int, default=5)
     args = ap.parse_args()

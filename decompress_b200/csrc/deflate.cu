@@ -64,26 +64,33 @@ struct DfTree {            // Huffman construction scratch; only alive after tok
 template <int HB>
 struct DfSmemT {
   static constexpr int HASH_BITS = HB;
+  // The hash table is dead once the chunk is tokenised; everything that is built afterwards lives in its space: the
+  // Huffman construction scratch, then (over the scratch) the output bit window, and behind them the codes.
   union {
     uint32_t head[1 << HB];   // two most recent positions per hash: [15:0] newest, [31:16] the one before
-    DfTree tree;
+    struct {
+      union {
+        DfTree tree;
+        uint32_t win[DF_WIN]; // output bit window: cleared and used only after the last tree is built
+      };
+      uint16_t code_l[288];
+      uint16_t code_d[32];
+      uint16_t code_bl[19];
+      uint8_t len_l[288];
+      uint8_t len_d[32];
+      uint8_t len_bl[19];
+      uint8_t rle_sym[320];
+      uint8_t rle_extra[320];
+    };
   };
   uint32_t freq_l[288];
   uint32_t freq_d[32];
   uint32_t freq_bl[19];
-  uint16_t code_l[288];
-  uint16_t code_d[32];
-  uint16_t code_bl[19];
-  uint8_t len_l[288];
-  uint8_t len_d[32];
-  uint8_t len_bl[19];
-  uint8_t rle_sym[320];
-  uint8_t rle_extra[320];
-  uint32_t win[DF_WIN];
   uint32_t extra_bits; // total extra bits of the tokens (for the stored/dynamic decision)
   int n_rle;
   int hlit, hdist;
 };
+static_assert(sizeof(DfTree) + 2 * (288 + 32 + 19) + (288 + 32 + 19) + 640 + 16 <= sizeof(uint32_t) * (1 << DF_HASH_BITS_FAST), "what follows tokenising overlays the hash table");
 static_assert(sizeof(DfTree) <= sizeof(uint32_t) * (1 << DF_HASH_BITS_FAST), "tree scratch overlays the hash table");
 
 __device__ __constant__ uint8_t c_bl_order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15}; // de.ml:237
@@ -637,6 +644,7 @@ int deflate_ctas_per_sm() {
   const size_t smem = deflate_smem_bytes(1);
   cudaFuncSetAttribute(deflate_chunk_kernel<DF_HASH_BITS_FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, deflate_chunk_kernel<DF_HASH_BITS_FAST>, DF_WARPS * 32, smem) != cudaSuccess || n < 1) n = 2;
+  if (getenv("DCMP_DEF_CTAS")) n = atoi(getenv("DCMP_DEF_CTAS")) > 0 ? atoi(getenv("DCMP_DEF_CTAS")) : n; // tuning knob
   return n;
 }
 #endif
