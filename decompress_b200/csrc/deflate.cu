@@ -120,8 +120,24 @@ __device__ __forceinline__ uint32_t df_load32(const uint8_t *p) { // unaligned l
 }
 // length of the common prefix of d[a..] and d[b..] (a < b), at most maxlen; `safe` = bytes from b that may be
 // read with the 8-byte-footprint word loads
+__device__ __forceinline__ unsigned long long df_load64(const uint8_t *p) { // the same from two aligned 64-bit words
+  const uintptr_t a = (uintptr_t)p;
+  const uint2 *w = reinterpret_cast<const uint2 *>(a & ~(uintptr_t)7);
+  const uint2 w0 = w[0], w1 = w[1];
+  const uint32_t sh = 8u * (uint32_t)(a & 3);
+  const bool hi = (a & 4) != 0; // start in the upper half of the first word
+  const uint32_t x0 = hi ? w0.y : w0.x, x1 = hi ? w1.x : w0.y, x2 = hi ? w1.y : w1.x;
+  return (unsigned long long)__funnelshift_r(x0, x1, sh) | ((unsigned long long)__funnelshift_r(x1, x2, sh) << 32);
+}
 __device__ __forceinline__ int df_match_len(const uint8_t *d, int a, int b, int maxlen, int safe) {
   int l = 0;
+  // eight bytes per step while the 16-byte footprint of the loads stays inside the chunk: most matches end in the first
+  const int wmax8 = maxlen < safe - 15 ? maxlen : safe - 15;
+  while (l + 8 <= wmax8) {
+    const unsigned long long x = df_load64(d + a + l) ^ df_load64(d + b + l);
+    if (x) return l + ((__ffsll((long long)x) - 1) >> 3);
+    l += 8;
+  }
   const int wmax = maxlen < safe - 7 ? maxlen : safe - 7;
   while (l + 4 <= wmax) {
     const uint32_t x = df_load32(d + a + l) ^ df_load32(d + b + l);
