@@ -129,8 +129,7 @@ __device__ __forceinline__ unsigned long long df_load64(const uint8_t *p) { // t
   const uint32_t x0 = hi ? w0.y : w0.x, x1 = hi ? w1.x : w0.y, x2 = hi ? w1.y : w1.x;
   return (unsigned long long)__funnelshift_r(x0, x1, sh) | ((unsigned long long)__funnelshift_r(x1, x2, sh) << 32);
 }
-__device__ __forceinline__ int df_match_len(const uint8_t *d, int a, int b, int maxlen, int safe) {
-  int l = 0;
+__device__ __forceinline__ int df_match_len(const uint8_t *d, int a, int b, int maxlen, int safe, int l = 0) { // l: bytes already known equal
   // eight bytes per step while the 16-byte footprint of the loads stays inside the chunk: most matches end in the first
   const int wmax8 = maxlen < safe - 15 ? maxlen : safe - 15;
   while (l + 8 <= wmax8) {
@@ -329,11 +328,23 @@ __device__ void df_compress_chunk(SM &S, const uint8_t *d, int len, bool last, i
         S.head[h] = (prev << 16) | (uint32_t)p;
       }
       if (cand0 >= 0 && cand0 < p && p - cand0 <= 32768) {
-        int l = df_match_len(d, cand0, p, maxlen, len - p);
-        int dist = p - cand0;
-        if (level >= 2 && l < maxlen && cand1 >= 0 && cand1 < cand0 && p - cand1 <= 32768) {
-          const int l1 = df_match_len(d, cand1, p, maxlen, len - p);
-          if (l1 > l) { l = l1; dist = p - cand1; }
+        const bool two = level >= 2 && cand1 >= 0 && cand1 < cand0 && p - cand1 <= 32768;
+        int l, dist = p - cand0;
+        if (maxlen >= 8 && len - p >= 16) {
+          // the first eight bytes of both candidates in one round trip: most matches end there
+          const unsigned long long P8 = df_load64(d + p), A8 = df_load64(d + cand0) ^ P8;
+          const unsigned long long B8 = two ? df_load64(d + cand1) ^ P8 : 1ull;
+          l = A8 ? (__ffsll((long long)A8) - 1) >> 3 : df_match_len(d, cand0, p, maxlen, len - p, 8);
+          if (two && l < maxlen) {
+            const int l1 = B8 ? (__ffsll((long long)B8) - 1) >> 3 : df_match_len(d, cand1, p, maxlen, len - p, 8);
+            if (l1 > l) { l = l1; dist = p - cand1; }
+          }
+        } else {
+          l = df_match_len(d, cand0, p, maxlen, len - p);
+          if (two && l < maxlen) {
+            const int l1 = df_match_len(d, cand1, p, maxlen, len - p);
+            if (l1 > l) { l = l1; dist = p - cand1; }
+          }
         }
         if (l >= DF_MIN_MATCH || (l == 3 && dist < DF_TOO_FAR)) { mlen = l; mdist = dist; }
       }
