@@ -504,12 +504,19 @@ lzo_parallel_kernel(int mode, int64_t nblocks, const uint8_t *src_base, const in
         if (r.mlen) {
           const int32_t s = i - (int32_t)r.dist; // symbol index of the first source byte (below bias: earlier rounds)
           const uint32_t len = (uint32_t)r.mlen, dist = r.dist;
-          for (uint32_t jj = 0; jj < len; jj++) {
-            const int32_t sj = s + (int32_t)(dist < len ? jj % dist : jj); // an overlapping copy points at its first period
-            uint32_t v;
-            if (sj >= (int32_t)bias) v = 256u + (uint32_t)sj;
-            else v = __ldcg(G0 + sj);
-            S.sym[i + (int32_t)jj] = (uint16_t)v;
+          const bool overlap = dist < len; // an overlapping copy points at its first period
+          for (uint32_t j0 = 0; j0 < len; j0 += 8) { // eight at a time: the history reads (L2) leave together
+            uint32_t v[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+              const uint32_t jj = j0 + (uint32_t)u;
+              const int32_t sj = s + (int32_t)(overlap ? jj % dist : jj);
+              v[u] = 256u + (uint32_t)sj;
+              if (jj < len && sj < (int32_t)bias) v[u] = __ldcg(G0 + sj);
+            }
+#pragma unroll
+            for (int u = 0; u < 8; u++)
+              if (j0 + (uint32_t)u < len) S.sym[i + (int32_t)j0 + u] = (uint16_t)v[u];
           }
           i += (int32_t)len;
           for (int jj = 0; jj < r.trail; jj++) S.sym[i + jj] = pay[jj];
