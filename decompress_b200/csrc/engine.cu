@@ -197,7 +197,7 @@ int dcmp_inflate_batch_device(dcmp_engine *e, int fmt, int64_t n, const uint8_t 
   cudaStream_t st = (cudaStream_t)cuda_stream; // NULL = the legacy default stream, as everywhere in CUDA
   // gzip: one member per unit.  The header is parsed on the device, the DEFLATE body goes through the raw
   // kernels with rebased offset tables, then CRC-32 / ISIZE are checked on the device (gzip_frame.cu).
-  const int64_t *g_src_off = d_src_off, *g_src_len = d_src_len;
+  const int64_t *g_src_off = d_src_off;
   int64_t *gz_off = nullptr, *gz_len = nullptr;
   int32_t *gz_pre = nullptr;
   if (fmt == DCMP_FMT_GZIP) {
@@ -240,7 +240,6 @@ int dcmp_inflate_batch_device(dcmp_engine *e, int fmt, int64_t n, const uint8_t 
                               d_status, st);
     e->launches += 1;
   }
-  (void)g_src_len;
   CU(cudaGetLastError());
   return DCMP_API_OK;
 }

@@ -10,32 +10,36 @@
 //   round = PT lanes x SUB_BITS-bit sub-chunks of the compressed stream (an odd number of
 //           32-bit words per lane, so the lanes of a warp read the TMA-staged window
 //           without shared-memory bank conflicts)
-//   A  speculative decode   every lane decodes its sub-chunk from an arbitrary bit offset
-//                           into 32-bit tokens (literal | len,dist) written to an
-//                           L2-resident scratch in [token][lane] order (coalesced), and
-//                           leaves a checkpoint (first token start, token index, bytes so
-//                           far) for every 64-bit window it crosses;
-//   B  head re-decode       lane t restarts at the true entry point handed over by lane
-//                           t-1 and decodes until its first token start inside a 64-bit
-//                           window equals the speculative pass's checkpoint (Huffman
-//                           self-synchronisation: ~10 tokens on text, geometric tail);
-//                           from there on the speculative tokens are the true ones;
-//   C  chain + scan         the round is cut at the first lane that cannot be validated
-//                           (end of block, token buffer full, no re-synchronisation,
-//                           output budget); an exclusive scan of emitted byte counts
-//                           gives every lane its output offset;
-//   D  symbol replay        every lane replays its tokens into a 16-bit symbol buffer at
-//                           its output offset.  A back-reference into the 32 KiB history
-//                           (earlier rounds: the stream's own output, read back through L2
-//                           with .cg loads — keeping it out of shared memory buys a third CTA
-//                           per SM; DCMP_HIST_GLOBAL=0 keeps a shared byte ring instead) is
-//                           copied; a back-reference into bytes produced in this round — by
-//                           another lane or by this one — is not waited for: the lane stores
-//                           a marker 256 + (index of the source symbol);
-//   E  resolve + drain      16 symbols per thread: markers are chased to a literal
-//                           (markers only point backwards, chains are short), the 16
-//                           bytes leave through one 128-bit store to HBM; Adler-32 is
-//                           folded over the same registers.
+//   A  speculative decode   every lane starts WARMUP_BITS before its sub-chunk, at an arbitrary bit
+//                           offset, and throws away what it decodes there (Huffman streams
+//                           self-synchronise: most lanes are on the true token boundaries when their
+//                           own bits begin); from bit 0 on it keeps 32-bit tokens (literal | len,dist),
+//                           written to an L2-resident scratch as 128-bit batches, and a checkpoint
+//                           (position, token index, bytes so far) per 2^CKPT_SHIFT-bit window;
+//   B  head re-decode       lane t restarts at the true entry point handed over by lane t-1 and
+//                           decodes until a token start coincides with a checkpoint of the
+//                           speculative pass (of its own sub-chunk, or of a later lane's when it
+//                           crosses its own without meeting one); from there on the speculative
+//                           tokens are the true ones.  With the warm-up ~5 % of the lanes need it;
+//   C  chain + scan         lanes covered by a crossing head are absorbed (pointer doubling); the round
+//                           is closed at the first lane that cannot be validated (end of block, token
+//                           buffer full); an exclusive scan of emitted byte counts gives every lane
+//                           its output offset; the output leaves in slices that fit the symbol buffer;
+//   D  symbol replay        every lane replays its tokens into a 16-bit symbol buffer at its output
+//                           offset.  A back-reference into the 32 KiB history (earlier rounds or
+//                           slices: the stream's own output, read back through L2 with .cg loads —
+//                           keeping it out of shared memory buys a third CTA per SM;
+//                           DCMP_HIST_GLOBAL=0 keeps a shared byte ring instead) is copied; a
+//                           back-reference into bytes produced in this slice — by another lane or
+//                           by this one — is not waited for: the lane stores a marker
+//                           256 + (index of the source symbol);
+//   E  resolve + drain      16 symbols per thread: markers are chased to a literal (markers only
+//                           point backwards, chains are short), the 16 bytes leave through one
+//                           128-bit store to HBM; Adler-32 is folded over the same registers
+//                           (symbol_drain.cuh).
+// Block headers: the serial part of a dynamic header is parsed ahead of time — the next stream's by the
+// CTA's last warp during phase B, the next block's during phase D when that warp has no lanes to replay;
+// stored payloads are copied straight from the input to the output (raw_copy).
 //
 // Anything that is not the happy path — stored blocks, malformed input, exotic code sets, an
 // output buffer that is too small — makes the CTA give the stream up with status
@@ -147,12 +151,6 @@ enum : int { NEXT_CONTINUE = 0, NEXT_HEADER = 1, NEXT_FINISH = 2, NEXT_RETRY = 3
 // checkpoint: [4:0] low bits of the position of the first token start inside the window,
 //             [12:5] index of that token, [30:13] bytes emitted before it, [31] none
 __device__ __forceinline__ bool tok_is_match(uint32_t t) { return (t >> 23) & 1u; }
-__device__ __forceinline__ void batch_put(uint4 &b, int k, uint32_t t) {
-  if (k == 0) b.x = t;
-  if (k == 1) b.y = t;
-  if (k == 2) b.z = t;
-  if (k == 3) b.w = t;
-}
 // one predicated 16-bit shared-memory store, without a branch
 __device__ __forceinline__ void st_sym_if(bool pred, uint16_t *addr, uint32_t v) {
 #ifdef DCMP_EMU
@@ -1136,7 +1134,6 @@ inflate_parallel_kernel(int fmt, int64_t nstreams, const uint8_t *src_base, cons
         //   straddling the start of the round, or overlapping itself inside the group: per symbol
         const int total_tok = in_slice ? d_nh + (d_spec ? ns - d_k : 0) : 0;
         const int delta = HEAD_CAP + d_k - d_nh; // token index -> slot for the speculative part
-        const uint4 *head_lane = reinterpret_cast<const uint4 *>(tok_scratch + ((size_t)blockIdx.x * PT + d_owner) * TOK_SLOTS);
         STAT(if (in_slice) { g_stats.head_tokens += d_nh; g_stats.used_tokens += total_tok; } long iters = 0;)
 #if DCMP_HIST_GLOBAL
         // history = the stream's own output in HBM/L2; symbol index s <-> address G0 + s.  L2-coherent loads
@@ -1193,7 +1190,9 @@ inflate_parallel_kernel(int fmt, int64_t nstreams, const uint8_t *src_base, cons
           const uint32_t m0 = (256u + (uint32_t)s) * 0x00010001u + 0x00010000u;
           // history: source entirely in earlier rounds (addresses are masked: the loads are always legal)
           const uint32_t r = g0_low + (uint32_t)s; // ring byte address (mod HIST) of the first source byte
+#if !DCMP_HIST_GLOBAL
           const uint32_t wi0 = r >> 2;
+#endif
           uint32_t w0 = 0, w1 = 0, w2 = 0;
           if (in_hist && rem > 0u) {
 #if DCMP_HIST_GLOBAL
