@@ -34,7 +34,10 @@
 namespace dcmp {
 
 constexpr int DF_CHUNK = 65536;
-constexpr int DF_WARPS = 4;
+#ifndef DCMP_DF_WARPS
+#define DCMP_DF_WARPS 4
+#endif
+constexpr int DF_WARPS = DCMP_DF_WARPS;
 constexpr int DF_HASH_BITS_FAST = 11;     // levels 1..6: 8 KiB of hash table per warp, four CTAs per SM
 constexpr int DF_HASH_BITS_BEST = 12;     // levels 7..12: 16 KiB, two CTAs per SM, ~2 % smaller output
 constexpr int DF_SLOT = DF_CHUNK + 64;   // bytes of scratch output per chunk (stored worst case: len + 15)

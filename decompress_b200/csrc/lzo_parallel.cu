@@ -48,7 +48,10 @@ constexpr int LZP_DEC = 1 << LZP_DEC_BITS; // window positions decoded as candid
 constexpr int LZP_WIN = 2 * LZP_DEC;     // input bytes staged per round
 constexpr int LZP_MAXI = LZP_DEC / 2 + 8;       // instructions per round (an instruction is at least two bytes long)
 constexpr int LZP_MAXMS = 1024;          // milestones of the serial walk
-constexpr int LZP_JUMP_PASSES = 3;       // doublings of the jump table: a milestone every 8..27 instructions
+#ifndef DCMP_LZP_JUMP_PASSES
+#define DCMP_LZP_JUMP_PASSES 3
+#endif
+constexpr int LZP_JUMP_PASSES = DCMP_LZP_JUMP_PASSES;       // doublings of the jump table: a milestone every 8..27 instructions
 constexpr int LZP_MAXZ = 80;            // zero bytes of a length extension a candidate decode follows (255 bytes each)
 constexpr int LZP_RETRY = 0x7f;          // never leaves the library
 constexpr uint32_t LZP_FAR = 0x7ffb, LZP_STEP = 0x7ffc, LZP_END = 0x7ffd, LZP_BAD = 0x7ffe, LZP_OUT = 0x7fff; // next[] codes above any index
