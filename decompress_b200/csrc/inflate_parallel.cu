@@ -232,6 +232,7 @@ struct ParSmem {
   uint32_t adler_a, adler_b;
   uint32_t mbar_phase;
   int abort_round;               // a lane met an invalid distance: the general kernel reports it
+  volatile uint32_t a_done[NWARP]; // round number up to which a warp has finished phase A (its lanes' exits and checkpoints are in place)
   int hdr_ready;                 // the first header of this stream was parsed ahead (S.pf)
   int nh_ready;                  // the header of the stream's NEXT block was parsed during phases D/E: lens, nh_*
   int nh_last;
@@ -661,9 +662,11 @@ inflate_parallel_kernel(int fmt, int64_t nstreams, const uint8_t *src_base, cons
     fence_mbar_init();
     S.mbar_phase = 0;
     S.pf.stream = -2;
+    for (int w = 0; w < NWARP; w++) S.a_done[w] = 0;
   }
   __syncthreads();
 
+  uint32_t round_no = 0; // data rounds this CTA has run (CTA-uniform)
   for (;;) {
     // ---------------------------------------------------------------- fetch a stream
     __syncthreads();
@@ -832,6 +835,8 @@ inflate_parallel_kernel(int fmt, int64_t nstreams, const uint8_t *src_base, cons
       uint4 *tok_spec = tok_lane + HEAD_CAP / 4;
       // lanes whose sub-chunk starts beyond the input decode nothing
       const bool lane_has_input = base_bit + (int64_t)SUB_BITS * tid < 8 * S.src_len;
+      round_no++;
+      if (tid == 0) { S.first_bad = PT; S.first_term = PT; S.abort_round = 0; S.pass_owner = -1; } // (read after the barrier that ends phase B)
       // ---- A: speculative decode of the own sub-chunk from bit 0
       int ns = 0;
       uint32_t out_s = 0;
@@ -874,8 +879,14 @@ inflate_parallel_kernel(int fmt, int64_t nstreams, const uint8_t *src_base, cons
       S.last_ck[tid] = (int8_t)last_ck;
       S.spec_ns[tid] = (uint8_t)ns;
       S.spec_out[tid] = (uint16_t)out_s;
-      if (tid == 0) { S.first_bad = PT; S.first_term = PT; S.abort_round = 0; S.pass_owner = -1; }
-      __syncthreads();
+      // No CTA-wide barrier between A and B: a head needs the exit of the lane before it and the checkpoints of the
+      // lanes it runs through, so a warp waits for the warp before it only (and, in the rare case that one of its
+      // heads crosses into a later warp's sub-chunks, for that warp).  Phase A never waits: no cycle.
+      __syncwarp();
+      if (lane == 0) { __threadfence_block(); S.a_done[warp] = round_no; }
+      if (warp > 0) { while (S.a_done[warp - 1] != round_no) DCMP_SPIN(); }
+      __threadfence_block();
+      __syncwarp();
       // ---- B: re-synchronise with the true entry point handed over by the previous lane.
       // Lane t assumes that lane t-1's true sequence ends in that lane's speculative sequence
       // (entry = its exit) and decodes from there until the start of one of its tokens coincides
@@ -910,6 +921,7 @@ inflate_parallel_kernel(int fmt, int64_t nstreams, const uint8_t *src_base, cons
                 ubase += SUB_BITS;
                 seen_ck = -1;
                 if (u >= PT) { hcat = H_PASS; hpos = p; break; } // past the window: the next round starts here
+                if ((u >> 5) != warp) { while (S.a_done[u >> 5] != round_no) DCMP_SPIN(); __threadfence_block(); } // that warp's phase A
                 lck = S.last_ck[u];
                 xk_u = S.exit_kind[u];
                 xp_u = S.exit_pos[u];

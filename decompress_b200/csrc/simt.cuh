@@ -9,6 +9,12 @@
 #define DCMP_DYN_SMEM(name) extern __shared__ __align__(128) unsigned char name[]
 #define DCMP_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
 #endif
+// inside a polling loop on a shared-memory flag: let the other warps (emulator: the other fibers) run
+#ifdef DCMP_EMU
+#define DCMP_SPIN() simt::yield_to_sched()
+#else
+#define DCMP_SPIN() __nanosleep(32)
+#endif
 
 namespace dcmp {
 __device__ __forceinline__ int imin(int a, int b) { return a < b ? a : b; }
