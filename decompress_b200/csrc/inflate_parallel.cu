@@ -103,7 +103,7 @@ __host__ __device__ constexpr uint32_t pe_make(uint32_t base, uint32_t extra, ui
 }
 constexpr int DCMP_INTERNAL_RETRY = 0x7f; // never leaves the library
 static_assert(SUB_WORDS % 2 == 1, "odd lane stride keeps the window reads conflict-free");
-static_assert(PT % 32 == 0 && PT <= 1024, "");
+static_assert(PT % 64 == 0 && PT <= 1024, "the two halves of the CTA build one decode table each");
 static_assert(SPEC_CAP < 256 && LANE_BYTE_CAP + 258 < (1 << 19), "checkpoint fields");
 static_assert(SPEC_CAP % 4 == 0 && HEAD_CAP % 4 == 0, "token slots are moved in batches of four");
 constexpr int MAX_CROSS = 6;              // sub-chunk boundaries one head decode may cross
@@ -203,7 +203,7 @@ struct ParSmem {
   uint32_t dist[(1 << DIST_ROOT) + DIST_SUB];
   uint8_t lens[MAX_LENS];
   HuffMeta ml, md;
-  uint32_t run_cnt[16];
+  uint32_t run_cnt[2][16];       // per table under construction (literal/length, distance)
   // per-lane results of a round
   uint16_t exit_pos[PT];         // spec pass: bit offset (own sub-chunk coordinates) after the last token
   uint8_t exit_kind[PT];
@@ -216,7 +216,7 @@ struct ParSmem {
   uint32_t warp_c[NWARP];
   unsigned long long adl_s[NWARP];
   long long adl_b[NWARP];
-  uint32_t hdr_hlit, hdr_hdist, tbl_ok, sub_alloc;
+  uint32_t hdr_hlit, hdr_hdist, tbl_ok2[2], sub_alloc2[2];
   int first_bad, first_term;
   uint32_t slice_end;
   // stream state (CTA-uniform)
@@ -323,7 +323,7 @@ __device__ __forceinline__ int decode_token(ParSmem &S, LaneBits &lb, uint32_t l
 // exactly 1) and, for the literal/length and distance alphabets, the two incomplete shapes the
 // reference accepts (de.ml:544-550): no code at all and a single 1-bit code; their unassigned slots
 // are PE_INVALID, which sends a stream that really uses them to the general kernel.  Returns false
-// (CTA-uniform) otherwise, or when the sub-tables do not fit.  `scratch`: (1 << root_max) + MAX_LENS words.
+// (CTA-uniform) otherwise, or when the sub-tables do not fit.  `scratch_all`: 2 x ((1 << LIT_ROOT) + MAX_LENS) words.
 __device__ __forceinline__ uint32_t pe_symbol(int kind, int s, uint32_t l) {
   if (kind == KIND_DISTS) {
     const uint32_t b = c_dist_base[s & 31];
@@ -334,24 +334,36 @@ __device__ __forceinline__ uint32_t pe_symbol(int kind, int s, uint32_t l) {
   const int i = (s - 257) & 31; // 286/287 decode as a length-3 match (de.ml:293-311)
   return PE_LEN | pe_make(c_len_base[i], c_len_extra[i], l);
 }
-__device__ bool build_fast_table(ParSmem &S, int kind, const uint8_t *lens, int n, uint32_t *tbl, int root_max, int sub_cap,
-                                 HuffMeta &m, uint32_t *scratch, int tid) {
+// Both tables of a block are built at the same time: the lower half of the CTA builds the literal/length table, the
+// upper half the distance table — same code, same barriers, half as many of them as one after the other.
+__device__ bool build_fast_tables(ParSmem &S, const uint8_t *lens_l, int n_l, const uint8_t *lens_d, int n_d, uint32_t *scratch_all,
+                                  int tid) {
+  constexpr int NT = PT / 2;
+  const int half = tid >= NT ? 1 : 0, t = tid - half * NT;
+  const int kind = half ? KIND_DISTS : KIND_LENS;
+  const uint8_t *lens = half ? lens_d : lens_l;
+  const int n = half ? n_d : n_l;
+  uint32_t *tbl = half ? S.dist : S.lit;
+  const int root_max = half ? DIST_ROOT : LIT_ROOT, sub_cap = half ? DIST_SUB : LIT_SUB;
+  HuffMeta &m = half ? S.md : S.ml;
+  uint32_t *scratch = scratch_all + half * ((1 << LIT_ROOT) + MAX_LENS); // (1 << root_max) + n words per table
   uint32_t *const code_of = scratch + (1 << root_max); // per symbol: bit-reversed code | len << 16
+  uint32_t *run_cnt = S.run_cnt[half];
   __syncthreads();
-  if (tid < 16) S.run_cnt[tid] = 0;
+  if (t < 16) run_cnt[t] = 0;
   __syncthreads();
-  for (int s = tid; s < n; s += PT) {
+  for (int s = t; s < n; s += NT) {
     int l = lens[s];
-    if (l) atomicAdd(&S.run_cnt[l], 1u);
+    if (l) atomicAdd(&run_cnt[l], 1u);
   }
   __syncthreads();
-  if (tid == 0) {
+  if (t == 0) {
     int left = 1, maxl = 0;
     uint32_t code = 0;
     m.cnt[0] = 0; m.first[0] = 0;
     for (int l = 1; l <= 15; l++) {
-      uint32_t c = S.run_cnt[l];
-      code = (code + (l > 1 ? S.run_cnt[l - 1] : 0)) << 1;
+      uint32_t c = run_cnt[l];
+      code = (code + (l > 1 ? run_cnt[l - 1] : 0)) << 1;
       m.first[l] = (uint16_t)code;
       m.cnt[l] = (uint16_t)c;
       left = (left << 1) - (int)c;
@@ -365,27 +377,27 @@ __device__ bool build_fast_table(ParSmem &S, int kind, const uint8_t *lens, int 
     }
     m.maxl = maxl;
     m.root = maxl < root_max ? maxl : root_max;
-    S.tbl_ok = ok ? 1u : 0u;
-    S.sub_alloc = 0;
+    S.tbl_ok2[half] = ok ? 1u : 0u;
+    S.sub_alloc2[half] = 0;
   }
   __syncthreads();
-  if (!S.tbl_ok) return false;
-  if (tid < 16) S.run_cnt[tid] = 0;
+  if (!(S.tbl_ok2[0] && S.tbl_ok2[1])) return false; // (CTA-uniform)
+  if (t < 16) run_cnt[t] = 0;
   const int root = m.root;
   const uint32_t rmask = (1u << root) - 1u;
-  for (int i = tid; i < (1 << root); i += PT) { tbl[i] = PE_INVALID; scratch[i] = 0; }
+  for (int i = t; i < (1 << root); i += NT) { tbl[i] = PE_INVALID; scratch[i] = 0; }
   __syncthreads();
   // canonical rank of every symbol among the symbols of its length (by symbol index):
-  // warp 0 walks the alphabet 32 symbols at a time, __match_any_sync groups equal lengths.
-  if (tid < 32) {
+  // the first warp of the half walks the alphabet 32 symbols at a time, __match_any_sync groups equal lengths.
+  if (t < 32) {
     for (int base = 0; base < n; base += 32) {
-      int s = base + tid;
+      int s = base + t;
       uint32_t l = s < n ? lens[s] : 0u;
       uint32_t grp = __match_any_sync(0xffffffffu, l);
-      uint32_t rank = (uint32_t)__popc(grp & ((1u << tid) - 1u));
-      uint32_t before = S.run_cnt[l];
+      uint32_t rank = (uint32_t)__popc(grp & ((1u << t) - 1u));
+      uint32_t before = run_cnt[l];
       __syncwarp();
-      if (l && rank == 0) S.run_cnt[l] = before + (uint32_t)__popc(grp);
+      if (l && rank == 0) run_cnt[l] = before + (uint32_t)__popc(grp);
       __syncwarp();
       if (s < n) {
         if (l) {
@@ -401,11 +413,11 @@ __device__ bool build_fast_table(ParSmem &S, int kind, const uint8_t *lens, int 
   }
   __syncthreads();
   // place the sub-tables (any order) and link them from the root
-  for (int i = tid; i < (1 << root); i += PT) {
+  for (int i = t; i < (1 << root); i += NT) {
     const uint32_t bits = scratch[i];
     if (bits) {
-      const uint32_t off = atomicAdd(&S.sub_alloc, 1u << bits);
-      if (off + (1u << bits) > (uint32_t)sub_cap) S.tbl_ok = 0;
+      const uint32_t off = atomicAdd(&S.sub_alloc2[half], 1u << bits);
+      if (off + (1u << bits) > (uint32_t)sub_cap) S.tbl_ok2[half] = 0;
       else {
         const uint32_t at = (1u << root) + off;
         tbl[i] = PE_RARE | PE_LINK | (at << 13) | (bits << 5);
@@ -415,8 +427,8 @@ __device__ bool build_fast_table(ParSmem &S, int kind, const uint8_t *lens, int 
     }
   }
   __syncthreads();
-  if (!S.tbl_ok) return false;
-  for (int s = tid; s < n; s += PT) {
+  if (!(S.tbl_ok2[0] && S.tbl_ok2[1])) return false;
+  for (int s = t; s < n; s += NT) {
     const uint32_t co = code_of[s];
     const uint32_t l = co >> 16;
     if (!l) continue;
@@ -788,8 +800,7 @@ inflate_parallel_kernel(int fmt, int64_t nstreams, const uint8_t *src_base, cons
         if (S.next != NEXT_CONTINUE) continue; // stored block (or an empty one): no tables to build
         const int hlit = (int)S.hdr_hlit, hdist = (int)S.hdr_hdist;
         // (the symbol buffer is idle between rounds: it lends the builder its scratch words)
-        bool ok = build_fast_table(S, KIND_LENS, S.lens, hlit, S.lit, LIT_ROOT, LIT_SUB, S.ml, reinterpret_cast<uint32_t *>(S.sym), tid);
-        ok = ok && build_fast_table(S, KIND_DISTS, S.lens + hlit, hdist, S.dist, DIST_ROOT, DIST_SUB, S.md, reinterpret_cast<uint32_t *>(S.sym), tid);
+        const bool ok = build_fast_tables(S, S.lens, hlit, S.lens + hlit, hdist, reinterpret_cast<uint32_t *>(S.sym), tid);
         if (!ok) {
           __syncthreads();
           if (tid == 0) S.next = NEXT_RETRY;
