@@ -50,7 +50,7 @@ struct DfChunk {       // built on the host by engine.cu
   int32_t len;         // 0..DF_CHUNK
   int32_t stream;      // owning stream
   int32_t flags;       // bit0: last chunk of its stream
-  int32_t pad;
+  int32_t hist;        // bytes of the same stream in front of the chunk (at most 32768): the decoder's window reaches them
 };
 struct DfChunkOut {
   uint32_t bytes;      // compressed bytes in the chunk's slot
@@ -283,7 +283,7 @@ __device__ void df_adler_partials(const uint8_t *p, int n, int lane, uint32_t *s
 
 // ---- one chunk ----------------------------------------------------------------------------------
 template <class SM>
-__device__ void df_compress_chunk(SM &S, const uint8_t *d, int len, bool last, int level, uint32_t *tok,
+__device__ void df_compress_chunk(SM &S, const uint8_t *d, int len, int hist, bool last, int level, uint32_t *tok,
                                   uint8_t *slot, DfChunkOut *res, bool want_adler, int lane) {
   uint32_t sum_a = 0, sum_b = 0;
   if (want_adler) df_adler_partials(d, len, lane, &sum_a, &sum_b);
@@ -297,6 +297,26 @@ __device__ void df_compress_chunk(SM &S, const uint8_t *d, int len, bool last, i
     if (lane < 32) S.freq_d[lane] = 0;
     if (lane == 0) S.extra_bits = 0;
     __syncwarp();
+    // Positions live in the table as 16 bits (p mod 65536): a candidate is the nearest earlier position with those low
+    // bits (an alias 64 KiB further back is beyond the window anyway; a wrong one fails the byte comparison).
+    auto pos_of = [](int p_cur, uint32_t c16) { return p_cur - (int)(((uint32_t)p_cur - c16) & 0xffffu); };
+    // The best levels first enter the `hist` bytes in front of the chunk into the table (no tokens): chunks are
+    // encoded independently, but the decoder's 32 KiB window does not know that.
+    for (int base = -((hist + 31) & ~31); base < 0; base += 32) {
+      const int p = base + lane;
+      uint32_t h = 0xffffffffu;
+      if (p >= -hist) {
+        const uint32_t v = (uint32_t)d[p] | ((uint32_t)d[p + 1] << 8) | ((uint32_t)d[p + 2] << 16) | ((uint32_t)d[p + 3] << 24);
+        h = (v * 0x9e3779b1u) >> (32 - SM::HASH_BITS);
+      }
+      const uint32_t same = __match_any_sync(0xffffffffu, h);
+      if (h != 0xffffffffu && (same >> lane) == 1u) {
+        const uint32_t lower = same & ((1u << lane) - 1u);
+        const uint32_t prev = lower ? (uint32_t)(base + (31 - __clz((int)lower))) : (S.head[h] & 0xffffu);
+        S.head[h] = ((prev & 0xffffu) << 16) | ((uint32_t)p & 0xffffu);
+      }
+      __syncwarp();
+    }
     int carry = 0; // first position of the step not covered by the previous token (may be >= 32)
     uint32_t my_extra = 0;
     for (int base = 0; base < len; base += 32) {
@@ -318,20 +338,20 @@ __device__ void df_compress_chunk(SM &S, const uint8_t *d, int len, bool last, i
           const int l0 = 31 - __clz((int)lower);
           cand0 = base + l0;
           const uint32_t lower2 = lower & ~(1u << l0);
-          cand1 = lower2 ? base + (31 - __clz((int)lower2)) : (int)(hd & 0xffffu);
+          cand1 = lower2 ? base + (31 - __clz((int)lower2)) : pos_of(p, hd & 0xffffu);
         } else {
-          cand0 = (int)(hd & 0xffffu);
-          cand1 = (int)(hd >> 16);
+          cand0 = pos_of(p, hd & 0xffffu);
+          cand1 = pos_of(p, hd >> 16);
         }
       }
       __syncwarp();
       if (h != 0xffffffffu && (same >> lane) == 1u) { // the last lane of a group records the group's two newest positions
         const uint32_t lower = same & ((1u << lane) - 1u);
         const uint32_t prev = lower ? (uint32_t)(base + (31 - __clz((int)lower))) : (S.head[h] & 0xffffu);
-        S.head[h] = (prev << 16) | (uint32_t)p;
+        S.head[h] = ((prev & 0xffffu) << 16) | ((uint32_t)p & 0xffffu);
       }
-      if (cand0 >= 0 && cand0 < p && p - cand0 <= 32768) {
-        const bool two = level >= 2 && cand1 >= 0 && cand1 < cand0 && p - cand1 <= 32768;
+      if (cand0 >= -hist && cand0 < p && p - cand0 <= 32768) {
+        const bool two = level >= 2 && cand1 >= -hist && cand1 < cand0 && p - cand1 <= 32768;
         int l, dist = p - cand0;
         if (maxlen >= 8 && len - p >= 16) {
           // the first eight bytes of both candidates in one round trip: most matches end there
@@ -553,7 +573,7 @@ deflate_chunk_kernel(int level, int want_adler, int64_t nchunks, const uint8_t *
     c = __shfl_sync(0xffffffffu, c, 0);
     if (c >= (unsigned long long)nchunks) break;
     const DfChunk ch = chunks[c];
-    df_compress_chunk(S, src_base + ch.src_off, ch.len, (ch.flags & 1) != 0, level, tok, slots + (size_t)c * DF_SLOT,
+    df_compress_chunk(S, src_base + ch.src_off, ch.len, HB == DF_HASH_BITS_BEST ? ch.hist : 0, (ch.flags & 1) != 0, level, tok, slots + (size_t)c * DF_SLOT,
                       &outs[c], want_adler != 0, lane);
     __syncwarp();
   }

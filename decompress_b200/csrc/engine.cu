@@ -41,7 +41,7 @@ size_t deflate_tok_bytes_per_cta();
 int deflate_ctas_per_sm();
 size_t deflate_slot_bytes();
 int deflate_chunk_size();
-struct DfChunkHost { int64_t src_off; int32_t len; int32_t stream; int32_t flags; int32_t pad; }; // = deflate.cu's DfChunk
+struct DfChunkHost { int64_t src_off; int32_t len; int32_t stream; int32_t flags; int32_t hist; }; // = deflate.cu's DfChunk
 constexpr int INTERNAL_RETRY = 0x7f; // inflate_parallel.cu: "this stream is for the general kernel"
 }
 
@@ -470,7 +470,7 @@ int dcmp_deflate_batch_device(dcmp_engine *e, int level, int fmt, int64_t n, con
     int64_t pos = 0;
     do {
       int64_t m = std::min<int64_t>(CH, h_src_len[k] - pos);
-      dcmp::DfChunkHost c{h_src_off[k] + pos, (int32_t)m, (int32_t)k, (pos + m == h_src_len[k]) ? 1 : 0, 0};
+      dcmp::DfChunkHost c{h_src_off[k] + pos, (int32_t)m, (int32_t)k, (pos + m == h_src_len[k]) ? 1 : 0, (int32_t)std::min<int64_t>(pos, 32768)};
       chunks.push_back(c);
       pos += m;
     } while (pos < h_src_len[k]);

@@ -72,7 +72,7 @@ int emu_deflate_batch(int level, int fmt, int64_t n, const uint8_t *src, const i
     int64_t pos = 0;
     do {
       int64_t m = std::min<int64_t>(DF_CHUNK, slen[k] - pos);
-      chunks.push_back(DfChunk{soff[k] + pos, (int32_t)m, (int32_t)k, (pos + m == slen[k]) ? 1 : 0, 0});
+      chunks.push_back(DfChunk{soff[k] + pos, (int32_t)m, (int32_t)k, (pos + m == slen[k]) ? 1 : 0, (int32_t)std::min<int64_t>(pos, 32768)});
       pos += m;
     } while (pos < slen[k]);
   }
