@@ -232,6 +232,7 @@ struct ParSmem {
   uint32_t adler_a, adler_b;
   uint32_t mbar_phase;
   int abort_round;               // a lane met an invalid distance: the general kernel reports it
+  int any_cross;                 // a head of this round crossed into another lane's sub-chunk
   volatile uint32_t a_done[NWARP]; // round number up to which a warp has finished phase A (its lanes' exits and checkpoints are in place)
   int hdr_ready;                 // the first header of this stream was parsed ahead (S.pf)
   int nh_ready;                  // the header of the stream's NEXT block was parsed during phases D/E: lens, nh_*
@@ -847,7 +848,7 @@ inflate_parallel_kernel(int fmt, int64_t nstreams, const uint8_t *src_base, cons
       // lanes whose sub-chunk starts beyond the input decode nothing
       const bool lane_has_input = base_bit + (int64_t)SUB_BITS * tid < 8 * S.src_len;
       round_no++;
-      if (tid == 0) { S.first_bad = PT; S.first_term = PT; S.abort_round = 0; S.pass_owner = -1; } // (read after the barrier that ends phase B)
+      if (tid == 0) { S.first_bad = PT; S.first_term = PT; S.abort_round = 0; S.pass_owner = -1; S.any_cross = 0; } // (read after the barrier that ends phase B)
       // ---- A: speculative decode of the own sub-chunk from bit 0
       int ns = 0;
       uint32_t out_s = 0;
@@ -973,11 +974,12 @@ inflate_parallel_kernel(int fmt, int64_t nstreams, const uint8_t *src_base, cons
         if (last > PT - 1) last = PT - 1;  // (H_PASS)
         M.jump[0][tid] = (uint16_t)(last + 1);
         M.mark[tid] = tid == 0 ? 1 : 0;
+        if (ncross) S.any_cross = 1;
       }
       __syncthreads();
       // ---- C: find the lanes whose head counts (the orbit of lane 0 under `jump`, by pointer doubling),
       // describe every lane's part, cut the round at the first lane that ends it, scan output sizes
-      {
+      if (S.any_cross) { // (with the warm-up a head rarely leaves its sub-chunk: most rounds have every lane in the orbit)
         int cur = 0;
 #pragma unroll 1
         for (int span = 1; span < PT; span <<= 1) {
@@ -992,7 +994,7 @@ inflate_parallel_kernel(int fmt, int64_t nstreams, const uint8_t *src_base, cons
           __syncthreads();
         }
       }
-      const bool owner = M.mark[tid] != 0;
+      const bool owner = !S.any_cross || M.mark[tid] != 0;
       {
         const uint32_t ow = __ballot_sync(0xffffffffu, owner);
         if (lane == 0) S.m_owner[warp] = ow;
