@@ -52,6 +52,9 @@
 
 namespace dcmp {
 
+#ifndef DCMP_PHASE_A_INLINE
+#define DCMP_PHASE_A_INLINE __noinline__
+#endif
 #ifndef DCMP_PT
 #define DCMP_PT 256
 #endif
@@ -65,7 +68,7 @@ constexpr int SUB_WORDS = DCMP_SUB_WORDS; // sub-chunk size in 32-bit words (odd
 constexpr int SUB_BITS = 32 * SUB_WORDS;
 constexpr int SPEC_CAP = ((SUB_BITS / 3) + 3) & ~3; // tokens a lane may produce speculatively (< 256: checkpoint field)
 constexpr int HEAD_CAP = 96;              // tokens a lane may produce while re-synchronising (p99 of the distance is ~55 on text)
-constexpr int TOK_SLOTS = SPEC_CAP + HEAD_CAP; // per lane, in the global scratch
+constexpr int TOK_SLOTS = SPEC_CAP + HEAD_CAP; // per lane, in the global scratch (64-bit tokens)
 constexpr int LANE_BYTE_CAP = 4096;       // bytes a lane may produce per pass (checkpoint field: 19 bits)
 #ifndef DCMP_WARMUP_BITS
 #define DCMP_WARMUP_BITS 384
@@ -85,32 +88,37 @@ constexpr int RSYM = DCMP_RSYM_K * 1024;  // symbols one round may produce (+ up
 constexpr int SYM_SLOTS = RSYM + 32;
 constexpr int WIN_WORDS = 3 + SUB_WORDS * PT + 4;        // staged input per round
 constexpr int WIN_BYTES = (WIN_WORDS * 4 + 15) & ~15;
-constexpr int HDR_BYTES = 1024 + 16;      // staged input for a block header
+constexpr int HDR_BYTES = 624 + 16;       // staged input for a block header (the longest one: 14 + 19*3 + 316*14 bits = 562 bytes)
 constexpr int LIT_ROOT = 10;
 constexpr int DIST_ROOT = 9;
-constexpr int LIT_SUB = 512;              // second-level entries (codes longer than the root); a code set that needs
-constexpr int DIST_SUB = 128;             // more goes to the general kernel
+constexpr int LIT_SUB = 320;              // second-level entries (codes longer than the root; zlib's `enough 286 10 15` = 1332 = 1024 + 308);
+constexpr int DIST_SUB = 128;             // a code set that needs more goes to the general kernel
+constexpr int LIT_N = (1 << LIT_ROOT) + LIT_SUB, DIST_N = (1 << DIST_ROOT) + DIST_SUB;
+constexpr uint32_t DIST_OFF = LIT_N;      // both tables live in one array: the distance table starts here
 // Decode-table entry of this kernel: one shared-memory load per code, fields placed for the hot loop.
-//  [4:0]   bits to drop: code length + extra bits     [8:5]  code length (LINK: index bits of the sub-table)
-//  [12:9]  number of extra bits                         [27:13] base: literal byte | match length base (3..258) |
-//                                                               distance base (1..24577) | LINK: sub-table offset
-//  [28] LINK  [29] EOB  [30] match length  [31] rare: EOB, LINK or an unassigned slot — one sign test takes all
-//  three off the hot path
-constexpr uint32_t PE_RARE = 1u << 31, PE_LEN = 1u << 30, PE_EOB = 1u << 29, PE_LINK = 1u << 28;
+//  [4:0]   bits to drop: code length + extra bits     [5]  LEN: a match length — the next code is a distance
+//  [11:8]  code length (LINK: index bits of the sub-table)
+//  [30:16] base: literal byte | match length base (3..258) | distance base (1..24577) | LINK: index of the sub-table
+//  [31] rare: EOB [6], LINK [7] or an unassigned slot — one sign test takes all three off the hot path
+constexpr uint32_t PE_RARE = 1u << 31, PE_LEN = 1u << 5, PE_EOB = 1u << 6, PE_LINK = 1u << 7;
 constexpr uint32_t PE_INVALID = PE_RARE;
 __host__ __device__ constexpr uint32_t pe_make(uint32_t base, uint32_t extra, uint32_t len) {
-  return (base << 13) | (extra << 9) | (len << 5) | (len + extra);
+  return (base << 16) | (len << 8) | (len + extra);
 }
 constexpr int DCMP_INTERNAL_RETRY = 0x7f; // never leaves the library
 static_assert(SUB_WORDS % 2 == 1, "odd lane stride keeps the window reads conflict-free");
 static_assert(PT % 64 == 0 && PT <= 1024, "the two halves of the CTA build one decode table each");
 static_assert(SPEC_CAP < 256 && LANE_BYTE_CAP + 258 < (1 << 19), "checkpoint fields");
-static_assert(SPEC_CAP % 4 == 0 && HEAD_CAP % 4 == 0, "token slots are moved in batches of four");
+static_assert(SPEC_CAP % 2 == 0 && HEAD_CAP % 2 == 0, "token slots are written in pairs");
+static_assert(PT * TOK_SLOTS <= 65536, "phase D addresses a CTA's token slots with 16 bits");
+
+constexpr int SEG_BIAS = 8192;            // phase D: a segment's symbol base may be negative by up to LANE_BYTE_CAP
 constexpr int MAX_CROSS = 6;              // sub-chunk boundaries one head decode may cross
 // Per-round metadata that is dead before phase D writes symbols; it overlays the symbol buffer.
 struct LaneDesc {          // what a lane replays in phase D, written by the lane that owns the head
   uint16_t owner;          // lane whose head slots hold the tokens
   uint8_t h0, h1;          // head tokens [h0, h1)
+  uint16_t head_o0;        // bytes the head had produced before token h0
   uint16_t out_head;       // bytes they produce
   uint8_t spec_k;          // speculative tokens from spec_k on (if has_spec)
   uint8_t flags;           // bit0 has_spec, bit1 terminal here (head ended: kind in bits 4..6)
@@ -142,12 +150,14 @@ static EmuStats g_stats;
 #endif
 } // namespace dcmp
 #include "symbol_drain.cuh"
+#if !DCMP_HIST_GLOBAL
+#error "inflate_parallel.cu reads the history from the output buffer (DCMP_HIST_GLOBAL=1)"
+#endif
 namespace dcmp {
 
 enum : int { X_NORMAL = 0, X_EOB = 1, X_CAP = 2, X_ERR = 3, X_NOSYNC = 4 };
 enum : int { NEXT_CONTINUE = 0, NEXT_HEADER = 1, NEXT_FINISH = 2, NEXT_RETRY = 3, NEXT_STORED = 4 };
 
-// token: [23] match flag; match: [22:8] distance-1, [7:0] length-3;  literal: [7:0] byte
 // checkpoint: [4:0] low bits of the position of the first token start inside the window,
 //             [12:5] index of that token, [30:13] bytes emitted before it, [31] none
 __device__ __forceinline__ bool tok_is_match(uint32_t t) { return (t >> 23) & 1u; }
@@ -161,18 +171,13 @@ __device__ __forceinline__ void st_sym_if(bool pred, uint16_t *addr, uint32_t v)
                : "memory");
 #endif
 }
-// A batch is filled as a shift register (newest token in .w): three moves per token, no indexing.
-__device__ __forceinline__ void batch_push(uint4 &b, uint32_t t) { b.x = b.y; b.y = b.z; b.z = b.w; b.w = t; }
-// bring the last r (1..3) tokens of a partial batch to the front
-__device__ __forceinline__ void batch_front(uint4 &b, int r) {
-  if (r == 1) b.x = b.w;
-  if (r == 2) { b.x = b.z; b.y = b.w; }
-  if (r == 3) { b.x = b.y; b.y = b.z; b.z = b.w; }
-}
-__device__ __forceinline__ uint32_t batch_get(const uint4 &b, int k) {
-  uint32_t lo = (k & 1) ? b.y : b.x, hi = (k & 1) ? b.w : b.z;
-  return (k & 2) ? hi : lo;
-}
+// A token leaves for the scratch as soon as it is decoded (one 64-bit store: nothing to carry from step to step).
+struct TokWriter {
+  __device__ __forceinline__ void push(uint4 *lane_slots, int n, uint32_t tok, uint32_t off) {
+    reinterpret_cast<uint2 *>(lane_slots)[n] = make_uint2(tok, off);
+  }
+  __device__ __forceinline__ void finish(uint4 *, int) {}
+};
 
 struct HuffMeta {      // canonical-code description of one alphabet
   uint16_t first[16];  // first code (MSB-first) of each length
@@ -199,17 +204,23 @@ struct ParSmem {
   __align__(16) uint8_t ring[HIST];        // last 32 KiB of output, indexed by (global address & HIST_MASK)
 #endif
   __align__(16) uint32_t win[WIN_BYTES / 4 + 4]; // staged compressed input (TMA destination)
-  uint32_t lit[(1 << LIT_ROOT) + LIT_SUB];   // root table, then the sub-tables of codes longer than the root
-  uint32_t dist[(1 << DIST_ROOT) + DIST_SUB];
+  uint32_t tbl[LIT_N + DIST_N];  // literal/length table (root, then the sub-tables of codes longer than the root), distance table
   uint8_t lens[MAX_LENS];
   HuffMeta ml, md;
   uint32_t run_cnt[2][16];       // per table under construction (literal/length, distance)
-  // per-lane results of a round
-  uint16_t exit_pos[PT];         // spec pass: bit offset (own sub-chunk coordinates) after the last token
-  uint8_t exit_kind[PT];
-  int8_t last_ck[PT];            // spec pass: last checkpoint window written
-  uint8_t spec_ns[PT];           // spec pass: tokens produced
-  uint16_t spec_out[PT];         // spec pass: bytes produced
+  union {
+    struct {                       // per-lane results of phase A, read by phase B
+      uint16_t exit_pos[PT];       // spec pass: bit offset (own sub-chunk coordinates) after the last token
+      uint8_t exit_kind[PT];
+      int8_t last_ck[PT];          // spec pass: last checkpoint window written
+      uint8_t spec_ns[PT];         // spec pass: tokens produced
+      uint16_t spec_out[PT];       // spec pass: bytes produced
+    };
+    struct {                       // phase D: the token lists of a warp's lanes, concatenated
+      uint16_t seg_pre[NWARP][34]; // [l]: tokens of the lanes before l; [32]: all
+      uint32_t seg_info[NWARP][32];// [15:0] first token (slot index in the CTA's scratch), [31:16] symbol index of offset 0, + SEG_BIAS
+    };
+  };
   uint32_t m_owner[NWARP];       // lanes whose own head decode counts (not covered by an earlier lane's head)
   int pass_owner;                // lane whose head ran past the end of the window (-1: none)
   int pass_pos;                  // its exit (own sub-chunk coordinates)
@@ -250,71 +261,65 @@ struct ParSmem {
 static_assert(sizeof(ParSmem) + 128 + 1024 <= 227 * 1024 / DCMP_CTAS_PER_SM, "shared memory per CTA for the intended residency");
 
 // ------------------------------------------------------------------------------------------
-// bit cursor over a lane's sub-chunk inside the staged window
-struct LaneBits {
-  uint64_t hold;
-  int nbits;            // valid bits in hold
-  const uint32_t *wp;   // next word to load
-  int p;                // bits consumed, in the lane's sub-chunk coordinates
-  __device__ __forceinline__ void init(const uint32_t *lane_words, int sh, int p0) {
-    const int b = p0 + sh; // sh: bit offset of the sub-chunk inside its first word
-    wp = lane_words + (b >> 5);
-    const int skip = b & 31;
-    hold = (uint64_t)(*wp++ >> skip);
-    nbits = 32 - skip;
-    p = p0;
-  }
-  __device__ __forceinline__ void refill() { // at least 32 valid bits afterwards
-    if (nbits < 32) {
-      hold |= (uint64_t)(*wp++) << nbits; // the window is padded: wp never leaves it
-      nbits += 32;
-    }
-  }
-  __device__ __forceinline__ int pos() const { return p; }
-  __device__ __forceinline__ void drop(uint32_t k) { hold >>= k; nbits -= (int)k; p += (int)k; }
+// The decoder of phases A and B.  One STEP = one table lookup: a literal/length code or — when the step before
+// met a match length — a distance code.  Every step runs the same instructions whichever of the two it is, so the
+// lanes of a warp stay converged (a literal takes one step, a match two; both cover 8..10 bits of input on text),
+// where a decoder that finishes a whole token per iteration runs the literal and the match path one after the
+// other.  The bit cursor is a bit index into the staged window: the next 32 bits are two shared-memory words and
+// a funnel shift (no 64-bit hold register, no refill branch).
+struct Cursor {
+  int q;            // bit index into S.win of the next code
+  uint32_t tb;      // 0: the next code is a literal/length code; DIST_OFF: a distance code
+  uint32_t mask;    // root-table index mask of that table
+  uint32_t pend;    // match length waiting for its distance (tb != 0)
+  __device__ __forceinline__ void start(int q0, uint32_t lmask) { q = q0; tb = 0; mask = lmask; pend = 0; }
+  __device__ __forceinline__ bool at_token() const { return tb == 0; }
 };
-
-enum : int { T_TOKEN = 0, T_EOB = 1, T_ERR = 2 };
-
-// Decode one literal / match at the cursor.  *tok gets the token, *nout its byte count.
-__device__ __forceinline__ uint32_t pe_value(uint32_t e, uint32_t lo) { // base + extra bits
-  return ((e >> 13) & 0x7fffu) + ((lo >> ((e >> 5) & 15u)) & ~(~0u << ((e >> 9) & 15u)));
+enum : int { STEP_NONE = 0, STEP_TOKEN = 1, STEP_EOB = 2, STEP_ERR = 3 };
+// a select the compiler does not turn into shifts and masks
+__device__ __forceinline__ uint32_t sel_u32(uint32_t nz, uint32_t a, uint32_t b) { // nz != 0 ? a : b
+#ifdef DCMP_EMU
+  return nz ? a : b;
+#else
+  uint32_t r;
+  asm("{\n .reg .pred p;\n setp.ne.u32 p, %1, 0;\n selp.u32 %0, %2, %3, p;\n}\n" : "=r"(r) : "r"(nz), "r"(a), "r"(b));
+  return r;
+#endif
 }
-__device__ __forceinline__ int decode_token(ParSmem &S, LaneBits &lb, uint32_t lmask, uint32_t dmask, int lroot, int droot,
-                                            uint32_t *tok, uint32_t *nout) {
-  lb.refill();
-  uint32_t lo = (uint32_t)lb.hold;
-  uint32_t e = S.lit[lo & lmask];
+
+// token (64 bits in the scratch): .x = [23] match flag; match: [22:8] distance-1, [7:0] length-3; literal: [7:0] byte
+//                                 .y = bytes the pass had produced before this token
+template <bool KEEP>
+__device__ __forceinline__ int dec_step(const uint32_t *__restrict__ tbl, const uint32_t *__restrict__ win, Cursor &c,
+                                        const uint32_t lmask, const uint32_t dmask, const int lroot, const int droot,
+                                        uint32_t &tok, uint32_t &nout) {
+  const uint32_t *wp = win + (c.q >> 5);
+  const uint32_t lo = __funnelshift_r(wp[0], wp[1], (uint32_t)c.q);
+  uint32_t e = tbl[c.tb + (lo & c.mask)];
   if ((int32_t)e < 0) { // rare: end of block, a code longer than the root table, an unassigned slot
-    if (e & PE_EOB) { lb.drop(e & 31u); return T_EOB; }
-    if (!(e & PE_LINK)) return T_ERR;
-    e = S.lit[((e >> 13) & 0x7fffu) + ((lo >> lroot) & ~(~0u << ((e >> 5) & 15u)))];
+    if (!(e & PE_LINK)) {
+      if (e & PE_EOB) { c.q += (int)(e & 31u); return STEP_EOB; }
+      return STEP_ERR;
+    }
+    e = tbl[(e >> 16 & 0x7fffu) + ((lo >> (c.tb ? droot : lroot)) & ~(~0u << ((e >> 8) & 15u)))];
     if ((int32_t)e < 0) {
-      if (e & PE_EOB) { lb.drop(e & 31u); return T_EOB; }
-      return T_ERR;
+      if (e & PE_EOB) { c.q += (int)(e & 31u); return STEP_EOB; }
+      return STEP_ERR;
     }
   }
-  if (!(e & PE_LEN)) {
-    lb.drop(e & 31u);
-    *tok = (e >> 13) & 0xffu;
-    *nout = 1;
-    return T_TOKEN;
+  c.q += (int)(e & 31u);
+  const uint32_t is_len = e & PE_LEN; // (never set in the distance table)
+  if (KEEP) {
+    // base + extra bits: the low [4:0] bits of lo, without the code ([12:8], bits 12 is clear: a wrapping shift takes
+    // the field as it is)
+    const uint32_t v = (e >> 16) + __funnelshift_r(lo & ~__funnelshift_l(0u, ~0u, e), 0u, e >> 8);
+    tok = c.tb ? ((1u << 23) | ((v - 1u) << 8) | (c.pend - 3u)) : v;
+    nout = c.tb ? c.pend : 1u;
+    c.pend = v;
   }
-  const uint32_t len = pe_value(e, lo);
-  lb.drop(e & 31u);
-  lb.refill();
-  lo = (uint32_t)lb.hold;
-  uint32_t d = S.dist[lo & dmask];
-  if ((int32_t)d < 0) { // longer than the root, or unassigned (empty / incomplete set, symbols 30/31: general kernel)
-    if (!(d & PE_LINK)) return T_ERR;
-    d = S.dist[((d >> 13) & 0x7fffu) + ((lo >> droot) & ~(~0u << ((d >> 5) & 15u)))];
-    if ((int32_t)d < 0) return T_ERR;
-  }
-  const uint32_t dd = pe_value(d, lo);
-  lb.drop(d & 31u);
-  *tok = (1u << 23) | ((dd - 1u) << 8) | (len - 3u);
-  *nout = len;
-  return T_TOKEN;
+  c.tb = sel_u32(is_len, DIST_OFF, 0u);
+  c.mask = sel_u32(is_len, dmask, lmask);
+  return is_len ? STEP_NONE : STEP_TOKEN;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -344,7 +349,7 @@ __device__ bool build_fast_tables(ParSmem &S, const uint8_t *lens_l, int n_l, co
   const int kind = half ? KIND_DISTS : KIND_LENS;
   const uint8_t *lens = half ? lens_d : lens_l;
   const int n = half ? n_d : n_l;
-  uint32_t *tbl = half ? S.dist : S.lit;
+  uint32_t *tbl = S.tbl + (half ? DIST_OFF : 0u);
   const int root_max = half ? DIST_ROOT : LIT_ROOT, sub_cap = half ? DIST_SUB : LIT_SUB;
   HuffMeta &m = half ? S.md : S.ml;
   uint32_t *scratch = scratch_all + half * ((1 << LIT_ROOT) + MAX_LENS); // (1 << root_max) + n words per table
@@ -421,7 +426,7 @@ __device__ bool build_fast_tables(ParSmem &S, const uint8_t *lens_l, int n_l, co
       if (off + (1u << bits) > (uint32_t)sub_cap) S.tbl_ok2[half] = 0;
       else {
         const uint32_t at = (1u << root) + off;
-        tbl[i] = PE_RARE | PE_LINK | (at << 13) | (bits << 5);
+        tbl[i] = PE_RARE | PE_LINK | ((at + (half ? DIST_OFF : 0u)) << 16) | (bits << 8);
         scratch[i] = at | (bits << 16);
         for (uint32_t j = 0; j < (1u << bits); j++) tbl[at + j] = PE_INVALID;
       }
@@ -657,6 +662,63 @@ __device__ void prefetch_next_stream(ParSmem &S, int fmt, int64_t nstreams, cons
 }
 
 // ------------------------------------------------------------------------------------------
+// Phase A of a round, one lane: speculative decode of the lane's own sub-chunk.  Results: the tokens (scratch), a
+// checkpoint per CKPT window, and exit position / kind, last checkpoint window, token and byte counts in S.
+__device__ DCMP_PHASE_A_INLINE void phase_a_lane(ParSmem &S, uint32_t (*ckpt)[PT], uint4 *tok_spec, const int q0, const int tid,
+                                          const bool lane_has_input) {
+  const int lroot = S.ml.root, droot = S.md.root;
+  const uint32_t lmask = (1u << lroot) - 1u, dmask = (1u << droot) - 1u;
+  int ns = 0;
+  uint32_t out_s = 0;
+  int xkind = X_ERR, xpos = 0;
+  int last_ck = -1;
+  if (lane_has_input) {
+#pragma unroll
+    for (int c = 0; c < NCKPT; c++) ckpt[c][tid] = CKPT_NONE; // (the buffer held symbols, or an older round's checkpoints)
+    Cursor cu;
+    uint32_t tok = 0, no = 0;
+    // Warm-up: the pass starts WARMUP_BITS before the sub-chunk and throws away what it decodes there, so that it
+    // has often found the true token boundaries by the time its own bits begin (lane 0 starts on one).
+    cu.start(q0 - imin(WARMUP_BITS, tid * SUB_BITS), lmask); // (never before lane 0's start, which is a token boundary)
+    while (cu.q < q0 || !cu.at_token()) {
+      if (dec_step<false>(S.tbl, S.win, cu, lmask, dmask, lroot, droot, tok, no) >= STEP_EOB) { cu.start(q0, lmask); break; }
+    }
+    TokWriter tw;
+    int tstart = 0;
+    for (;;) {
+      if (cu.at_token()) {
+        const int p = cu.q - q0;
+        tstart = p;
+        // one test for the three ways out: the sub-chunk is done, the token slots or the byte budget are used up
+        if (((SUB_BITS - 1 - p) | (SPEC_CAP - 1 - ns) | (LANE_BYTE_CAP - 258 - (int)out_s)) < 0) {
+          xkind = p >= SUB_BITS ? X_NORMAL : X_CAP;
+          xpos = p;
+          break;
+        }
+        const int ck = p >> CKPT_SHIFT;
+        if (ck != last_ck) {
+          ckpt[ck][tid] = (uint32_t)(p & 31) | ((uint32_t)ns << 5) | (out_s << 13);
+          last_ck = ck;
+        }
+      }
+      const int r = dec_step<true>(S.tbl, S.win, cu, lmask, dmask, lroot, droot, tok, no);
+      if (r == STEP_NONE) continue;
+      if (r == STEP_EOB) { xkind = X_EOB; xpos = cu.q - q0; break; }
+      if (r == STEP_ERR) { xkind = X_ERR; xpos = tstart; break; }
+      tw.push(tok_spec, ns, tok, out_s);
+      ns++;
+      out_s += no;
+    }
+    tw.finish(tok_spec, ns);
+  }
+  S.exit_pos[tid] = (uint16_t)xpos;
+  S.exit_kind[tid] = (uint8_t)xkind;
+  S.last_ck[tid] = (int8_t)last_ck;
+  S.spec_ns[tid] = (uint8_t)ns;
+  S.spec_out[tid] = (uint16_t)out_s;
+}
+
+// ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(PT, DCMP_CTAS_PER_SM)
 inflate_parallel_kernel(int fmt, int64_t nstreams, const uint8_t *src_base, const int64_t *src_off,
                         const int64_t *src_len, uint8_t *dst_base, const int64_t *dst_off, const int64_t *dst_cap,
@@ -836,61 +898,23 @@ inflate_parallel_kernel(int fmt, int64_t nstreams, const uint8_t *src_base, cons
         int64_t want = vend - v0;
         stage_window(S, g0, WIN_BYTES, (int)(want > WIN_BYTES ? WIN_BYTES : want), tid);
       }
-      const int sh = bit0 & 31;
-      const uint32_t *lane_words = S.win + (bit0 >> 5) + SUB_WORDS * tid;
+      const int q0 = bit0 + SUB_BITS * tid; // bit index of this lane's sub-chunk in the staged window
       const int lroot = S.ml.root, droot = S.md.root;
       const uint32_t lmask = (1u << lroot) - 1u, dmask = (1u << droot) - 1u;
       // this lane's token slots in the L2-resident scratch: [HEAD_CAP head tokens | SPEC_CAP speculative tokens],
-      // written and read back as 128-bit batches of four
-      uint4 *tok_lane = reinterpret_cast<uint4 *>(tok_scratch + ((size_t)blockIdx.x * PT + tid) * TOK_SLOTS);
+      // 64-bit tokens written in pairs
+      uint4 *tok_lane = reinterpret_cast<uint4 *>(tok_scratch + ((size_t)blockIdx.x * PT + tid) * (TOK_SLOTS * 2));
       uint4 *tok_head = tok_lane;
-      uint4 *tok_spec = tok_lane + HEAD_CAP / 4;
+      uint4 *tok_spec = tok_lane + HEAD_CAP / 2;
       // lanes whose sub-chunk starts beyond the input decode nothing
       const bool lane_has_input = base_bit + (int64_t)SUB_BITS * tid < 8 * S.src_len;
       round_no++;
       if (tid == 0) { S.first_bad = PT; S.first_term = PT; S.abort_round = 0; S.pass_owner = -1; S.any_cross = 0; } // (read after the barrier that ends phase B)
-      // ---- A: speculative decode of the own sub-chunk from bit 0
-      int ns = 0;
-      uint32_t out_s = 0;
-      int xkind = X_ERR, xpos = 0;
-      int last_ck = -1;
-      if (lane_has_input) {
-#pragma unroll
-        for (int c = 0; c < NCKPT; c++) ckpt[c][tid] = CKPT_NONE; // (the buffer held symbols, or an older round's checkpoints)
-        LaneBits lb;
-        // Warm-up: the pass starts WARMUP_BITS before the sub-chunk and throws away what it decodes there, so that it
-        // has often found the true token boundaries by the time its own bits begin (lane 0 starts on one).
-        lb.init(lane_words, sh, -imin(WARMUP_BITS, tid * SUB_BITS)); // (never before lane 0's start, which is a token boundary)
-        while (lb.pos() < 0) {
-          uint32_t tok, no;
-          if (decode_token(S, lb, lmask, dmask, lroot, droot, &tok, &no) != T_TOKEN) { lb.init(lane_words, sh, 0); break; }
-        }
-        uint4 tbuf = make_uint4(0, 0, 0, 0);
-        for (;;) {
-          int p = lb.pos();
-          if (p >= SUB_BITS) { xkind = X_NORMAL; xpos = p; break; }
-          if (ns == SPEC_CAP || out_s > (uint32_t)(LANE_BYTE_CAP - 258)) { xkind = X_CAP; xpos = p; break; }
-          int ck = p >> CKPT_SHIFT;
-          if (ck != last_ck) {
-            ckpt[ck][tid] = (uint32_t)(p & 31) | ((uint32_t)ns << 5) | (out_s << 13);
-            last_ck = ck;
-          }
-          uint32_t tok, no;
-          int r = decode_token(S, lb, lmask, dmask, lroot, droot, &tok, &no);
-          if (r == T_EOB) { xkind = X_EOB; xpos = lb.pos(); break; }
-          if (r == T_ERR) { xkind = X_ERR; xpos = p; break; }
-          batch_push(tbuf, tok);
-          if ((ns & 3) == 3) tok_spec[ns >> 2] = tbuf;
-          ns++;
-          out_s += no;
-        }
-        if (ns & 3) { batch_front(tbuf, ns & 3); tok_spec[ns >> 2] = tbuf; }
-      }
-      S.exit_pos[tid] = (uint16_t)xpos;
-      S.exit_kind[tid] = (uint8_t)xkind;
-      S.last_ck[tid] = (int8_t)last_ck;
-      S.spec_ns[tid] = (uint8_t)ns;
-      S.spec_out[tid] = (uint16_t)out_s;
+      // ---- A: speculative decode of the own sub-chunk from bit 0 (a function of its own: the hot loop gets the
+      // whole register budget, not what the rest of the kernel leaves it)
+      phase_a_lane(S, ckpt, tok_spec, q0, tid, lane_has_input);
+      const int ns = S.spec_ns[tid], xkind = S.exit_kind[tid], xpos = S.exit_pos[tid], last_ck = S.last_ck[tid];
+      const uint32_t out_s = S.spec_out[tid];
       // No CTA-wide barrier between A and B: a head needs the exit of the lane before it and the checkpoints of the
       // lanes it runs through, so a warp waits for the warp before it only (and, in the rare case that one of its
       // heads crosses into a later warp's sub-chunks, for that warp).  Phase A never waits: no cycle.
@@ -918,49 +942,52 @@ inflate_parallel_kernel(int fmt, int64_t nstreams, const uint8_t *src_base, cons
           if (tid == 0 && ns > 0) {
             hcat = H_MERGE; // lane 0's speculative pass started at the true position
           } else {
-            LaneBits lb;
-            lb.init(lane_words, sh, entry);
-            uint4 tbuf = make_uint4(0, 0, 0, 0);
-            int u = tid, ubase = 0, lck = last_ck, seen_ck = -1, xk_u = xkind, xp_u = xpos;
+            Cursor cu;
+            cu.start(q0 + entry, lmask);
+            TokWriter tw;
+            uint32_t tok = 0, no = 0;
+            int u = tid, ubase = 0, lck = last_ck, seen_ck = -1, xk_u = xkind, xp_u = xpos, tstart = entry;
             for (;;) {
-              const int p = lb.pos();
-              if (p - ubase >= SUB_BITS) { // crossed into the next sub-chunk (rare)
-                if (ncross == MAX_CROSS) { hcat = H_TERM; hkind = X_CAP; hpos = p; break; }
-                M.cross_nh[tid][ncross] = (uint16_t)nh;
-                M.cross_out[tid][ncross] = (uint16_t)out_h;
-                ncross++;
-                u++;
-                ubase += SUB_BITS;
-                seen_ck = -1;
-                if (u >= PT) { hcat = H_PASS; hpos = p; break; } // past the window: the next round starts here
-                if ((u >> 5) != warp) { while (S.a_done[u >> 5] != round_no) DCMP_SPIN(); __threadfence_block(); } // that warp's phase A
-                lck = S.last_ck[u];
-                xk_u = S.exit_kind[u];
-                xp_u = S.exit_pos[u];
-              }
-              const int pl = p - ubase;
-              const int ck = pl >> CKPT_SHIFT;
-              if (ck != seen_ck) {
-                seen_ck = ck;
-                if (ck <= lck) { // the speculative pass of lane u left a checkpoint for this window
-                  const uint32_t c = ckpt[ck][u];
-                  if ((c & (CKPT_NONE | 31u)) == (uint32_t)(pl & 31)) { mk = (int)((c >> 5) & 255u); mskip = c >> 13; hcat = H_MERGE; break; }
+              if (cu.at_token()) {
+                const int p = cu.q - q0;
+                tstart = p;
+                if (p - ubase >= SUB_BITS) { // crossed into the next sub-chunk (rare)
+                  if (ncross == MAX_CROSS) { hcat = H_TERM; hkind = X_CAP; hpos = p; break; }
+                  M.cross_nh[tid][ncross] = (uint16_t)nh;
+                  M.cross_out[tid][ncross] = (uint16_t)out_h;
+                  ncross++;
+                  u++;
+                  ubase += SUB_BITS;
+                  seen_ck = -1;
+                  if (u >= PT) { hcat = H_PASS; hpos = p; break; } // past the window: the next round starts here
+                  if ((u >> 5) != warp) { while (S.a_done[u >> 5] != round_no) DCMP_SPIN(); __threadfence_block(); } // that warp's phase A
+                  lck = S.last_ck[u];
+                  xk_u = S.exit_kind[u];
+                  xp_u = S.exit_pos[u];
                 }
+                const int pl = p - ubase;
+                const int ck = pl >> CKPT_SHIFT;
+                if (ck != seen_ck) {
+                  seen_ck = ck;
+                  if (ck <= lck) { // the speculative pass of lane u left a checkpoint for this window
+                    const uint32_t c = ckpt[ck][u];
+                    if ((c & (CKPT_NONE | 31u)) == (uint32_t)(pl & 31)) { mk = (int)((c >> 5) & 255u); mskip = c >> 13; hcat = H_MERGE; break; }
+                  }
+                }
+                if (xk_u == X_CAP && pl == xp_u) { // met that pass where its token buffer filled up
+                  mk = S.spec_ns[u]; mskip = S.spec_out[u]; hcat = H_MERGE; break;
+                }
+                if (nh == HEAD_CAP || out_h > (uint32_t)(LANE_BYTE_CAP - 258)) { hcat = H_TERM; hkind = X_CAP; hpos = p; break; }
               }
-              if (xk_u == X_CAP && pl == xp_u) { // met that pass where its token buffer filled up
-                mk = S.spec_ns[u]; mskip = S.spec_out[u]; hcat = H_MERGE; break;
-              }
-              if (nh == HEAD_CAP || out_h > (uint32_t)(LANE_BYTE_CAP - 258)) { hcat = H_TERM; hkind = X_CAP; hpos = p; break; }
-              uint32_t tok, no;
-              const int r = decode_token(S, lb, lmask, dmask, lroot, droot, &tok, &no);
-              if (r == T_EOB) { hcat = H_TERM; hkind = X_EOB; hpos = lb.pos(); break; }
-              if (r == T_ERR) { hcat = H_TERM; hkind = X_ERR; hpos = p; break; }
-              batch_push(tbuf, tok);
-              if ((nh & 3) == 3) tok_head[nh >> 2] = tbuf;
+              const int r = dec_step<true>(S.tbl, S.win, cu, lmask, dmask, lroot, droot, tok, no);
+              if (r == STEP_NONE) continue;
+              if (r == STEP_EOB) { hcat = H_TERM; hkind = X_EOB; hpos = cu.q - q0; break; }
+              if (r == STEP_ERR) { hcat = H_TERM; hkind = X_ERR; hpos = tstart; break; }
+              tw.push(tok_head, nh, tok, out_h);
               nh++;
               out_h += no;
             }
-            if (nh & 3) { batch_front(tbuf, nh & 3); tok_head[nh >> 2] = tbuf; }
+            tw.finish(tok_head, nh);
           }
         }
         STAT(if (hcat != H_BAD && tid > 0) { if (hcat == H_MERGE && ncross == 0) g_stats.hist_nh[nh < 47 ? nh : 47]++; else if (hcat != H_TERM) g_stats.nosync_lanes++; })
@@ -1010,6 +1037,7 @@ inflate_parallel_kernel(int fmt, int64_t nstreams, const uint8_t *src_base, cons
           d.h0 = (uint8_t)(j == 0 ? 0 : M.cross_nh[tid][j - 1]);
           d.h1 = (uint8_t)(j < ncross ? M.cross_nh[tid][j] : nh);
           const uint32_t o0 = j == 0 ? 0u : M.cross_out[tid][j - 1], o1 = j < ncross ? M.cross_out[tid][j] : out_h;
+          d.head_o0 = (uint16_t)o0;
           d.out_head = (uint16_t)(o1 - o0);
           d.spec_k = (uint8_t)mk;
           d.spec_skip = (uint16_t)mskip;
@@ -1024,6 +1052,7 @@ inflate_parallel_kernel(int fmt, int64_t nstreams, const uint8_t *src_base, cons
       // every lane's final contribution: head tokens [d_h0, d_h0 + d_nh) of lane d_owner, then (d_spec) its own
       // speculative tokens from d_k on
       int d_owner = tid, d_h0 = 0, d_nh = 0, d_k = 0, tkind = X_NORMAL;
+      uint32_t d_head_o0 = 0, d_out_head = 0, d_spec_skip = 0;
       int64_t t_next = 0; // where the stream continues if this lane closes the round
       bool d_spec = false, in_ok = true, term = false, clean = false;
       uint32_t out_valid = 0;
@@ -1034,6 +1063,9 @@ inflate_parallel_kernel(int fmt, int64_t nstreams, const uint8_t *src_base, cons
           d_owner = d.owner;
           d_h0 = d.h0;
           d_nh = (int)d.h1 - (int)d.h0;
+          d_head_o0 = d.head_o0;
+          d_out_head = d.out_head;
+          d_spec_skip = d.spec_skip;
           out_valid = d.out_head;
           if (d.flags & 1) { // the true sequence leaves this sub-chunk the way the speculative one does
             d_spec = true;
@@ -1151,124 +1183,151 @@ inflate_parallel_kernel(int fmt, int64_t nstreams, const uint8_t *src_base, cons
         S.sym[E + tid] = 0;
       }
       {
-        // Every lane walks its own token list: head tokens [0, nh), then the speculative tokens from
-        // the merge point on.  One step of the (warp-uniform) loop emits a literal or up to eight
-        // symbols of a match; the source of a match decides how:
-        //   inside this round (any lane, this one included): markers 256 + source index, no load at all
-        //   entirely in earlier rounds: bytes of the history ring
-        //   straddling the start of the round, or overlapping itself inside the group: per symbol
-        const int total_tok = in_slice ? d_nh + (d_spec ? ns - d_k : 0) : 0;
-        const int delta = HEAD_CAP + d_k - d_nh; // token index -> slot for the speculative part
-        STAT(if (in_slice) { g_stats.head_tokens += d_nh; g_stats.used_tokens += total_tok; } long iters = 0;)
-#if DCMP_HIST_GLOBAL
-        // history = the stream's own output in HBM/L2; symbol index s <-> address G0 + s.  L2-coherent loads
-        // (.cg): the bytes were stored by this CTA in earlier rounds, a barrier ago at least.
-        const uint32_t *hist32 = reinterpret_cast<const uint32_t *>(G0 - ((uintptr_t)G0 & 3)); // G0 is 16-aligned: no-op
-#else
-        const uint32_t *ring32 = reinterpret_cast<const uint32_t *>(S.ring);
-#endif
-        int ti = 0;
-        int32_t i = (int32_t)(my_start - s0 + bias); // next symbol to write
-        int32_t s = 0;                // next source symbol of the pending match
-        uint32_t rem = 0;             // symbols the pending match still owes
-        uint32_t dist = 0;
-        // tokens are fetched three ahead of their use (scalar L2 loads: the lists were written as 128-bit batches)
-        const uint32_t *head32 = tok_scratch + ((size_t)blockIdx.x * PT + d_owner) * TOK_SLOTS + d_h0;
-        const uint32_t *spec32 = tok_scratch + ((size_t)blockIdx.x * PT + tid) * TOK_SLOTS + delta;
-        auto tok_at = [&](int t) { return __ldcg((t < d_nh ? head32 : spec32) + t); };
-        uint32_t q0 = 0, q1 = 0, q2 = 0;
-        if (0 < total_tok) q0 = tok_at(0);
-        if (1 < total_tok) q1 = tok_at(1);
-        if (2 < total_tok) q2 = tok_at(2);
-        bool active = total_tok > 0;
-        while (__any_sync(0xffffffffu, active)) {
-          STAT(if (active) iters++;)
-          // -- next token, for the lanes that finished the previous one
-          bool fetch = active && rem == 0;
-          if (fetch && ti == total_tok) { active = false; fetch = false; }
-          uint32_t t = 0;
-          if (fetch) {
-            t = q0;
-            q0 = q1;
-            q1 = q2;
-            if (ti + 3 < total_tok) q2 = tok_at(ti + 3);
-            ti++;
-          }
-          const bool new_match = fetch && tok_is_match(t);
-          if (new_match) {
-            dist = ((t >> 8) & 0x7fffu) + 1u;
-            rem = (t & 0xffu) + 3u;
-            s = i - (int32_t)dist;
-            if (dist > slice_out0 + (uint32_t)(i - (int32_t)bias)) { // Invalid distance (de.ml:1700): the general kernel reports it
-              S.abort_round = 1;
-              active = false;
-              rem = 0;
-            }
-          }
-          // -- this step's symbols (branch-free for the three common cases)
-          const bool lit = fetch && !new_match;
-          const uint32_t n = lit ? 1u : (rem < 8u ? rem : 8u);  // 0 for idle lanes
+        // Token-parallel inside each warp: the token lists of the warp's 32 lanes are laid end to end and the
+        // threads take consecutive tokens, 32 per step — whatever the lengths of the lists, the warp needs
+        // ceil(total / 32) steps (replaying lane by lane it needed as many as its longest list had).  Two passes:
+        // the head parts, then the speculative parts.  A token carries the number of bytes its pass had produced
+        // before it, so its place in the symbol buffer is a per-list base plus that offset.  The source of a match
+        // decides how its symbols are made:
+        //   inside this slice (any lane's output): markers 256 + source index, no load at all
+        //   entirely in earlier rounds / slices: bytes of the stream's own output, read back through L2 (.cg loads:
+        //     they were stored by this CTA a barrier ago at least)
+        //   straddling the start of the slice, or overlapping itself inside a group of eight: per symbol
+        // A match longer than COOP_LEN symbols is spread over the lanes of the warp.
+        constexpr uint32_t COOP_LEN = 16;
+        const int32_t i0 = (int32_t)(my_start - s0 + bias); // symbol index of this lane's first byte
+        const uint2 *const tok_cta = reinterpret_cast<const uint2 *>(tok_scratch) + (size_t)blockIdx.x * PT * TOK_SLOTS;
+        const uint32_t *const hist32 = reinterpret_cast<const uint32_t *>(G0); // G0 is 16-byte aligned
+        STAT(if (in_slice) { g_stats.head_tokens += d_nh; g_stats.used_tokens += d_nh + (d_spec ? ns - d_k : 0); })
+        // up to eight symbols of a match: sym[i .. i+n) <- the bytes at symbol indices [s, s+n)
+        auto group8 = [&](const int32_t i, const int32_t s, const uint32_t n, const uint32_t dist) {
           const bool in_round = s >= (int32_t)bias;
           const bool in_hist = s + (int32_t)n <= (int32_t)bias;
-          const bool slow = rem > 0u && (in_round ? dist < n : !in_hist);
-          // markers: source inside this round (another lane's output or this lane's own)
-          const uint32_t m0 = (256u + (uint32_t)s) * 0x00010001u + 0x00010000u;
-          // history: source entirely in earlier rounds (addresses are masked: the loads are always legal)
-          const uint32_t r = g0_low + (uint32_t)s; // ring byte address (mod HIST) of the first source byte
-#if !DCMP_HIST_GLOBAL
-          const uint32_t wi0 = r >> 2;
-#endif
-          uint32_t w0 = 0, w1 = 0, w2 = 0;
-          if (in_hist && rem > 0u) {
-#if DCMP_HIST_GLOBAL
-            const int32_t gw = s >> 2; // word index relative to G0 (negative: before this round)
-            const uint32_t span = ((uint32_t)s & 3u) + n; // only words that hold a source byte are touched
-            w0 = __ldcg(hist32 + gw);
-            if (span > 4u) w1 = __ldcg(hist32 + gw + 1);
-            if (span > 8u) w2 = __ldcg(hist32 + gw + 2);
-#else
-            w0 = ring32[wi0 & (HIST / 4 - 1)];
-            w1 = ring32[(wi0 + 1u) & (HIST / 4 - 1)];
-            w2 = ring32[(wi0 + 2u) & (HIST / 4 - 1)];
-#endif
-          }
-          const uint32_t sh8 = 8u * (r & 3u);
-          const uint32_t ha = __funnelshift_r(w0, w1, sh8), hb = __funnelshift_r(w1, w2, sh8);
-          uint32_t p0 = in_round ? m0 : __byte_perm(ha, 0u, 0x4140);
-          const uint32_t p1 = in_round ? m0 + 0x00020002u : __byte_perm(ha, 0u, 0x4342);
-          const uint32_t p2 = in_round ? m0 + 0x00040004u : __byte_perm(hb, 0u, 0x4140);
-          const uint32_t p3 = in_round ? m0 + 0x00060006u : __byte_perm(hb, 0u, 0x4342);
-          if (lit) p0 = t & 0xffu;
-          STAT(if (!slow && rem > 0) { if (in_round) g_stats.markers += n; else g_stats.hist_bytes += n; })
-          if (slow) {
-            // straddles the start of the round, or overlaps itself inside the group (point at the first period)
+          if (in_round ? dist < n : !in_hist) {
             for (uint32_t k = 0; k < n; k++) {
-              const int32_t sk = s + (int32_t)(dist < n ? k % dist : k);
+              const int32_t sk = s + (int32_t)(dist < n ? k % dist : k); // (an overlapping copy points at its first period)
               uint32_t v;
               if (sk >= (int32_t)bias) { v = 256u + (uint32_t)sk; STAT(g_stats.markers++;) }
-#if DCMP_HIST_GLOBAL
               else { v = __ldcg(G0 + sk); STAT(g_stats.hist_bytes++;) }
-#else
-              else { v = S.ring[(g0_low + (uint32_t)sk) & HIST_MASK]; STAT(g_stats.hist_bytes++;) }
-#endif
               S.sym[i + (int32_t)k] = (uint16_t)v;
             }
-          } else {
-            // eight predicated stores (the compiler turns the plain `if`s into a cascade of eight divergent branches)
-            uint16_t *const at = S.sym + i;
-            st_sym_if(n > 0u, at + 0, p0);
-            st_sym_if(n > 1u, at + 1, p0 >> 16);
-            st_sym_if(n > 2u, at + 2, p1);
-            st_sym_if(n > 3u, at + 3, p1 >> 16);
-            st_sym_if(n > 4u, at + 4, p2);
-            st_sym_if(n > 5u, at + 5, p2 >> 16);
-            st_sym_if(n > 6u, at + 6, p3);
-            st_sym_if(n > 7u, at + 7, p3 >> 16);
+            return;
           }
-          i += (int32_t)n;
-          if (rem > 0u) { s += (int32_t)n; rem -= n; }
+          STAT(if (in_round) g_stats.markers += n; else g_stats.hist_bytes += n;)
+          uint32_t p0, p1, p2, p3;
+          if (in_round) {
+            p0 = (256u + (uint32_t)s) * 0x00010001u + 0x00010000u;
+            p1 = p0 + 0x00020002u;
+            p2 = p0 + 0x00040004u;
+            p3 = p0 + 0x00060006u;
+          } else {
+            const int32_t gw = s >> 2;                    // word index relative to G0 (negative: before this slice)
+            const uint32_t span = ((uint32_t)s & 3u) + n; // only words that hold a source byte are touched
+            const uint32_t w0 = __ldcg(hist32 + gw);
+            const uint32_t w1 = span > 4u ? __ldcg(hist32 + gw + 1) : 0u;
+            const uint32_t w2 = span > 8u ? __ldcg(hist32 + gw + 2) : 0u;
+            const uint32_t sh8 = 8u * ((uint32_t)s & 3u);
+            const uint32_t ha = __funnelshift_r(w0, w1, sh8), hb = __funnelshift_r(w1, w2, sh8);
+            p0 = __byte_perm(ha, 0u, 0x4140);
+            p1 = __byte_perm(ha, 0u, 0x4342);
+            p2 = __byte_perm(hb, 0u, 0x4140);
+            p3 = __byte_perm(hb, 0u, 0x4342);
+          }
+          uint16_t *const at = S.sym + i;
+          st_sym_if(n > 0u, at + 0, p0);
+          st_sym_if(n > 1u, at + 1, p0 >> 16);
+          st_sym_if(n > 2u, at + 2, p1);
+          st_sym_if(n > 3u, at + 3, p1 >> 16);
+          st_sym_if(n > 4u, at + 4, p2);
+          st_sym_if(n > 5u, at + 5, p2 >> 16);
+          st_sym_if(n > 6u, at + 6, p3);
+          st_sym_if(n > 7u, at + 7, p3 >> 16);
+        };
+#pragma unroll 1
+        for (int pass = 0; pass < 2; pass++) {
+          uint32_t n_seg, ptr;
+          int32_t base;
+          if (pass == 0) {
+            n_seg = in_slice ? (uint32_t)d_nh : 0u;
+            ptr = (uint32_t)(d_owner * TOK_SLOTS + d_h0);
+            base = i0 - (int32_t)d_head_o0;
+          } else {
+            n_seg = in_slice && d_spec ? (uint32_t)(ns - d_k) : 0u;
+            ptr = (uint32_t)(tid * TOK_SLOTS + HEAD_CAP + d_k);
+            base = i0 + (int32_t)d_out_head - (int32_t)d_spec_skip;
+          }
+          const uint32_t incl = warp_incl_scan(n_seg, lane);
+          const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+          if (total == 0u) continue; // (warp-uniform)
+          __syncwarp();
+          S.seg_pre[warp][lane] = (uint16_t)(incl - n_seg);
+          if (lane == 31) S.seg_pre[warp][32] = (uint16_t)total;
+          S.seg_info[warp][lane] = ptr | ((uint32_t)(base + SEG_BIAS) << 16);
+          __syncwarp();
+          // token c of the concatenation belongs to list l: seg_pre[l] <= c < seg_pre[l + 1]; c only grows, so l does too
+          int l = 0;
+          uint32_t pl = 0, pn = S.seg_pre[warp][1];
+          uint2 tk = make_uint2(0u, 0u);
+          int32_t tk_base = 0;
+          auto fetch = [&](const uint32_t c) {
+            while (c >= pn) { l++; pl = pn; pn = S.seg_pre[warp][l + 1]; }
+            const uint32_t info = S.seg_info[warp][l];
+            tk = __ldcg(tok_cta + (info & 0xffffu) + (c - pl));
+            tk_base = (int32_t)(info >> 16) - SEG_BIAS;
+          };
+          if ((uint32_t)lane < total) fetch((uint32_t)lane);
+          const uint32_t nit = (total + 31u) >> 5;
+#pragma unroll 1
+          for (uint32_t it = 0; it < nit; it++) {
+            const uint32_t c = it * 32u + (uint32_t)lane;
+            const uint32_t t = tk.x;
+            int32_t i = tk_base + (int32_t)tk.y;
+            const bool valid = c < total;
+            if (c + 32u < total) fetch(c + 32u); // the next step's token is in flight while this one is replayed
+            STAT(if (valid) g_stats.d_iters++;)
+            bool big = false;
+            int32_t s = 0;
+            uint32_t len = 0, dist = 0;
+            if (valid) {
+              if (!tok_is_match(t)) {
+                S.sym[i] = (uint16_t)t;
+              } else {
+                dist = ((t >> 8) & 0x7fffu) + 1u;
+                len = (t & 0xffu) + 3u;
+                s = i - (int32_t)dist;
+                if (dist > slice_out0 + (uint32_t)(i - (int32_t)bias)) { // Invalid distance (de.ml:1700): the general kernel reports it
+                  S.abort_round = 1;
+                } else if (len > COOP_LEN) {
+                  big = true;
+                } else {
+                  group8(i, s, len < 8u ? len : 8u, dist);
+                  if (len > 8u) group8(i + 8, s + 8, len - 8u, dist);
+                }
+              }
+            }
+            // long matches: the whole warp writes one, eight symbols per lane and step
+            uint32_t bm = __ballot_sync(0xffffffffu, big);
+            while (bm) {
+              const int src = __ffs((int)bm) - 1;
+              bm &= bm - 1u;
+              const int32_t bi = __shfl_sync(0xffffffffu, i, src), bs = __shfl_sync(0xffffffffu, s, src);
+              const uint32_t blen = __shfl_sync(0xffffffffu, len, src), bdist = __shfl_sync(0xffffffffu, dist, src);
+              for (uint32_t k0 = 8u * (uint32_t)lane; k0 < blen; k0 += 256u) {
+                const uint32_t n = blen - k0 < 8u ? blen - k0 : 8u;
+                if (bdist >= blen) group8(bi + (int32_t)k0, bs + (int32_t)k0, n, bdist);
+                else { // overlapping: every symbol points into the first period (short chains for phase E)
+                  for (uint32_t k = 0; k < n; k++) {
+                    const int32_t sk = bs + (int32_t)((k0 + k) % bdist);
+                    uint32_t v;
+                    if (sk >= (int32_t)bias) { v = 256u + (uint32_t)sk; STAT(g_stats.markers++;) }
+                    else { v = __ldcg(G0 + sk); STAT(g_stats.hist_bytes++;) }
+                    S.sym[bi + (int32_t)(k0 + k)] = (uint16_t)v;
+                  }
+                }
+              }
+            }
+          }
         }
-        STAT(g_stats.d_iters += iters; if (iters > g_stats.d_lane_max_iters) g_stats.d_lane_max_iters = iters;)
       }
       __syncthreads();
       if (S.abort_round) { round_failed = true; break; }
@@ -1316,7 +1375,7 @@ inflate_parallel_kernel(int fmt, int64_t nstreams, const uint8_t *src_base, cons
 size_t inflate_parallel_smem_bytes() { return sizeof(ParSmem) + 128; }
 int inflate_parallel_ctas_per_sm() { return DCMP_CTAS_PER_SM; }
 // bytes of token scratch one CTA needs (global memory, stays L2-resident)
-size_t inflate_parallel_scratch_bytes_per_cta() { return (size_t)TOK_SLOTS * PT * sizeof(uint32_t) + 64; }
+size_t inflate_parallel_scratch_bytes_per_cta() { return (size_t)TOK_SLOTS * PT * sizeof(uint2) + 64; }
 
 #ifndef DCMP_EMU
 int launch_inflate_parallel(int fmt, int64_t n, const uint8_t *src_base, const int64_t *src_off, const int64_t *src_len,
