@@ -704,20 +704,18 @@ size_t deflate_slot_bytes() { return DF_SLOT; }
 int deflate_chunk_size() { return DF_CHUNK; }
 
 #ifndef DCMP_EMU
+int configure_deflate() { // per device (see configure_inflate_parallel)
+  cudaError_t e = cudaFuncSetAttribute(deflate_chunk_kernel<DF_HASH_BITS_FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)deflate_smem_bytes(1));
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(deflate_chunk_kernel<DF_HASH_BITS_BEST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)deflate_smem_bytes(9));
+  return (int)e;
+}
 int launch_deflate(int level, int fmt, int64_t nstreams, int64_t nchunks, const uint8_t *src_base, const void *chunks,
                    const int64_t *first_chunk, void *outs, uint8_t *slots, int64_t *chunk_dst, uint32_t *tok_scratch,
                    unsigned long long *work_counter, int ctas, uint8_t *dst_base, const int64_t *dst_off,
                    const int64_t *dst_cap, int64_t *written, int32_t *status, cudaStream_t stream) {
-  static bool configured = false;
   const size_t smem = deflate_smem_bytes(level);
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(deflate_chunk_kernel<DF_HASH_BITS_FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)deflate_smem_bytes(1));
-    if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(deflate_chunk_kernel<DF_HASH_BITS_BEST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)deflate_smem_bytes(9));
-    if (e != cudaSuccess) return (int)e;
-    configured = true;
-  }
   if (nchunks > 0) {
     int64_t want = (nchunks + DF_WARPS - 1) / DF_WARPS;
     if (ctas > want) ctas = (int)want;

@@ -21,6 +21,10 @@ int launch_inflate_parallel(int fmt, int64_t n, const uint8_t *src_base, const i
                             int64_t *produced, int32_t *status, unsigned long long *work_counter, uint32_t *tok_scratch,
                             int ctas, cudaStream_t stream);
 size_t inflate_parallel_scratch_bytes_per_cta();
+int configure_inflate_parallel();
+int configure_lzo_parallel();
+int configure_lzo_decode();
+int configure_deflate();
 int inflate_parallel_ctas_per_sm();
 void launch_gzip_header(int64_t n, const uint8_t *src_base, const int64_t *src_off, const int64_t *src_len, int64_t *body_off,
                         int64_t *body_len, int32_t *pre_status, cudaStream_t stream);
@@ -159,6 +163,16 @@ int dcmp_engine_create(int device, dcmp_engine **out) {
   eng->par_ctas = dcmp::inflate_parallel_ctas_per_sm() * (eng->sm_count > 0 ? eng->sm_count : 148);
   se = cudaMalloc(&eng->d_scratch, 256 + (size_t)eng->par_ctas * dcmp::inflate_parallel_scratch_bytes_per_cta());
   if (se != cudaSuccess) { set_err("cudaMalloc(scratch)", se); cudaStreamDestroy(eng->stream); delete eng; return DCMP_API_OUT_OF_MEMORY; }
+  // kernels that need more than 48 KiB of dynamic shared memory opt in per device
+  int ce = dcmp::configure_inflate_parallel();
+  if (ce == 0) ce = dcmp::configure_lzo_parallel();
+  if (ce == 0) ce = dcmp::configure_lzo_decode();
+  if (ce == 0) ce = dcmp::configure_deflate();
+  if (ce != 0) {
+    set_err("cudaFuncSetAttribute(MaxDynamicSharedMemorySize)", (cudaError_t)ce);
+    cudaFree(eng->d_scratch); cudaStreamDestroy(eng->stream); delete eng;
+    return DCMP_API_CUDA_ERROR;
+  }
   const char *m = getenv("DCMP_INFLATE_MODE");
   eng->mode = (m && strcmp(m, "serial") == 0) ? 1 : 0;
   *out = eng;

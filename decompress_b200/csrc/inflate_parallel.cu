@@ -53,7 +53,7 @@
 namespace dcmp {
 
 #ifndef DCMP_PHASE_A_INLINE
-#define DCMP_PHASE_A_INLINE __noinline__
+#define DCMP_PHASE_A_INLINE __forceinline__
 #endif
 #ifndef DCMP_PT
 #define DCMP_PT 256
@@ -68,10 +68,10 @@ constexpr int SUB_WORDS = DCMP_SUB_WORDS; // sub-chunk size in 32-bit words (odd
 constexpr int SUB_BITS = 32 * SUB_WORDS;
 constexpr int SPEC_CAP = ((SUB_BITS / 3) + 3) & ~3; // tokens a lane may produce speculatively (< 256: checkpoint field)
 constexpr int HEAD_CAP = 96;              // tokens a lane may produce while re-synchronising (p99 of the distance is ~55 on text)
-constexpr int TOK_SLOTS = SPEC_CAP + HEAD_CAP; // per lane, in the global scratch (64-bit tokens)
+constexpr int TOK_SLOTS = SPEC_CAP + HEAD_CAP; // per lane, in the global scratch
 constexpr int LANE_BYTE_CAP = 4096;       // bytes a lane may produce per pass (checkpoint field: 19 bits)
 #ifndef DCMP_WARMUP_BITS
-#define DCMP_WARMUP_BITS 384
+#define DCMP_WARMUP_BITS 768
 #endif
 constexpr int WARMUP_BITS = DCMP_WARMUP_BITS; // a lane's speculative pass starts this far inside the previous sub-chunk
 #ifndef DCMP_CKPT_SHIFT
@@ -109,16 +109,12 @@ constexpr int DCMP_INTERNAL_RETRY = 0x7f; // never leaves the library
 static_assert(SUB_WORDS % 2 == 1, "odd lane stride keeps the window reads conflict-free");
 static_assert(PT % 64 == 0 && PT <= 1024, "the two halves of the CTA build one decode table each");
 static_assert(SPEC_CAP < 256 && LANE_BYTE_CAP + 258 < (1 << 19), "checkpoint fields");
-static_assert(SPEC_CAP % 2 == 0 && HEAD_CAP % 2 == 0, "token slots are written in pairs");
-static_assert(PT * TOK_SLOTS <= 65536, "phase D addresses a CTA's token slots with 16 bits");
 
-constexpr int SEG_BIAS = 8192;            // phase D: a segment's symbol base may be negative by up to LANE_BYTE_CAP
 constexpr int MAX_CROSS = 6;              // sub-chunk boundaries one head decode may cross
 // Per-round metadata that is dead before phase D writes symbols; it overlays the symbol buffer.
 struct LaneDesc {          // what a lane replays in phase D, written by the lane that owns the head
   uint16_t owner;          // lane whose head slots hold the tokens
   uint8_t h0, h1;          // head tokens [h0, h1)
-  uint16_t head_o0;        // bytes the head had produced before token h0
   uint16_t out_head;       // bytes they produce
   uint8_t spec_k;          // speculative tokens from spec_k on (if has_spec)
   uint8_t flags;           // bit0 has_spec, bit1 terminal here (head ended: kind in bits 4..6)
@@ -171,14 +167,9 @@ __device__ __forceinline__ void st_sym_if(bool pred, uint16_t *addr, uint32_t v)
                : "memory");
 #endif
 }
-// A token leaves for the scratch as soon as it is decoded (one 64-bit store: nothing to carry from step to step).
-struct TokWriter {
-  __device__ __forceinline__ void push(uint4 *lane_slots, int n, uint32_t tok, uint32_t off) {
-    reinterpret_cast<uint2 *>(lane_slots)[n] = make_uint2(tok, off);
-  }
-  __device__ __forceinline__ void finish(uint4 *, int) {}
-};
-
+// A token leaves for the scratch as soon as it is decoded (nothing to carry from step to step).  The scratch of a
+// CTA is slot-major — token k of lane t at [k][t] — so the lanes of a warp that are at the same token count write
+// (phase A) and read (phase D) one line.
 struct HuffMeta {      // canonical-code description of one alphabet
   uint16_t first[16];  // first code (MSB-first) of each length
   uint16_t cnt[16];
@@ -208,19 +199,12 @@ struct ParSmem {
   uint8_t lens[MAX_LENS];
   HuffMeta ml, md;
   uint32_t run_cnt[2][16];       // per table under construction (literal/length, distance)
-  union {
-    struct {                       // per-lane results of phase A, read by phase B
-      uint16_t exit_pos[PT];       // spec pass: bit offset (own sub-chunk coordinates) after the last token
-      uint8_t exit_kind[PT];
-      int8_t last_ck[PT];          // spec pass: last checkpoint window written
-      uint8_t spec_ns[PT];         // spec pass: tokens produced
-      uint16_t spec_out[PT];       // spec pass: bytes produced
-    };
-    struct {                       // phase D: the token lists of a warp's lanes, concatenated
-      uint16_t seg_pre[NWARP][34]; // [l]: tokens of the lanes before l; [32]: all
-      uint32_t seg_info[NWARP][32];// [15:0] first token (slot index in the CTA's scratch), [31:16] symbol index of offset 0, + SEG_BIAS
-    };
-  };
+  // per-lane results of phase A, read by phase B
+  uint16_t exit_pos[PT];         // spec pass: bit offset (own sub-chunk coordinates) after the last token
+  uint8_t exit_kind[PT];
+  int8_t last_ck[PT];            // spec pass: last checkpoint window written
+  uint8_t spec_ns[PT];           // spec pass: tokens produced
+  uint16_t spec_out[PT];         // spec pass: bytes produced
   uint32_t m_owner[NWARP];       // lanes whose own head decode counts (not covered by an earlier lane's head)
   int pass_owner;                // lane whose head ran past the end of the window (-1: none)
   int pass_pos;                  // its exit (own sub-chunk coordinates)
@@ -241,7 +225,6 @@ struct ParSmem {
   int n_valid;                   // lanes accepted in this round
   uint32_t round_out;            // bytes produced by this round
   uint32_t adler_a, adler_b;
-  uint32_t mbar_phase;
   int abort_round;               // a lane met an invalid distance: the general kernel reports it
   int any_cross;                 // a head of this round crossed into another lane's sub-chunk
   volatile uint32_t a_done[NWARP]; // round number up to which a warp has finished phase A (its lanes' exits and checkpoints are in place)
@@ -287,8 +270,7 @@ __device__ __forceinline__ uint32_t sel_u32(uint32_t nz, uint32_t a, uint32_t b)
 #endif
 }
 
-// token (64 bits in the scratch): .x = [23] match flag; match: [22:8] distance-1, [7:0] length-3; literal: [7:0] byte
-//                                 .y = bytes the pass had produced before this token
+// token: [23] match flag; match: [22:8] distance-1, [7:0] length-3; literal: [7:0] byte
 template <bool KEEP>
 __device__ __forceinline__ int dec_step(const uint32_t *__restrict__ tbl, const uint32_t *__restrict__ win, Cursor &c,
                                         const uint32_t lmask, const uint32_t dmask, const int lroot, const int droot,
@@ -564,21 +546,21 @@ __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, int lane) {
 }
 
 // Stage `bytes` (16-byte multiple) from global `g` (16-byte aligned) into S.win; bytes past
-// `valid` are zero-filled by the threads.  All threads call; returns after the data landed.
-__device__ void stage_window(ParSmem &S, const uint8_t *g, int bytes, int valid, int tid) {
+// `valid` are zero-filled by the threads.  All threads call; returns after the data landed.  `phase` is the
+// mbarrier's parity, kept by every thread (CTA-uniform).
+__device__ void stage_window(ParSmem &S, const uint8_t *g, int bytes, int valid, int tid, uint32_t &phase) {
   // previous readers of S.win are done (callers sync before)
   if (valid > bytes) valid = bytes;
   if (valid < 0) valid = 0;
   for (int i = valid + tid * 16; i < bytes; i += PT * 16) *(uint4 *)((uint8_t *)S.win + i) = make_uint4(0, 0, 0, 0);
-  if (tid == 0 && valid > 0) {
-    mbar_expect_tx(&S.mbar, (uint32_t)valid);
-    tma_load_1d(S.win, g, (uint32_t)valid, &S.mbar);
-  }
   if (valid > 0) {
-    mbar_wait(&S.mbar, S.mbar_phase & 1u);
+    if (tid == 0) {
+      mbar_expect_tx(&S.mbar, (uint32_t)valid);
+      tma_load_1d(S.win, g, (uint32_t)valid, &S.mbar);
+    }
+    mbar_wait(&S.mbar, phase & 1u);
+    phase ^= 1u;
   }
-  __syncthreads();
-  if (tid == 0 && valid > 0) S.mbar_phase ^= 1u;
   __syncthreads();
 }
 
@@ -664,7 +646,7 @@ __device__ void prefetch_next_stream(ParSmem &S, int fmt, int64_t nstreams, cons
 // ------------------------------------------------------------------------------------------
 // Phase A of a round, one lane: speculative decode of the lane's own sub-chunk.  Results: the tokens (scratch), a
 // checkpoint per CKPT window, and exit position / kind, last checkpoint window, token and byte counts in S.
-__device__ DCMP_PHASE_A_INLINE void phase_a_lane(ParSmem &S, uint32_t (*ckpt)[PT], uint4 *tok_spec, const int q0, const int tid,
+__device__ DCMP_PHASE_A_INLINE void phase_a_lane(ParSmem &S, uint32_t (*ckpt)[PT], uint32_t *tok_spec, const int q0, const int tid,
                                           const bool lane_has_input) {
   const int lroot = S.ml.root, droot = S.md.root;
   const uint32_t lmask = (1u << lroot) - 1u, dmask = (1u << droot) - 1u;
@@ -683,7 +665,6 @@ __device__ DCMP_PHASE_A_INLINE void phase_a_lane(ParSmem &S, uint32_t (*ckpt)[PT
     while (cu.q < q0 || !cu.at_token()) {
       if (dec_step<false>(S.tbl, S.win, cu, lmask, dmask, lroot, droot, tok, no) >= STEP_EOB) { cu.start(q0, lmask); break; }
     }
-    TokWriter tw;
     int tstart = 0;
     for (;;) {
       if (cu.at_token()) {
@@ -705,11 +686,10 @@ __device__ DCMP_PHASE_A_INLINE void phase_a_lane(ParSmem &S, uint32_t (*ckpt)[PT
       if (r == STEP_NONE) continue;
       if (r == STEP_EOB) { xkind = X_EOB; xpos = cu.q - q0; break; }
       if (r == STEP_ERR) { xkind = X_ERR; xpos = tstart; break; }
-      tw.push(tok_spec, ns, tok, out_s);
+      tok_spec[ns * PT] = tok;
       ns++;
       out_s += no;
     }
-    tw.finish(tok_spec, ns);
   }
   S.exit_pos[tid] = (uint16_t)xpos;
   S.exit_kind[tid] = (uint8_t)xkind;
@@ -735,13 +715,13 @@ inflate_parallel_kernel(int fmt, int64_t nstreams, const uint8_t *src_base, cons
   if (tid == 0) {
     mbar_init(&S.mbar, 1);
     fence_mbar_init();
-    S.mbar_phase = 0;
     S.pf.stream = -2;
     for (int w = 0; w < NWARP; w++) S.a_done[w] = 0;
   }
   __syncthreads();
 
   uint32_t round_no = 0; // data rounds this CTA has run (CTA-uniform)
+  uint32_t mbar_phase = 0; // parity of the window mbarrier (CTA-uniform)
   for (;;) {
     // ---------------------------------------------------------------- fetch a stream
     __syncthreads();
@@ -808,7 +788,7 @@ inflate_parallel_kernel(int fmt, int64_t nstreams, const uint8_t *src_base, cons
             S.hdr_ready = 0;
             S.next = NEXT_CONTINUE;
           }
-        } else stage_window(S, g0, HDR_BYTES, (int)(vend - v0 > HDR_BYTES ? HDR_BYTES : vend - v0), tid);
+        } else stage_window(S, g0, HDR_BYTES, (int)(vend - v0 > HDR_BYTES ? HDR_BYTES : vend - v0), tid, mbar_phase);
         if (tid == 0 && !ahead && !ahead2) {
           STAT(g_stats.hdr_rounds++;)
           HdrBits hb;
@@ -896,20 +876,26 @@ inflate_parallel_kernel(int fmt, int64_t nstreams, const uint8_t *src_base, cons
       // -------------------------------------------------------------- data round
       {
         int64_t want = vend - v0;
-        stage_window(S, g0, WIN_BYTES, (int)(want > WIN_BYTES ? WIN_BYTES : want), tid);
+        stage_window(S, g0, WIN_BYTES, (int)(want > WIN_BYTES ? WIN_BYTES : want), tid, mbar_phase);
       }
       const int q0 = bit0 + SUB_BITS * tid; // bit index of this lane's sub-chunk in the staged window
       const int lroot = S.ml.root, droot = S.md.root;
       const uint32_t lmask = (1u << lroot) - 1u, dmask = (1u << droot) - 1u;
-      // this lane's token slots in the L2-resident scratch: [HEAD_CAP head tokens | SPEC_CAP speculative tokens],
-      // 64-bit tokens written in pairs
-      uint4 *tok_lane = reinterpret_cast<uint4 *>(tok_scratch + ((size_t)blockIdx.x * PT + tid) * (TOK_SLOTS * 2));
-      uint4 *tok_head = tok_lane;
-      uint4 *tok_spec = tok_lane + HEAD_CAP / 2;
+      // this lane's token slots in the L2-resident scratch, slot-major: [HEAD_CAP head tokens | SPEC_CAP speculative tokens][PT]
+      uint32_t *const tok_cta = tok_scratch + (size_t)blockIdx.x * PT * TOK_SLOTS;
+      uint32_t *const tok_head = tok_cta + tid;
+      uint32_t *const tok_spec = tok_cta + (size_t)HEAD_CAP * PT + tid;
       // lanes whose sub-chunk starts beyond the input decode nothing
       const bool lane_has_input = base_bit + (int64_t)SUB_BITS * tid < 8 * S.src_len;
       round_no++;
       if (tid == 0) { S.first_bad = PT; S.first_term = PT; S.abort_round = 0; S.pass_owner = -1; S.any_cross = 0; } // (read after the barrier that ends phase B)
+      // The CTA's next stream is claimed and its first header parsed (a serial job of ~30k cycles) by the last warp in
+      // a round that leaves it without input — the last round of a stream as a rule — while the other warps are in
+      // phase A; a stream whose rounds are all full has its successor's header parsed in line.
+      if (warp == NWARP - 1 && !(base_bit + (int64_t)SUB_BITS * (PT - 32) < 8 * S.src_len)) {
+        const int todo = __shfl_sync(0xffffffffu, S.pf_done == 0 ? 1 : 0, 0); // (lane 0 sets the flag in there: one reader)
+        if (todo) prefetch_next_stream(S, fmt, nstreams, src_base, src_off, src_len, dst_base, dst_off, dst_cap, work_counter, lane);
+      }
       // ---- A: speculative decode of the own sub-chunk from bit 0 (a function of its own: the hot loop gets the
       // whole register budget, not what the rest of the kernel leaves it)
       phase_a_lane(S, ckpt, tok_spec, q0, tid, lane_has_input);
@@ -944,7 +930,6 @@ inflate_parallel_kernel(int fmt, int64_t nstreams, const uint8_t *src_base, cons
           } else {
             Cursor cu;
             cu.start(q0 + entry, lmask);
-            TokWriter tw;
             uint32_t tok = 0, no = 0;
             int u = tid, ubase = 0, lck = last_ck, seen_ck = -1, xk_u = xkind, xp_u = xpos, tstart = entry;
             for (;;) {
@@ -983,19 +968,13 @@ inflate_parallel_kernel(int fmt, int64_t nstreams, const uint8_t *src_base, cons
               if (r == STEP_NONE) continue;
               if (r == STEP_EOB) { hcat = H_TERM; hkind = X_EOB; hpos = cu.q - q0; break; }
               if (r == STEP_ERR) { hcat = H_TERM; hkind = X_ERR; hpos = tstart; break; }
-              tw.push(tok_head, nh, tok, out_h);
+              tok_head[nh * PT] = tok;
               nh++;
               out_h += no;
             }
-            tw.finish(tok_head, nh);
           }
         }
         STAT(if (hcat != H_BAD && tid > 0) { if (hcat == H_MERGE && ncross == 0) g_stats.hist_nh[nh < 47 ? nh : 47]++; else if (hcat != H_TERM) g_stats.nosync_lanes++; })
-        // the last warp, once its own heads are done, opens the CTA's next stream (the others are still in their tails)
-        if (warp == NWARP - 1 && !S.pf_done) {
-          __syncwarp();
-          prefetch_next_stream(S, fmt, nstreams, src_base, src_off, src_len, dst_base, dst_off, dst_cap, work_counter, lane);
-        }
         // the lane after the ones this head covers is the next one whose own head counts
         int last = tid + ncross;           // lane in which the head ended
         if (last > PT - 1) last = PT - 1;  // (H_PASS)
@@ -1037,7 +1016,6 @@ inflate_parallel_kernel(int fmt, int64_t nstreams, const uint8_t *src_base, cons
           d.h0 = (uint8_t)(j == 0 ? 0 : M.cross_nh[tid][j - 1]);
           d.h1 = (uint8_t)(j < ncross ? M.cross_nh[tid][j] : nh);
           const uint32_t o0 = j == 0 ? 0u : M.cross_out[tid][j - 1], o1 = j < ncross ? M.cross_out[tid][j] : out_h;
-          d.head_o0 = (uint16_t)o0;
           d.out_head = (uint16_t)(o1 - o0);
           d.spec_k = (uint8_t)mk;
           d.spec_skip = (uint16_t)mskip;
@@ -1052,7 +1030,6 @@ inflate_parallel_kernel(int fmt, int64_t nstreams, const uint8_t *src_base, cons
       // every lane's final contribution: head tokens [d_h0, d_h0 + d_nh) of lane d_owner, then (d_spec) its own
       // speculative tokens from d_k on
       int d_owner = tid, d_h0 = 0, d_nh = 0, d_k = 0, tkind = X_NORMAL;
-      uint32_t d_head_o0 = 0, d_out_head = 0, d_spec_skip = 0;
       int64_t t_next = 0; // where the stream continues if this lane closes the round
       bool d_spec = false, in_ok = true, term = false, clean = false;
       uint32_t out_valid = 0;
@@ -1063,9 +1040,6 @@ inflate_parallel_kernel(int fmt, int64_t nstreams, const uint8_t *src_base, cons
           d_owner = d.owner;
           d_h0 = d.h0;
           d_nh = (int)d.h1 - (int)d.h0;
-          d_head_o0 = d.head_o0;
-          d_out_head = d.out_head;
-          d_spec_skip = d.spec_skip;
           out_valid = d.out_head;
           if (d.flags & 1) { // the true sequence leaves this sub-chunk the way the speculative one does
             d_spec = true;
@@ -1084,13 +1058,13 @@ inflate_parallel_kernel(int fmt, int64_t nstreams, const uint8_t *src_base, cons
       }
       if (!in_ok) atomicMin(&S.first_bad, tid);
       if (term) atomicMin(&S.first_term, tid);
+      // (the scan runs over every lane that could be chained: the lanes in front of the cut are all among them, and
+      // only their sums are used)
+      uint32_t incl = warp_incl_scan(in_ok ? out_valid : 0u, lane);
+      if (lane == 31) S.warp_c[warp] = incl;
       __syncthreads();
       const int first_bad = S.first_bad, first_term = S.first_term;
       int n_valid = first_term < first_bad ? first_term + 1 : first_bad;
-      uint32_t mine = tid < n_valid ? out_valid : 0u;
-      uint32_t incl = warp_incl_scan(mine, lane);
-      if (lane == 31) S.warp_c[warp] = incl;
-      __syncthreads();
       {
         uint32_t woff = 0;
 #pragma unroll
@@ -1137,11 +1111,14 @@ inflate_parallel_kernel(int fmt, int64_t nstreams, const uint8_t *src_base, cons
       uint32_t s0 = 0;
       bool round_failed = false;
       while (s0 < round_total) {
-      if (tid == 0) S.slice_end = s0;
-      __syncthreads();
-      if (tid < n_valid && my_end <= s0 + (uint32_t)RSYM) atomicMax(&S.slice_end, my_end); // a prefix of the lanes
-      __syncthreads();
-      const uint32_t s1 = S.slice_end;
+      uint32_t s1 = round_total;
+      if (round_total - s0 > (uint32_t)RSYM) { // (CTA-uniform; the rule is one slice)
+        if (tid == 0) S.slice_end = s0;
+        __syncthreads();
+        if (tid < n_valid && my_end <= s0 + (uint32_t)RSYM) atomicMax(&S.slice_end, my_end); // a prefix of the lanes
+        __syncthreads();
+        s1 = S.slice_end;
+      }
       if (s1 == s0) { round_failed = true; break; } // cannot happen: one lane's output always fits
       const bool in_slice = tid < n_valid && my_start >= s0 && my_end <= s1 && out_valid > 0u;
       const uint32_t slice_out0 = out0 + s0;   // stream position of the slice's first byte
@@ -1183,151 +1160,123 @@ inflate_parallel_kernel(int fmt, int64_t nstreams, const uint8_t *src_base, cons
         S.sym[E + tid] = 0;
       }
       {
-        // Token-parallel inside each warp: the token lists of the warp's 32 lanes are laid end to end and the
-        // threads take consecutive tokens, 32 per step — whatever the lengths of the lists, the warp needs
-        // ceil(total / 32) steps (replaying lane by lane it needed as many as its longest list had).  Two passes:
-        // the head parts, then the speculative parts.  A token carries the number of bytes its pass had produced
-        // before it, so its place in the symbol buffer is a per-list base plus that offset.  The source of a match
-        // decides how its symbols are made:
-        //   inside this slice (any lane's output): markers 256 + source index, no load at all
-        //   entirely in earlier rounds / slices: bytes of the stream's own output, read back through L2 (.cg loads:
-        //     they were stored by this CTA a barrier ago at least)
-        //   straddling the start of the slice, or overlapping itself inside a group of eight: per symbol
-        // A match longer than COOP_LEN symbols is spread over the lanes of the warp.
-        constexpr uint32_t COOP_LEN = 16;
-        const int32_t i0 = (int32_t)(my_start - s0 + bias); // symbol index of this lane's first byte
-        const uint2 *const tok_cta = reinterpret_cast<const uint2 *>(tok_scratch) + (size_t)blockIdx.x * PT * TOK_SLOTS;
-        const uint32_t *const hist32 = reinterpret_cast<const uint32_t *>(G0); // G0 is 16-byte aligned
-        STAT(if (in_slice) { g_stats.head_tokens += d_nh; g_stats.used_tokens += d_nh + (d_spec ? ns - d_k : 0); })
-        // up to eight symbols of a match: sym[i .. i+n) <- the bytes at symbol indices [s, s+n)
-        auto group8 = [&](const int32_t i, const int32_t s, const uint32_t n, const uint32_t dist) {
+        // Every lane walks its own token list: head tokens [0, nh), then the speculative tokens from
+        // the merge point on.  One step of the (warp-uniform) loop emits a literal or up to eight
+        // symbols of a match; the source of a match decides how:
+        //   inside this round (any lane, this one included): markers 256 + source index, no load at all
+        //   entirely in earlier rounds: bytes of the history ring
+        //   straddling the start of the round, or overlapping itself inside the group: per symbol
+        const int total_tok = in_slice ? d_nh + (d_spec ? ns - d_k : 0) : 0;
+        STAT(if (in_slice) { g_stats.head_tokens += d_nh; g_stats.used_tokens += total_tok; } long iters = 0;)
+#if DCMP_HIST_GLOBAL
+        // history = the stream's own output in HBM/L2; symbol index s <-> address G0 + s.  L2-coherent loads
+        // (.cg): the bytes were stored by this CTA in earlier rounds, a barrier ago at least.
+        const uint32_t *hist32 = reinterpret_cast<const uint32_t *>(G0 - ((uintptr_t)G0 & 3)); // G0 is 16-aligned: no-op
+#else
+        const uint32_t *ring32 = reinterpret_cast<const uint32_t *>(S.ring);
+#endif
+        int ti = 0;
+        int32_t i = (int32_t)(my_start - s0 + bias); // next symbol to write
+        int32_t s = 0;                // next source symbol of the pending match
+        uint32_t rem = 0;             // symbols the pending match still owes
+        uint32_t dist = 0;
+        // tokens are fetched three ahead of their use (slot-major scratch: a warp's loads of one slot are one line)
+        const uint32_t *head32 = tok_cta + (size_t)d_h0 * PT + d_owner;                     // head token t: + t * PT
+        const uint32_t *spec32 = tok_cta + (size_t)(HEAD_CAP + d_k - d_nh) * PT + tid;     // speculative token t (>= d_nh): + t * PT
+        auto tok_at = [&](int t) { return __ldcg((t < d_nh ? head32 : spec32) + (size_t)t * PT); };
+        uint32_t q0 = 0, q1 = 0, q2 = 0;
+        if (0 < total_tok) q0 = tok_at(0);
+        if (1 < total_tok) q1 = tok_at(1);
+        if (2 < total_tok) q2 = tok_at(2);
+        bool active = total_tok > 0;
+        while (__any_sync(0xffffffffu, active)) {
+          STAT(if (active) iters++;)
+          // -- next token, for the lanes that finished the previous one
+          bool fetch = active && rem == 0;
+          if (fetch && ti == total_tok) { active = false; fetch = false; }
+          uint32_t t = 0;
+          if (fetch) {
+            t = q0;
+            q0 = q1;
+            q1 = q2;
+            if (ti + 3 < total_tok) q2 = tok_at(ti + 3);
+            ti++;
+          }
+          const bool new_match = fetch && tok_is_match(t);
+          if (new_match) {
+            dist = ((t >> 8) & 0x7fffu) + 1u;
+            rem = (t & 0xffu) + 3u;
+            s = i - (int32_t)dist;
+            if (dist > slice_out0 + (uint32_t)(i - (int32_t)bias)) { // Invalid distance (de.ml:1700): the general kernel reports it
+              S.abort_round = 1;
+              active = false;
+              rem = 0;
+            }
+          }
+          // -- this step's symbols (branch-free for the three common cases)
+          const bool lit = fetch && !new_match;
+          const uint32_t n = lit ? 1u : (rem < 8u ? rem : 8u);  // 0 for idle lanes
           const bool in_round = s >= (int32_t)bias;
           const bool in_hist = s + (int32_t)n <= (int32_t)bias;
-          if (in_round ? dist < n : !in_hist) {
+          const bool slow = rem > 0u && (in_round ? dist < n : !in_hist);
+          // markers: source inside this round (another lane's output or this lane's own)
+          const uint32_t m0 = (256u + (uint32_t)s) * 0x00010001u + 0x00010000u;
+          // history: source entirely in earlier rounds (addresses are masked: the loads are always legal)
+          const uint32_t r = g0_low + (uint32_t)s; // ring byte address (mod HIST) of the first source byte
+#if !DCMP_HIST_GLOBAL
+          const uint32_t wi0 = r >> 2;
+#endif
+          uint32_t w0 = 0, w1 = 0, w2 = 0;
+          if (in_hist && rem > 0u) {
+#if DCMP_HIST_GLOBAL
+            const int32_t gw = s >> 2; // word index relative to G0 (negative: before this round)
+            const uint32_t span = ((uint32_t)s & 3u) + n; // only words that hold a source byte are touched
+            w0 = __ldcg(hist32 + gw);
+            if (span > 4u) w1 = __ldcg(hist32 + gw + 1);
+            if (span > 8u) w2 = __ldcg(hist32 + gw + 2);
+#else
+            w0 = ring32[wi0 & (HIST / 4 - 1)];
+            w1 = ring32[(wi0 + 1u) & (HIST / 4 - 1)];
+            w2 = ring32[(wi0 + 2u) & (HIST / 4 - 1)];
+#endif
+          }
+          const uint32_t sh8 = 8u * (r & 3u);
+          const uint32_t ha = __funnelshift_r(w0, w1, sh8), hb = __funnelshift_r(w1, w2, sh8);
+          uint32_t p0 = in_round ? m0 : __byte_perm(ha, 0u, 0x4140);
+          const uint32_t p1 = in_round ? m0 + 0x00020002u : __byte_perm(ha, 0u, 0x4342);
+          const uint32_t p2 = in_round ? m0 + 0x00040004u : __byte_perm(hb, 0u, 0x4140);
+          const uint32_t p3 = in_round ? m0 + 0x00060006u : __byte_perm(hb, 0u, 0x4342);
+          if (lit) p0 = t & 0xffu;
+          STAT(if (!slow && rem > 0) { if (in_round) g_stats.markers += n; else g_stats.hist_bytes += n; })
+          if (slow) {
+            // straddles the start of the round, or overlaps itself inside the group (point at the first period)
             for (uint32_t k = 0; k < n; k++) {
-              const int32_t sk = s + (int32_t)(dist < n ? k % dist : k); // (an overlapping copy points at its first period)
+              const int32_t sk = s + (int32_t)(dist < n ? k % dist : k);
               uint32_t v;
               if (sk >= (int32_t)bias) { v = 256u + (uint32_t)sk; STAT(g_stats.markers++;) }
+#if DCMP_HIST_GLOBAL
               else { v = __ldcg(G0 + sk); STAT(g_stats.hist_bytes++;) }
+#else
+              else { v = S.ring[(g0_low + (uint32_t)sk) & HIST_MASK]; STAT(g_stats.hist_bytes++;) }
+#endif
               S.sym[i + (int32_t)k] = (uint16_t)v;
             }
-            return;
-          }
-          STAT(if (in_round) g_stats.markers += n; else g_stats.hist_bytes += n;)
-          uint32_t p0, p1, p2, p3;
-          if (in_round) {
-            p0 = (256u + (uint32_t)s) * 0x00010001u + 0x00010000u;
-            p1 = p0 + 0x00020002u;
-            p2 = p0 + 0x00040004u;
-            p3 = p0 + 0x00060006u;
           } else {
-            const int32_t gw = s >> 2;                    // word index relative to G0 (negative: before this slice)
-            const uint32_t span = ((uint32_t)s & 3u) + n; // only words that hold a source byte are touched
-            const uint32_t w0 = __ldcg(hist32 + gw);
-            const uint32_t w1 = span > 4u ? __ldcg(hist32 + gw + 1) : 0u;
-            const uint32_t w2 = span > 8u ? __ldcg(hist32 + gw + 2) : 0u;
-            const uint32_t sh8 = 8u * ((uint32_t)s & 3u);
-            const uint32_t ha = __funnelshift_r(w0, w1, sh8), hb = __funnelshift_r(w1, w2, sh8);
-            p0 = __byte_perm(ha, 0u, 0x4140);
-            p1 = __byte_perm(ha, 0u, 0x4342);
-            p2 = __byte_perm(hb, 0u, 0x4140);
-            p3 = __byte_perm(hb, 0u, 0x4342);
+            // eight predicated stores (the compiler turns the plain `if`s into a cascade of eight divergent branches)
+            uint16_t *const at = S.sym + i;
+            st_sym_if(n > 0u, at + 0, p0);
+            st_sym_if(n > 1u, at + 1, p0 >> 16);
+            st_sym_if(n > 2u, at + 2, p1);
+            st_sym_if(n > 3u, at + 3, p1 >> 16);
+            st_sym_if(n > 4u, at + 4, p2);
+            st_sym_if(n > 5u, at + 5, p2 >> 16);
+            st_sym_if(n > 6u, at + 6, p3);
+            st_sym_if(n > 7u, at + 7, p3 >> 16);
           }
-          uint16_t *const at = S.sym + i;
-          st_sym_if(n > 0u, at + 0, p0);
-          st_sym_if(n > 1u, at + 1, p0 >> 16);
-          st_sym_if(n > 2u, at + 2, p1);
-          st_sym_if(n > 3u, at + 3, p1 >> 16);
-          st_sym_if(n > 4u, at + 4, p2);
-          st_sym_if(n > 5u, at + 5, p2 >> 16);
-          st_sym_if(n > 6u, at + 6, p3);
-          st_sym_if(n > 7u, at + 7, p3 >> 16);
-        };
-#pragma unroll 1
-        for (int pass = 0; pass < 2; pass++) {
-          uint32_t n_seg, ptr;
-          int32_t base;
-          if (pass == 0) {
-            n_seg = in_slice ? (uint32_t)d_nh : 0u;
-            ptr = (uint32_t)(d_owner * TOK_SLOTS + d_h0);
-            base = i0 - (int32_t)d_head_o0;
-          } else {
-            n_seg = in_slice && d_spec ? (uint32_t)(ns - d_k) : 0u;
-            ptr = (uint32_t)(tid * TOK_SLOTS + HEAD_CAP + d_k);
-            base = i0 + (int32_t)d_out_head - (int32_t)d_spec_skip;
-          }
-          const uint32_t incl = warp_incl_scan(n_seg, lane);
-          const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-          if (total == 0u) continue; // (warp-uniform)
-          __syncwarp();
-          S.seg_pre[warp][lane] = (uint16_t)(incl - n_seg);
-          if (lane == 31) S.seg_pre[warp][32] = (uint16_t)total;
-          S.seg_info[warp][lane] = ptr | ((uint32_t)(base + SEG_BIAS) << 16);
-          __syncwarp();
-          // token c of the concatenation belongs to list l: seg_pre[l] <= c < seg_pre[l + 1]; c only grows, so l does too
-          int l = 0;
-          uint32_t pl = 0, pn = S.seg_pre[warp][1];
-          uint2 tk = make_uint2(0u, 0u);
-          int32_t tk_base = 0;
-          auto fetch = [&](const uint32_t c) {
-            while (c >= pn) { l++; pl = pn; pn = S.seg_pre[warp][l + 1]; }
-            const uint32_t info = S.seg_info[warp][l];
-            tk = __ldcg(tok_cta + (info & 0xffffu) + (c - pl));
-            tk_base = (int32_t)(info >> 16) - SEG_BIAS;
-          };
-          if ((uint32_t)lane < total) fetch((uint32_t)lane);
-          const uint32_t nit = (total + 31u) >> 5;
-#pragma unroll 1
-          for (uint32_t it = 0; it < nit; it++) {
-            const uint32_t c = it * 32u + (uint32_t)lane;
-            const uint32_t t = tk.x;
-            int32_t i = tk_base + (int32_t)tk.y;
-            const bool valid = c < total;
-            if (c + 32u < total) fetch(c + 32u); // the next step's token is in flight while this one is replayed
-            STAT(if (valid) g_stats.d_iters++;)
-            bool big = false;
-            int32_t s = 0;
-            uint32_t len = 0, dist = 0;
-            if (valid) {
-              if (!tok_is_match(t)) {
-                S.sym[i] = (uint16_t)t;
-              } else {
-                dist = ((t >> 8) & 0x7fffu) + 1u;
-                len = (t & 0xffu) + 3u;
-                s = i - (int32_t)dist;
-                if (dist > slice_out0 + (uint32_t)(i - (int32_t)bias)) { // Invalid distance (de.ml:1700): the general kernel reports it
-                  S.abort_round = 1;
-                } else if (len > COOP_LEN) {
-                  big = true;
-                } else {
-                  group8(i, s, len < 8u ? len : 8u, dist);
-                  if (len > 8u) group8(i + 8, s + 8, len - 8u, dist);
-                }
-              }
-            }
-            // long matches: the whole warp writes one, eight symbols per lane and step
-            uint32_t bm = __ballot_sync(0xffffffffu, big);
-            while (bm) {
-              const int src = __ffs((int)bm) - 1;
-              bm &= bm - 1u;
-              const int32_t bi = __shfl_sync(0xffffffffu, i, src), bs = __shfl_sync(0xffffffffu, s, src);
-              const uint32_t blen = __shfl_sync(0xffffffffu, len, src), bdist = __shfl_sync(0xffffffffu, dist, src);
-              for (uint32_t k0 = 8u * (uint32_t)lane; k0 < blen; k0 += 256u) {
-                const uint32_t n = blen - k0 < 8u ? blen - k0 : 8u;
-                if (bdist >= blen) group8(bi + (int32_t)k0, bs + (int32_t)k0, n, bdist);
-                else { // overlapping: every symbol points into the first period (short chains for phase E)
-                  for (uint32_t k = 0; k < n; k++) {
-                    const int32_t sk = bs + (int32_t)((k0 + k) % bdist);
-                    uint32_t v;
-                    if (sk >= (int32_t)bias) { v = 256u + (uint32_t)sk; STAT(g_stats.markers++;) }
-                    else { v = __ldcg(G0 + sk); STAT(g_stats.hist_bytes++;) }
-                    S.sym[bi + (int32_t)(k0 + k)] = (uint16_t)v;
-                  }
-                }
-              }
-            }
-          }
+          i += (int32_t)n;
+          if (rem > 0u) { s += (int32_t)n; rem -= n; }
         }
+        STAT(g_stats.d_iters += iters; if (iters > g_stats.d_lane_max_iters) g_stats.d_lane_max_iters = iters;)
       }
       __syncthreads();
       if (S.abort_round) { round_failed = true; break; }
@@ -1375,20 +1324,19 @@ inflate_parallel_kernel(int fmt, int64_t nstreams, const uint8_t *src_base, cons
 size_t inflate_parallel_smem_bytes() { return sizeof(ParSmem) + 128; }
 int inflate_parallel_ctas_per_sm() { return DCMP_CTAS_PER_SM; }
 // bytes of token scratch one CTA needs (global memory, stays L2-resident)
-size_t inflate_parallel_scratch_bytes_per_cta() { return (size_t)TOK_SLOTS * PT * sizeof(uint2) + 64; }
+size_t inflate_parallel_scratch_bytes_per_cta() { return (size_t)TOK_SLOTS * PT * sizeof(uint32_t) + 64; }
 
 #ifndef DCMP_EMU
+// The opt-in to more than 48 KiB of dynamic shared memory is per device: dcmp_engine_create calls this after
+// cudaSetDevice for every engine.
+int configure_inflate_parallel() {
+  return (int)cudaFuncSetAttribute(inflate_parallel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)inflate_parallel_smem_bytes());
+}
 int launch_inflate_parallel(int fmt, int64_t n, const uint8_t *src_base, const int64_t *src_off, const int64_t *src_len,
                             uint8_t *dst_base, const int64_t *dst_off, const int64_t *dst_cap, int64_t *consumed,
                             int64_t *produced, int32_t *status, unsigned long long *work_counter, uint32_t *tok_scratch,
                             int ctas, cudaStream_t stream) {
-  static bool configured = false;
-  size_t smem = inflate_parallel_smem_bytes();
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(inflate_parallel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
-    configured = true;
-  }
+  const size_t smem = inflate_parallel_smem_bytes();
   if (ctas > n) ctas = (int)n;
   inflate_parallel_kernel<<<(unsigned)ctas, PT, smem, stream>>>(fmt, n, src_base, src_off, src_len, dst_base, dst_off,
                                                                dst_cap, consumed, produced, status, work_counter,

@@ -138,9 +138,17 @@ struct LzoWarp {
         ring[(uint32_t)(o_pos + k) & LZO_RING_MASK] = b;
         out[o_pos + k] = b;
       }
-    } else { // the copy overlaps itself: byte k repeats byte k mod off of the first period
+    } else if (len <= (P)LZO_RING - off) { // the copy overlaps itself: byte k repeats byte k mod off of the first period
       for (P k = lane; k < len; k += 32) {
         const uint8_t b = ring[(uint32_t)(s + k % off) & LZO_RING_MASK];
+        ring[(uint32_t)(o_pos + k) & LZO_RING_MASK] = b;
+        out[o_pos + k] = b;
+      }
+    } else {
+      // ... and is so long that its own ring writes wrap round onto the slots of that period: the period is read
+      // from the output instead (final since flush_pending + __syncwarp above; never written by this loop)
+      for (P k = lane; k < len; k += 32) {
+        const uint8_t b = out[s + k % off];
         ring[(uint32_t)(o_pos + k) & LZO_RING_MASK] = b;
         out[o_pos + k] = b;
       }
@@ -287,17 +295,15 @@ lzo_decode_kernel(int mode, int64_t nblocks, const uint8_t *src_base, const int6
 }
 
 #ifndef DCMP_EMU
+int configure_lzo_decode() { // per device (see configure_inflate_parallel)
+  return (int)cudaFuncSetAttribute(lzo_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LZO_WARPS * (LZO_RING + LZO_CACHE));
+}
 void launch_lzo_decode(int mode, int64_t n, const uint8_t *src_base, const int64_t *src_off, const int64_t *src_len,
                        uint8_t *dst_base, const int64_t *dst_off, const int64_t *dst_cap, int64_t *consumed,
                        int64_t *produced, int32_t *status, int only_status, cudaStream_t stream) {
   if (n <= 0) return;
   const int64_t blocks = (n + LZO_WARPS - 1) / LZO_WARPS;
   const size_t smem = (size_t)LZO_WARPS * (LZO_RING + LZO_CACHE);
-  static bool configured = false;
-  if (!configured) {
-    cudaFuncSetAttribute(lzo_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    configured = true;
-  }
   lzo_decode_kernel<<<(unsigned)blocks, LZO_WARPS * 32, smem, stream>>>(mode, n, src_base, src_off, src_len, dst_base,
                                                                     dst_off, dst_cap, consumed, produced, status, only_status);
 }

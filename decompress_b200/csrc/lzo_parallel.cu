@@ -563,17 +563,14 @@ lzo_parallel_kernel(int mode, int64_t nblocks, const uint8_t *src_base, const in
 size_t lzo_parallel_smem_bytes() { return sizeof(LzpSmem) + 128; }
 
 #ifndef DCMP_EMU
+int configure_lzo_parallel() { // per device (see configure_inflate_parallel)
+  return (int)cudaFuncSetAttribute(lzo_parallel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lzo_parallel_smem_bytes());
+}
 int launch_lzo_parallel(int mode, int64_t n, const uint8_t *src_base, const int64_t *src_off, const int64_t *src_len,
                         uint8_t *dst_base, const int64_t *dst_off, const int64_t *dst_cap, int64_t *consumed,
                         int64_t *produced, int32_t *status, cudaStream_t stream) {
   if (n <= 0) return 0;
-  static bool configured = false;
   const size_t smem = lzo_parallel_smem_bytes();
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(lzo_parallel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
-    configured = true;
-  }
   lzo_parallel_kernel<<<(unsigned)n, LZP_PT, smem, stream>>>(mode, n, src_base, src_off, src_len, dst_base, dst_off, dst_cap,
                                                             consumed, produced, status);
   return 0;

@@ -70,3 +70,30 @@ def mutated_streams(count=300, seed=7):
             s += bytes(rnd.randrange(256) for _ in range(rnd.randrange(1, 16)))
         out.append(("mut%03d_m%d" % (k, mode), bytes(s)))
     return out
+
+
+def lzo_block(literals, off, length):
+    """A hand-made LZO1X block (lzo.ml:315-393): an initial literal run, ONE match of `length` bytes at distance `off`
+    (M3 for off <= 16384, M4 beyond), the end marker.  For the long self-overlapping copies no compressor emits."""
+    assert len(literals) >= 4 and length >= 4 and 1 <= off <= min(49151, len(literals)) and off != 16384
+    if len(literals) <= 238:
+        out = bytearray([17 + len(literals)]) + bytearray(literals)
+    else:  # opcode 0 in the main loop: a run of 18 + count() literals
+        z, r = divmod(len(literals) - 18 - 1, 255)
+        out = bytearray([0]) + bytes(z) + bytes([r + 1]) + bytearray(literals)
+    ln = length - 2
+
+    def count(base_bits, first):
+        # len field: (first | len) when it fits the opcode's bits, else zeros * 255 + a last non-zero byte
+        if ln <= base_bits:
+            return bytes([first | ln])
+        rest = ln - base_bits
+        z, r = divmod(rest - 1, 255)
+        return bytes([first]) + bytes(z) + bytes([r + 1])
+
+    if off <= 16384:
+        out += count(31, 0x20) + ((off - 1) << 2).to_bytes(2, "little")
+    else:
+        o = off - 16384
+        out += count(7, 0x10 | ((o >> 11) & 8)) + ((o & 0x3fff) << 2).to_bytes(2, "little")
+    return bytes(out + b"\x11\x00\x00")

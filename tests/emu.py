@@ -52,8 +52,9 @@ def inflate_streams(streams, caps, fmt=0, mode=0, ctas=2):
     return out, retried
 
 
-def lzo_blocks(blocks, caps, mode=0):
-    """LZO kernel on the emulator: list of (status, consumed, produced, bytes)."""
+def lzo_blocks(blocks, caps, mode=0, which=0):
+    """LZO kernels on the emulator: list of (status, consumed, produced, bytes).  which=0: CTA-per-block kernel, then the
+    general one on the blocks it gave up (like engine.cu); which=2: the general kernel alone."""
     from decompress_b200 import batch
 
     src, so, sl, dst, do, dc = batch.pack(blocks, caps)
@@ -63,9 +64,9 @@ def lzo_blocks(blocks, caps, mode=0):
     st = np.full(n, -1, dtype=np.int32)
     p = lambda a: C.c_void_p(a.ctypes.data)
     L = lib()
-    L.emu_lzo_batch.restype = C.c_int
-    L.emu_lzo_batch.argtypes = [C.c_int, C.c_int64] + [C.c_void_p] * 9
-    L.emu_lzo_batch(mode, n, p(src), p(so), p(sl), p(dst), p(do), p(dc), p(cons), p(prod), p(st))
+    L.emu_lzo_batch2.restype = C.c_int
+    L.emu_lzo_batch2.argtypes = [C.c_int, C.c_int, C.c_int64] + [C.c_void_p] * 9
+    L.emu_lzo_batch2(mode, which, n, p(src), p(so), p(sl), p(dst), p(do), p(dc), p(cons), p(prod), p(st))
     return [(int(st[k]), int(cons[k]), int(prod[k]), dst[do[k]:do[k] + int(min(max(prod[k], 0), dc[k]))].tobytes()) for k in range(n)]
 
 

@@ -86,6 +86,20 @@ def test_lzo_goldens_and_blocks(emu):
         assert r == (0, len(c), len(p), p)
 
 
+def test_lzo_long_overlapping_copy_general_kernel(emu):
+    """A self-overlapping match longer than the ring minus its distance: its own ring writes wrap round onto the period
+    it repeats (lzo_decode.cu read stale ring bytes there and still answered Ok)."""
+    lit = b"abcdefgh" + bytes(range(64, 128)) + workloads.text(30000, 3)
+    blocks = [cases.lzo_block(lit[:max(off, 4 + off % 60)], off, ln) for off, ln in
+              ((3, 70000), (5, 200000), (30000, 40000), (30000, 100000), (7, 65536 - 7 + 1), (4, 65536))]
+    caps = [300000] * len(blocks)
+    for which in (2, 0):
+        res = emu.lzo_blocks(blocks, caps, mode=1, which=which)
+        for b, r in zip(blocks, res):
+            rc, cons, prod, out = oracle.lzo_uncompress_with_buffer(b, 300000)
+            assert rc == 0 and r[0] == 0 and r[2] == prod and r[3] == out, (which, len(out))
+
+
 def test_deflate_round_trip(emu):
     txt = workloads.text(150000, 2)
     ins = [txt, b"", txt[:100], bytes(70000), txt[:65537]]

@@ -10,7 +10,7 @@ import pytest
 
 import workloads
 from decompress_b200 import Error, Ok, _lib, lzo
-from tests import oracle
+from tests import cases, oracle
 
 pytestmark = pytest.mark.gpu
 G = os.path.join(os.path.dirname(__file__), "golden")
@@ -164,3 +164,18 @@ def test_cta_per_block_kernel_paths(eng):
         assert (st, cons, prod, out) == (0, len(small[o]), 5000 + o, txt[o:o + 5000 + o]), o
     _check(comps, [len(p) - 1 for p in plains], 0, eng)
     _check(comps, [len(p) // 2 for p in plains], 1, eng)
+
+
+def test_long_overlapping_copy_both_kernels(monkeypatch):
+    """A self-overlapping match longer than the general kernel's 64 KiB ring minus its distance (ADVICE r1,
+    lzo_decode.cu): hand-made blocks no compressor emits, through the default two-stage dispatch and through the
+    general kernel alone (DCMP_INFLATE_MODE=serial), against the oracle."""
+    lit = b"abcdefgh" + bytes(range(64, 128)) + workloads.text(30000, 3)
+    blocks = [cases.lzo_block(lit[:max(off, 4 + off % 60)], off, ln) for off, ln in
+              ((3, 70000), (5, 200000), (30000, 40000), (30000, 100000), (7, 65536 - 7 + 1), (4, 65536))]
+    for serial in (False, True):
+        if serial:
+            monkeypatch.setenv("DCMP_INFLATE_MODE", "serial")
+        e = _lib.Engine(0)
+        for mode in (0, 1):
+            _check(blocks, [300000] * len(blocks), mode, e)
