@@ -92,7 +92,12 @@ def main():
         assert int(st.item()) == 0
         comp = d_dst[:w].cpu().numpy().tobytes()
         assert zlib.decompress(comp) == txt, "deflate output does not round-trip through system zlib"
-        rc, cons, prod, out = oracle.zl_inflate_ns(comp[:1], 0)  # (the oracle round trip at full size lives in tests/)
+        # round trip through the reference's Zl.Inf.Ns.inflate (the CPU oracle's restatement), at full size
+        obuf = np.zeros(size + 16, dtype=np.uint8)
+        oc, op = C.c_int64(0), C.c_int64(0)
+        rc = oracle.lib().orc_zl_inflate_ns(comp, w, C.c_void_p(obuf.ctypes.data), size, C.byref(oc), C.byref(op))
+        assert (rc, oc.value, op.value) == (0, w, size) and obuf[:size].tobytes() == txt, "oracle Inf round trip failed"
+        del obuf
         t0 = time.time()
         zc = zlib.compress(txt[:64 << 20], 6)
         zsec = time.time() - t0

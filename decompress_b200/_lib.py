@@ -37,6 +37,7 @@ _SIGNATURES = {
     "dcmp_last_error": (C.c_char_p, []),
     "dcmp_status_string": (C.c_char_p, [C.c_int]),
     "dcmp_engine_launch_count": (C.c_int64, [C.c_void_p]),
+    "dcmp_engine_stats": (C.c_int, [C.c_void_p, p_i64, C.c_int]),
     "dcmp_inflate_batch": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, p_u8, p_i64, p_i64, p_u8, p_i64, p_i64,
                                      p_i64, p_i64, p_i32]),
     "dcmp_inflate_batch_device": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, p_u8, p_i64, p_i64, p_u8, p_i64, p_i64,
@@ -115,6 +116,12 @@ class Engine:
 
     def launch_count(self):
         return lib().dcmp_engine_launch_count(self._h)
+
+    def stats(self):
+        """dcmp_engine_stats: units submitted to / redone by the general kernels of the two-stage dispatch."""
+        out = (C.c_int64 * 5)()
+        check(lib().dcmp_engine_stats(self._h, out, 5), "dcmp_engine_stats")
+        return dict(zip(("inflate_streams", "inflate_redone", "lzo_blocks", "lzo_redone", "launches"), list(out)))
 
     def close(self):
         if self._h:

@@ -15,7 +15,8 @@
 namespace dcmp {
 void launch_inflate_serial(int fmt, int64_t n, const uint8_t *src_base, const int64_t *src_off, const int64_t *src_len,
                            uint8_t *dst_base, const int64_t *dst_off, const int64_t *dst_cap, int64_t *consumed,
-                           int64_t *produced, int32_t *status, int only_status, cudaStream_t stream);
+                           int64_t *produced, int32_t *status, int only_status, unsigned long long *redo_count,
+                           cudaStream_t stream);
 int launch_inflate_parallel(int fmt, int64_t n, const uint8_t *src_base, const int64_t *src_off, const int64_t *src_len,
                             uint8_t *dst_base, const int64_t *dst_off, const int64_t *dst_cap, int64_t *consumed,
                             int64_t *produced, int32_t *status, unsigned long long *work_counter, uint32_t *tok_scratch,
@@ -33,7 +34,8 @@ void launch_gzip_trailer(int64_t n, const uint8_t *src_base, const int64_t *src_
                          int64_t *produced, int32_t *status, cudaStream_t stream);
 void launch_lzo_decode(int mode, int64_t n, const uint8_t *src_base, const int64_t *src_off, const int64_t *src_len,
                        uint8_t *dst_base, const int64_t *dst_off, const int64_t *dst_cap, int64_t *consumed,
-                       int64_t *produced, int32_t *status, int only_status, cudaStream_t stream);
+                       int64_t *produced, int32_t *status, int only_status, unsigned long long *redo_count,
+                       cudaStream_t stream);
 int launch_lzo_parallel(int mode, int64_t n, const uint8_t *src_base, const int64_t *src_off, const int64_t *src_len,
                         uint8_t *dst_base, const int64_t *dst_off, const int64_t *dst_cap, int64_t *consumed,
                         int64_t *produced, int32_t *status, cudaStream_t stream);
@@ -68,9 +70,10 @@ struct dcmp_engine {
   uint8_t *d_buf = nullptr; // one growable device arena: [src | dst | tables]
   size_t d_cap = 0;
   int64_t launches = 0;
+  int64_t n_inflate = 0, n_lzo = 0;  // units submitted to the two-stage dispatch (dcmp_engine_stats)
   int sm_count = 0;
   int par_ctas = 0;                  // persistent CTAs of the sub-chunk-parallel kernel (2 per SM)
-  uint8_t *d_scratch = nullptr;      // [work counter (256 B) | token scratch of every CTA]
+  uint8_t *d_scratch = nullptr;      // [work counter, +64: inflate streams redone, +72: LZO blocks redone (256 B) | token scratch of every CTA]
   int mode = 0;                      // 0 = parallel + general, 1 = general kernel only (DCMP_INFLATE_MODE=serial)
   uint8_t *d_gz = nullptr;           // gzip: rebased body offsets / lengths / header status per member
   size_t gz_cap = 0;
@@ -163,6 +166,7 @@ int dcmp_engine_create(int device, dcmp_engine **out) {
   eng->par_ctas = dcmp::inflate_parallel_ctas_per_sm() * (eng->sm_count > 0 ? eng->sm_count : 148);
   se = cudaMalloc(&eng->d_scratch, 256 + (size_t)eng->par_ctas * dcmp::inflate_parallel_scratch_bytes_per_cta());
   if (se != cudaSuccess) { set_err("cudaMalloc(scratch)", se); cudaStreamDestroy(eng->stream); delete eng; return DCMP_API_OUT_OF_MEMORY; }
+  cudaMemset(eng->d_scratch, 0, 256);
   // kernels that need more than 48 KiB of dynamic shared memory opt in per device
   int ce = dcmp::configure_inflate_parallel();
   if (ce == 0) ce = dcmp::configure_lzo_parallel();
@@ -198,6 +202,17 @@ void dcmp_engine_destroy(dcmp_engine *e) {
 }
 
 int64_t dcmp_engine_launch_count(const dcmp_engine *e) { return e ? e->launches : 0; }
+
+int dcmp_engine_stats(dcmp_engine *e, int64_t *out, int n_out) {
+  if (!e || !out || n_out < 0) return DCMP_API_INVALID_ARGUMENT;
+  CU(cudaSetDevice(e->device));
+  CU(cudaDeviceSynchronize()); // (the counters are written by kernels on whatever stream the caller used)
+  unsigned long long redo[2] = {0, 0};
+  CU(cudaMemcpy(redo, e->d_scratch + 64, sizeof redo, cudaMemcpyDeviceToHost));
+  const int64_t v[DCMP_STATS_COUNT] = {e->n_inflate, (int64_t)redo[0], e->n_lzo, (int64_t)redo[1], e->launches};
+  for (int i = 0; i < n_out && i < DCMP_STATS_COUNT; i++) out[i] = v[i];
+  return DCMP_API_OK;
+}
 
 int dcmp_inflate_batch_device(dcmp_engine *e, int fmt, int64_t n, const uint8_t *d_src_base, const int64_t *d_src_off,
                               const int64_t *d_src_len, uint8_t *d_dst_base, const int64_t *d_dst_off,
@@ -242,11 +257,12 @@ int dcmp_inflate_batch_device(dcmp_engine *e, int fmt, int64_t n, const uint8_t 
     if (rc != 0) { set_err("launch_inflate_parallel", (cudaError_t)rc); return DCMP_API_CUDA_ERROR; }
     CU(cudaGetLastError());
     dcmp::launch_inflate_serial(fmt, n, d_src_base, d_src_off, d_src_len, d_dst_base, d_dst_off, d_dst_cap, d_consumed,
-                                d_produced, d_status, dcmp::INTERNAL_RETRY, st);
+                                d_produced, d_status, dcmp::INTERNAL_RETRY, (unsigned long long *)(e->d_scratch + 64), st);
     e->launches += 2;
+    e->n_inflate += n;
   } else {
     dcmp::launch_inflate_serial(fmt, n, d_src_base, d_src_off, d_src_len, d_dst_base, d_dst_off, d_dst_cap, d_consumed,
-                                d_produced, d_status, -1, st);
+                                d_produced, d_status, -1, nullptr, st);
     e->launches += 1;
   }
   if (gz_pre) {
@@ -405,11 +421,13 @@ int dcmp_lzo_uncompress_batch_device(dcmp_engine *e, int mode, int64_t n, const 
     static const bool no_fallback = getenv("DCMP_LZO_NO_FALLBACK") != nullptr; // debugging aid: given-up blocks keep status 0x7f
     if (!no_fallback)
       dcmp::launch_lzo_decode(mode, n, d_src_base, d_src_off, d_src_len, d_dst_base, d_dst_off, d_dst_cap, d_consumed,
-                              d_produced, d_status, dcmp::INTERNAL_RETRY, (cudaStream_t)cuda_stream);
+                              d_produced, d_status, dcmp::INTERNAL_RETRY, (unsigned long long *)(e->d_scratch + 72),
+                              (cudaStream_t)cuda_stream);
     e->launches += 2;
+    e->n_lzo += n;
   } else {
     dcmp::launch_lzo_decode(mode, n, d_src_base, d_src_off, d_src_len, d_dst_base, d_dst_off, d_dst_cap, d_consumed,
-                            d_produced, d_status, -1, (cudaStream_t)cuda_stream);
+                            d_produced, d_status, -1, nullptr, (cudaStream_t)cuda_stream);
     e->launches += 1;
   }
   CU(cudaGetLastError());

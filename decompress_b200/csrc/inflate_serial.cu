@@ -304,7 +304,7 @@ __device__ uint32_t warp_adler32(const uint8_t *p, int64_t n, int lane) {
 __global__ void __launch_bounds__(SERIAL_WARPS * 32)
 inflate_serial_kernel(int fmt, int64_t nstreams, const uint8_t *src_base, const int64_t *src_off, const int64_t *src_len,
                       uint8_t *dst_base, const int64_t *dst_off, const int64_t *dst_cap, int64_t *consumed,
-                      int64_t *produced, int32_t *status, int only_status) {
+                      int64_t *produced, int32_t *status, int only_status, unsigned long long *redo_count) {
   __shared__ WarpScratch scratch[SERIAL_WARPS];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -312,6 +312,7 @@ inflate_serial_kernel(int fmt, int64_t nstreams, const uint8_t *src_base, const 
   if (k >= nstreams) return;
   // second stage of the dispatcher: only the streams the sub-chunk-parallel kernel gave up
   if (only_status >= 0 && status[k] != only_status) return;
+  if (only_status >= 0 && redo_count && lane == 0) atomicAdd(redo_count, 1ull); // dcmp_engine_stats: streams the fast kernel gave up
   const uint8_t *src = src_base + src_off[k];
   int64_t n = src_len[k];
   uint8_t *dst = dst_base + dst_off[k];
@@ -355,11 +356,12 @@ inflate_serial_kernel(int fmt, int64_t nstreams, const uint8_t *src_base, const 
 #ifndef DCMP_EMU
 void launch_inflate_serial(int fmt, int64_t n, const uint8_t *src_base, const int64_t *src_off, const int64_t *src_len,
                            uint8_t *dst_base, const int64_t *dst_off, const int64_t *dst_cap, int64_t *consumed,
-                           int64_t *produced, int32_t *status, int only_status, cudaStream_t stream) {
+                           int64_t *produced, int32_t *status, int only_status, unsigned long long *redo_count,
+                           cudaStream_t stream) {
   if (n <= 0) return;
   int64_t blocks = (n + SERIAL_WARPS - 1) / SERIAL_WARPS;
   inflate_serial_kernel<<<(unsigned)blocks, SERIAL_WARPS * 32, 0, stream>>>(
-      fmt, n, src_base, src_off, src_len, dst_base, dst_off, dst_cap, consumed, produced, status, only_status);
+      fmt, n, src_base, src_off, src_len, dst_base, dst_off, dst_cap, consumed, produced, status, only_status, redo_count);
 }
 #endif
 

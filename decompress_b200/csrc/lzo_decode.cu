@@ -253,7 +253,7 @@ __device__ int lzo_run(LzoWarp<P> &w) {
 __global__ void __launch_bounds__(LZO_WARPS * 32)
 lzo_decode_kernel(int mode, int64_t nblocks, const uint8_t *src_base, const int64_t *src_off, const int64_t *src_len,
                   uint8_t *dst_base, const int64_t *dst_off, const int64_t *dst_cap, int64_t *consumed,
-                  int64_t *produced, int32_t *status, int only_status) {
+                  int64_t *produced, int32_t *status, int only_status, unsigned long long *redo_count) {
   DCMP_DYN_SMEM(smem_raw);
   uint8_t(*cache)[LZO_CACHE] = reinterpret_cast<uint8_t(*)[LZO_CACHE]>(smem_raw + (size_t)LZO_WARPS * LZO_RING);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -261,6 +261,7 @@ lzo_decode_kernel(int mode, int64_t nblocks, const uint8_t *src_base, const int6
   if (k >= nblocks) return;
   // second stage of the dispatcher: only the blocks the CTA-per-block kernel (lzo_parallel.cu) gave up
   if (only_status >= 0 && status[k] != only_status) return;
+  if (only_status >= 0 && redo_count && lane == 0) atomicAdd(redo_count, 1ull); // dcmp_engine_stats: blocks the fast kernel gave up
   const int64_t n_in = src_len[k], n_out = dst_cap[k];
   int r;
   int64_t cons, prod;
@@ -300,12 +301,13 @@ int configure_lzo_decode() { // per device (see configure_inflate_parallel)
 }
 void launch_lzo_decode(int mode, int64_t n, const uint8_t *src_base, const int64_t *src_off, const int64_t *src_len,
                        uint8_t *dst_base, const int64_t *dst_off, const int64_t *dst_cap, int64_t *consumed,
-                       int64_t *produced, int32_t *status, int only_status, cudaStream_t stream) {
+                       int64_t *produced, int32_t *status, int only_status, unsigned long long *redo_count,
+                       cudaStream_t stream) {
   if (n <= 0) return;
   const int64_t blocks = (n + LZO_WARPS - 1) / LZO_WARPS;
   const size_t smem = (size_t)LZO_WARPS * (LZO_RING + LZO_CACHE);
   lzo_decode_kernel<<<(unsigned)blocks, LZO_WARPS * 32, smem, stream>>>(mode, n, src_base, src_off, src_len, dst_base,
-                                                                    dst_off, dst_cap, consumed, produced, status, only_status);
+                                                                    dst_off, dst_cap, consumed, produced, status, only_status, redo_count);
 }
 #endif
 

@@ -13,7 +13,10 @@
 #ifdef DCMP_EMU
 #define DCMP_SPIN() simt::yield_to_sched()
 #else
-#define DCMP_SPIN() __nanosleep(32)
+#ifndef DCMP_SPIN_NS
+#define DCMP_SPIN_NS 32
+#endif
+#define DCMP_SPIN() __nanosleep(DCMP_SPIN_NS)
 #endif
 
 namespace dcmp {

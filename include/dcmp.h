@@ -88,6 +88,13 @@ const char *dcmp_last_error(void);
 const char *dcmp_status_string(int status); /* lib/de.ml:1557-1567, lib/zl.ml:177-183 */
 /* Number of kernels this engine has launched since creation (bench.py's gpu_launches). */
 int64_t dcmp_engine_launch_count(const dcmp_engine *e);
+/* Counters of the two-stage dispatch since the engine was created (synchronises the device).  The fast kernels
+ * (one CTA per stream / block) hand what they cannot finish — malformed or truncated input, output windows that
+ * are too small, exotic code sets — to the general kernels; a benchmark whose streams are all valid must see
+ * zero of them redone.  out[0] inflate streams submitted, out[1] inflate streams redone by the general kernel,
+ * out[2] LZO blocks submitted, out[3] LZO blocks redone, out[4] kernels launched. */
+#define DCMP_STATS_COUNT 5
+int dcmp_engine_stats(dcmp_engine *e, int64_t *out, int n_out);
 
 /* ---- batched inflate ---------------------------------------------------------
  * Replaces De.Inf.Ns.inflate (lib/de.mli:160-172, lib/de.ml:1807-1822) /

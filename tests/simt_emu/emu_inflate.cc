@@ -33,7 +33,7 @@ int emu_inflate_batch(int mode, int fmt, int64_t n, const uint8_t *src, const in
     if (mode == 2 || status[k] == DCMP_INTERNAL_RETRY) retried++;
   if (retried) {
     simt::launch(simt::dim3((unsigned)((n + SERIAL_WARPS - 1) / SERIAL_WARPS)), simt::dim3(SERIAL_WARPS * 32), 0, [&]() {
-      inflate_serial_kernel(fmt, n, src, soff, slen, dst, doff, dcap, cons, prod, status, mode == 2 ? -1 : DCMP_INTERNAL_RETRY);
+      inflate_serial_kernel(fmt, n, src, soff, slen, dst, doff, dcap, cons, prod, status, mode == 2 ? -1 : DCMP_INTERNAL_RETRY, nullptr);
     });
   }
   return retried;
@@ -53,7 +53,7 @@ int emu_lzo_batch2(int lzo_mode, int which, int64_t n, const uint8_t *src, const
     if (!retried) return 0;
   }
   simt::launch(simt::dim3((unsigned)((n + LZO_WARPS - 1) / LZO_WARPS)), simt::dim3(LZO_WARPS * 32), (size_t)LZO_WARPS * (LZO_RING + LZO_CACHE), [&]() {
-    lzo_decode_kernel(lzo_mode, n, src, soff, slen, dst, doff, dcap, cons, prod, status, which == 2 ? -1 : LZP_RETRY);
+    lzo_decode_kernel(lzo_mode, n, src, soff, slen, dst, doff, dcap, cons, prod, status, which == 2 ? -1 : LZP_RETRY, nullptr);
   });
   return retried;
 }
