@@ -58,6 +58,35 @@ _SIGNATURES = {
                                             p_i64, p_i64, p_i32, C.c_void_p]),
     "dcmp_def_ns_deflate": (C.c_int, [C.c_void_p, C.c_int, p_u8, C.c_int64, p_u8, C.c_int64, C.POINTER(C.c_int64)]),
     "dcmp_zl_def_ns_deflate": (C.c_int, [C.c_void_p, C.c_int, p_u8, C.c_int64, p_u8, C.c_int64, C.POINTER(C.c_int64)]),
+    "dcmp_engine_device": (C.c_int, [C.c_void_p]),
+    # streaming decoders / encoders (csrc/stream.cu)
+    "dcmp_inf_new": (C.c_int, [C.c_void_p, C.c_int, p_u8, C.c_int64, C.POINTER(C.c_void_p)]),
+    "dcmp_inf_free": (None, [C.c_void_p]),
+    "dcmp_inf_src": (C.c_int, [C.c_void_p, p_u8, C.c_int64]),
+    "dcmp_inf_dst": (C.c_int, [C.c_void_p, p_u8, C.c_int64]),
+    "dcmp_inf_decode": (C.c_int, [C.c_void_p]),
+    "dcmp_inf_status": (C.c_int, [C.c_void_p]),
+    "dcmp_inf_error": (C.c_char_p, [C.c_void_p]),
+    "dcmp_inf_dst_rem": (C.c_int64, [C.c_void_p]),
+    "dcmp_inf_src_rem": (C.c_int64, [C.c_void_p]),
+    "dcmp_inf_flush": (None, [C.c_void_p]),
+    "dcmp_inf_reset": (None, [C.c_void_p]),
+    "dcmp_inf_checksum": (C.c_uint32, [C.c_void_p]),
+    "dcmp_inf_write": (C.c_int64, [C.c_void_p]),
+    "dcmp_inf_launches": (C.c_int64, [C.c_void_p]),
+    "dcmp_inf_buffered": (C.c_int64, [C.c_void_p]),
+    "dcmp_gz_inf_os": (C.c_int, [C.c_void_p]),
+    "dcmp_gz_inf_mtime": (C.c_uint32, [C.c_void_p]),
+    "dcmp_gz_inf_field": (C.c_int64, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]),
+    "dcmp_def_new": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    "dcmp_def_free": (None, [C.c_void_p]),
+    "dcmp_def_gz_header": (C.c_int, [C.c_void_p, C.c_uint32, C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_int64, C.c_char_p,
+                                     C.c_int64]),
+    "dcmp_def_src": (C.c_int, [C.c_void_p, p_u8, C.c_int64]),
+    "dcmp_def_dst": (C.c_int, [C.c_void_p, p_u8, C.c_int64]),
+    "dcmp_def_encode": (C.c_int, [C.c_void_p]),
+    "dcmp_def_src_rem": (C.c_int64, [C.c_void_p]),
+    "dcmp_def_dst_rem": (C.c_int64, [C.c_void_p]),
     "dcmp_adler32": (C.c_uint32, [C.c_uint32, p_u8, C.c_int64]),
     "dcmp_crc32": (C.c_uint32, [C.c_uint32, p_u8, C.c_int64]),
 }

@@ -11,6 +11,7 @@
 #include <algorithm>
 #include <vector>
 #include "../../include/dcmp.h"
+#include "status_strings.h"
 
 namespace dcmp {
 void launch_inflate_serial(int fmt, int64_t n, const uint8_t *src_base, const int64_t *src_off, const int64_t *src_len,
@@ -43,6 +44,9 @@ int launch_deflate(int level, int fmt, int64_t nstreams, int64_t nchunks, const 
                    const int64_t *first_chunk, void *outs, uint8_t *slots, int64_t *chunk_dst, uint32_t *tok_scratch,
                    unsigned long long *work_counter, int ctas, uint8_t *dst_base, const int64_t *dst_off,
                    const int64_t *dst_cap, int64_t *written, int32_t *status, cudaStream_t stream);
+void launch_gzip_wrap(int64_t n, int level, int os, const uint8_t *src_base, const int64_t *src_off, const int64_t *src_len,
+                      uint8_t *dst_base, const int64_t *dst_off, const int64_t *dst_cap, int64_t *written, int32_t *status,
+                      cudaStream_t stream);
 size_t deflate_tok_bytes_per_cta();
 int deflate_ctas_per_sm();
 size_t deflate_slot_bytes();
@@ -122,29 +126,7 @@ int dcmp_device_count(void) {
 
 const char *dcmp_last_error(void) { return g_err; }
 
-const char *dcmp_status_string(int s) {
-  switch (s) {
-  case DCMP_OK: return "Ok";
-  case DCMP_UNEXPECTED_END_OF_INPUT: return "Unexpected end of input";
-  case DCMP_UNEXPECTED_END_OF_OUTPUT: return "Unexpected end of output";
-  case DCMP_INVALID_KIND_OF_BLOCK: return "Invalid kind of block";
-  case DCMP_INVALID_DICTIONARY: return "Invalid dictionary";
-  case DCMP_INVALID_COMPLEMENT_OF_LENGTH: return "Invalid complement of length";
-  case DCMP_INVALID_DISTANCE: return "Invalid distance";
-  case DCMP_INVALID_DISTANCE_CODE: return "Invalid distance code";
-  case DCMP_REF_EXCEPTION: return "Reference raises an exception (index out of bounds)";
-  case DCMP_INVALID_HEADER: return "Invalid header";
-  case DCMP_INVALID_CHECKSUM: return "Invalid checksum";
-  case DCMP_INVALID_GZIP_HEADER: return "Invalid GZip header";
-  case DCMP_INVALID_GZIP_HEADER_CHECKSUM: return "Invalid GZip header checksum";
-  case DCMP_INVALID_INPUT_SIZE: return "Invalid input size";
-  case DCMP_LZO_MALFORMED: return "Malformed";
-  case DCMP_LZO_INVALID_ARGUMENT: return "Input is malformed or output is not large enough";
-  case DCMP_LZO_INVALID_DICTIONARY: return "Invalid dictionary";
-  case DCMP_INVALID_COMPRESSION_LEVEL: return "Invalid compression level";
-  default: return "?";
-  }
-}
+const char *dcmp_status_string(int s) { return dcmp::status_string(s); }
 
 int dcmp_engine_create(int device, dcmp_engine **out) {
   if (!out) return DCMP_API_INVALID_ARGUMENT;
@@ -202,6 +184,7 @@ void dcmp_engine_destroy(dcmp_engine *e) {
 }
 
 int64_t dcmp_engine_launch_count(const dcmp_engine *e) { return e ? e->launches : 0; }
+int dcmp_engine_device(const dcmp_engine *e) { return e ? e->device : -1; }
 
 int dcmp_engine_stats(dcmp_engine *e, int64_t *out, int n_out) {
   if (!e || !out || n_out < 0) return DCMP_API_INVALID_ARGUMENT;
@@ -471,7 +454,7 @@ int64_t dcmp_deflate_bound(int64_t len, int fmt) {
   // De.Def.Ns.compress_bound (lib/de.ml:3993-3996), + 6 for zlib (lib/zl.ml:598)
   if (len < 0) return -1;
   int64_t blocks = std::max<int64_t>(1, (len + 9999) / 10000);
-  return 5 * blocks + len + 1 + 8 + (fmt == DCMP_FMT_ZLIB ? 6 : 0);
+  return 5 * blocks + len + 1 + 8 + (fmt == DCMP_FMT_ZLIB ? 6 : fmt == DCMP_FMT_GZIP ? 18 : 0);
 }
 
 int dcmp_deflate_batch_device(dcmp_engine *e, int level, int fmt, int64_t n, const uint8_t *d_src_base,
@@ -479,9 +462,25 @@ int dcmp_deflate_batch_device(dcmp_engine *e, int level, int fmt, int64_t n, con
                               const int64_t *h_dst_off, const int64_t *h_dst_cap, int64_t *d_written,
                               int32_t *d_status, void *cuda_stream) {
   if (!e || n < 0) return DCMP_API_INVALID_ARGUMENT;
-  if (fmt != DCMP_FMT_RAW && fmt != DCMP_FMT_ZLIB) return DCMP_API_INVALID_ARGUMENT;
+  // DCMP_DEFLATE_NO_FINAL: every block leaves with BFINAL = 0 and the output ends on a byte boundary (the streaming
+  // encoders, csrc/stream.cu, emit a stream segment by segment and close it themselves)
+  const bool no_final = (fmt & DCMP_DEFLATE_NO_FINAL) != 0;
+  fmt &= ~DCMP_DEFLATE_NO_FINAL;
+  if (fmt != DCMP_FMT_RAW && fmt != DCMP_FMT_ZLIB && fmt != DCMP_FMT_GZIP) return DCMP_API_INVALID_ARGUMENT;
+  if (no_final && fmt != DCMP_FMT_RAW) return DCMP_API_INVALID_ARGUMENT;
   if (n == 0) return DCMP_API_OK;
   if (!h_src_off || !h_src_len || !h_dst_off || !h_dst_cap || !d_written || !d_status) return DCMP_API_INVALID_ARGUMENT;
+  // gzip: the body is written 10 bytes into the window, the header and the CRC-32 / ISIZE trailer are added around
+  // it on the device (gzip_frame.cu)
+  const bool gz = fmt == DCMP_FMT_GZIP;
+  std::vector<int64_t> gz_off, gz_cap;
+  const int64_t *body_off = h_dst_off, *body_cap = h_dst_cap;
+  if (gz) {
+    gz_off.resize((size_t)n); gz_cap.resize((size_t)n);
+    for (int64_t k = 0; k < n; k++) { gz_off[k] = h_dst_off[k] + 10; gz_cap[k] = std::max<int64_t>(0, h_dst_cap[k] - 18); }
+    body_off = gz_off.data(); body_cap = gz_cap.data();
+    fmt = DCMP_FMT_RAW;
+  }
   CU(cudaSetDevice(e->device));
   cudaStream_t st = (cudaStream_t)cuda_stream;
   if (level < 0 || level > 12) {
@@ -502,7 +501,7 @@ int dcmp_deflate_batch_device(dcmp_engine *e, int level, int fmt, int64_t n, con
     int64_t pos = 0;
     do {
       int64_t m = std::min<int64_t>(CH, h_src_len[k] - pos);
-      dcmp::DfChunkHost c{h_src_off[k] + pos, (int32_t)m, (int32_t)k, (pos + m == h_src_len[k]) ? 1 : 0, (int32_t)std::min<int64_t>(pos, 32768)};
+      dcmp::DfChunkHost c{h_src_off[k] + pos, (int32_t)m, (int32_t)k, (!no_final && pos + m == h_src_len[k]) ? 1 : 0, (int32_t)std::min<int64_t>(pos, 32768)};
       chunks.push_back(c);
       pos += m;
     } while (pos < h_src_len[k]);
@@ -520,7 +519,11 @@ int dcmp_deflate_batch_device(dcmp_engine *e, int level, int fmt, int64_t n, con
   size_t o_first = align_up(o_cdst + (size_t)nc * 8, 256);
   size_t o_doff = align_up(o_first + (size_t)(n + 1) * 8, 256);
   size_t o_dcap = align_up(o_doff + (size_t)n * 8, 256);
-  size_t o_slots = align_up(o_dcap + (size_t)n * 8, 256);
+  size_t o_soff = align_up(o_dcap + (size_t)n * 8, 256);   // gzip only: the input table and the caller's windows
+  size_t o_slen = align_up(o_soff + (gz ? (size_t)n * 8 : 0), 256);
+  size_t o_goff = align_up(o_slen + (gz ? (size_t)n * 8 : 0), 256);
+  size_t o_gcap = align_up(o_goff + (gz ? (size_t)n * 8 : 0), 256);
+  size_t o_slots = align_up(o_gcap + (gz ? (size_t)n * 8 : 0), 256);
   size_t need = o_slots + (size_t)nc * slot + 256;
   if (need > e->def_arena_cap) {
     if (e->d_def_arena) { CU(cudaFree(e->d_def_arena)); e->d_def_arena = nullptr; e->def_arena_cap = 0; }
@@ -530,8 +533,14 @@ int dcmp_deflate_batch_device(dcmp_engine *e, int level, int fmt, int64_t n, con
   uint8_t *A = e->d_def_arena;
   CU(cudaMemcpyAsync(A + o_chunks, chunks.data(), (size_t)nc * sizeof(dcmp::DfChunkHost), cudaMemcpyHostToDevice, st));
   CU(cudaMemcpyAsync(A + o_first, first.data(), (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, st));
-  CU(cudaMemcpyAsync(A + o_doff, h_dst_off, (size_t)n * 8, cudaMemcpyHostToDevice, st));
-  CU(cudaMemcpyAsync(A + o_dcap, h_dst_cap, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(A + o_doff, body_off, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(A + o_dcap, body_cap, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+  if (gz) {
+    CU(cudaMemcpyAsync(A + o_soff, h_src_off, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(A + o_slen, h_src_len, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(A + o_goff, h_dst_off, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(A + o_gcap, h_dst_cap, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+  }
   unsigned long long *counter = (unsigned long long *)e->d_def_scratch;
   CU(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), st));
   int rc = dcmp::launch_deflate(level, fmt, n, nc, d_src_base, A + o_chunks, (const int64_t *)(A + o_first), A + o_outs,
@@ -540,6 +549,11 @@ int dcmp_deflate_batch_device(dcmp_engine *e, int level, int fmt, int64_t n, con
                                 d_written, d_status, st);
   if (rc != 0) { set_err("launch_deflate", (cudaError_t)rc); return DCMP_API_CUDA_ERROR; }
   e->launches += 3;
+  if (gz) {
+    dcmp::launch_gzip_wrap(n, level, 3 /* Unix */, d_src_base, (const int64_t *)(A + o_soff), (const int64_t *)(A + o_slen), d_dst_base,
+                           (const int64_t *)(A + o_goff), (const int64_t *)(A + o_gcap), d_written, d_status, st);
+    e->launches += 1;
+  }
   CU(cudaGetLastError());
   // the uploads above read host vectors that die with this frame
   CU(cudaStreamSynchronize(st));

@@ -177,6 +177,46 @@ gzip_trailer_kernel(int64_t n, const uint8_t *src_base, const int64_t *src_off, 
   }
 }
 
+
+// Gz.Def's framing around a DEFLATE body the deflate kernels wrote at dst + 10 (lib/gz.ml:794-813 header: magic, CM = 8,
+// FLG = 0, MTIME = 0 — big-endian in the reference, all zero here —, XFL = 2 for level 9 and above, OS; lib/gz.ml:725-733
+// trailer: CRC-32 and ISIZE of the input, little-endian).  One warp per stream; the CRC-32 of the input is folded
+// like gzip_trailer_kernel folds the output.
+__global__ void __launch_bounds__(128)
+gzip_wrap_kernel(int64_t n, int level, int os, const uint8_t *src_base, const int64_t *src_off, const int64_t *src_len,
+                 uint8_t *dst_base, const int64_t *dst_off, const int64_t *dst_cap, int64_t *written, int32_t *status) {
+  __shared__ uint32_t T8[8][256];
+  crc_build_slices(T8, threadIdx.x, blockDim.x);
+  const int lane = threadIdx.x & 31;
+  const int64_t k = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (k >= n) return;
+  if (status[k] != DCMP_OK) return;
+  if (dst_cap[k] < 18) { if (lane == 0) { status[k] = DCMP_UNEXPECTED_END_OF_OUTPUT; written[k] = 0; } return; }
+  const uint8_t *p = src_base + src_off[k];
+  const int64_t len = src_len[k];
+  const int64_t per = (len + 31) / 32;
+  const int64_t lo = per * lane < len ? per * lane : len, hi = lo + per < len ? lo + per : len;
+  uint32_t c = crc_bytes8(T8, lane == 0 ? 0xffffffffu : 0u, p + lo, hi - lo);
+  for (int s = 1; s < 32; s <<= 1) {
+    const uint32_t right = __shfl_down_sync(0xffffffffu, c, s);
+    const int64_t right_lo = __shfl_down_sync(0xffffffffu, lo, s);
+    const int64_t span_end = per * (lane + 2 * s) < len ? per * (lane + 2 * s) : len;
+    if (lane + s < 32 && (lane & (2 * s - 1)) == 0) {
+      const int64_t rlen = span_end - right_lo;
+      c = rlen > 0 ? gf2_mulmod(gf2_xpow8n((uint64_t)rlen), c) ^ right : c;
+    }
+  }
+  if (lane == 0) {
+    const uint32_t crc = ~c, isize = (uint32_t)len;
+    uint8_t *o = dst_base + dst_off[k];
+    const int64_t body = written[k];
+    const uint8_t hdr[10] = {0x1f, 0x8b, 8, 0, 0, 0, 0, 0, (uint8_t)(level >= 9 ? 2 : 0), (uint8_t)os};
+    for (int i = 0; i < 10; i++) o[i] = hdr[i];
+    uint8_t *t = o + 10 + body;
+    for (int i = 0; i < 4; i++) { t[i] = (uint8_t)(crc >> (8 * i)); t[4 + i] = (uint8_t)(isize >> (8 * i)); }
+    written[k] = body + 18;
+  }
+}
 #ifndef DCMP_EMU
 void launch_gzip_header(int64_t n, const uint8_t *src_base, const int64_t *src_off, const int64_t *src_len, int64_t *body_off,
                         int64_t *body_len, int32_t *pre_status, cudaStream_t stream) {
@@ -187,6 +227,12 @@ void launch_gzip_trailer(int64_t n, const uint8_t *src_base, const int64_t *src_
                          int64_t *produced, int32_t *status, cudaStream_t stream) {
   gzip_trailer_kernel<<<(unsigned)((n + 3) / 4), 128, 0, stream>>>(n, src_base, src_off, body_off, body_len, pre_status, dst_base,
                                                                   dst_off, consumed, produced, status);
+}
+void launch_gzip_wrap(int64_t n, int level, int os, const uint8_t *src_base, const int64_t *src_off, const int64_t *src_len,
+                      uint8_t *dst_base, const int64_t *dst_off, const int64_t *dst_cap, int64_t *written, int32_t *status,
+                      cudaStream_t stream) {
+  gzip_wrap_kernel<<<(unsigned)((n + 3) / 4), 128, 0, stream>>>(n, level, os, src_base, src_off, src_len, dst_base, dst_off, dst_cap,
+                                                               written, status);
 }
 #endif
 

@@ -19,6 +19,7 @@
 //   * after the final block consumed = ceil(c/8), or, when c ran past the input,
 //     n - ((8n - c) lsr 3) in 63-bit OCaml arithmetic (de.ml:1805).
 #include "inflate_tables.cuh"
+#include "inflate_stream.h"
 #include "simt.cuh"
 
 namespace dcmp {
@@ -117,7 +118,9 @@ __device__ int inflate_block(BitCursor &br, StreamOut &out, const uint32_t *lit,
   }
 }
 
-__device__ int decode_dynamic_header(BitCursor &br, WarpScratch &ws, int lane, TableInfo &li, TableInfo &di) {
+__device__ int build_dynamic_tables(WarpScratch &ws, int hlit, int hdist, int lane, TableInfo &li, TableInfo &di);
+__device__ int decode_dynamic_header(BitCursor &br, WarpScratch &ws, int lane, TableInfo &li, TableInfo &di,
+                                     int *hlit_out = nullptr, int *hdist_out = nullptr) {
   // de.ml:1788-1793
   br.refill();
   if (br.real_bits_left() < 14) return DCMP_UNEXPECTED_END_OF_INPUT;
@@ -177,8 +180,13 @@ __device__ int decode_dynamic_header(BitCursor &br, WarpScratch &ws, int lane, T
     prev = fillv;
     i += copy;
   }
+  if (hlit_out) { *hlit_out = hlit; *hdist_out = hdist; }
+  return build_dynamic_tables(ws, hlit, hdist, lane, li, di);
+}
+
+// de.ml:1718-1731: the two decode tables of a dynamic block from its code lengths (ws.lens[0 .. hlit + hdist))
+__device__ int build_dynamic_tables(WarpScratch &ws, int hlit, int hdist, int lane, TableInfo &li, TableInfo &di) {
   __syncwarp();
-  // de.ml:1718-1731
   if (ws.lens[256] == 0) return DCMP_INVALID_DICTIONARY;
   int rl = 0, rd = 0;
   if (lane == 0) {
@@ -352,6 +360,185 @@ inflate_serial_kernel(int fmt, int64_t nstreams, const uint8_t *src_base, const 
     status[k] = st;
   }
 }
+
+// ------------------------------------------------------------------------------------------------------------------
+// Resumable inflate of ONE stream: the device side of the streaming decoders (De.Inf.decoder / Zl.Inf / Gz.Inf behind
+// dcmp_inf_* in csrc/stream.cu).  One warp decodes from the saved state until the input runs out (the cursor goes
+// back to the last block header / token boundary: `Await), the launch's output budget is used up (`Flush), the final
+// block ends (`End) or the stream is malformed.  The window (WInf, de.ml:436-508) is a device ring that also takes
+// the output; code lengths of the block in progress live in the state, so a block of any size is decoded with
+// bounded memory.  At the end of the input (`eof`) a token that needs bits the input does not have is
+// "Unexpected end of input" (de.ml:760-762, 938-945); before that it just waits for them.
+struct RingOut {
+  uint8_t *ring;
+  int64_t mask;
+  int64_t pos;      // total bytes produced since the stream began
+  int64_t limit;    // pos may not pass this in this launch
+};
+
+enum : int { BR_EOB = -1, BR_AWAIT = -2, BR_FULL = -3 };
+
+__device__ int inflate_block_resumable(BitCursor &br, RingOut &out, const uint32_t *lit, int lit_root, const uint32_t *dist,
+                                       int dist_root, int lane, bool eof, int64_t *resume_bit) {
+  const int64_t nbits = 8 * br.n;
+  for (;;) {
+    const int64_t t0 = br.consumed_bits();
+    if (out.pos + 258 > out.limit) { *resume_bit = t0; return BR_FULL; }
+    // with fewer than 48 real bits ahead (the longest token: 15 + 5 + 15 + 13) and more input to come, nothing
+    // this token decodes to is final
+    const bool tentative = !eof && nbits - t0 < 48;
+    br.refill();
+    uint32_t e = lookup(lit, lit_root, br.hold);
+    uint32_t kind = e_kind(e);
+    if (kind == K_INVALID) { if (tentative) { *resume_bit = t0; return BR_AWAIT; } return br.consumed_bits() >= nbits ? DCMP_UNEXPECTED_END_OF_INPUT : DCMP_REF_EXCEPTION; }
+    br.drop(e_len(e));
+    if (kind == K_LIT) {
+      if (br.consumed_bits() > nbits) { if (!eof) { *resume_bit = t0; return BR_AWAIT; } return DCMP_UNEXPECTED_END_OF_INPUT; }
+      if (lane == 0) out.ring[out.pos & out.mask] = (uint8_t)e_base(e);
+      out.pos++;
+      continue;
+    }
+    if (kind == K_EOB) {
+      if (br.consumed_bits() > nbits) { if (!eof) { *resume_bit = t0; return BR_AWAIT; } return DCMP_UNEXPECTED_END_OF_INPUT; }
+      return BR_EOB;
+    }
+    int len = (int)e_base(e) + (int)br.pop(e_extra(e));
+    br.refill();
+    uint32_t d = lookup(dist, dist_root, br.hold);
+    if (e_kind(d) == K_INVALID) { if (tentative) { *resume_bit = t0; return BR_AWAIT; } return br.consumed_bits() >= nbits ? DCMP_UNEXPECTED_END_OF_INPUT : DCMP_REF_EXCEPTION; }
+    br.drop(e_len(d));
+    int64_t dd = (int64_t)e_base(d) + (int64_t)br.pop(e_extra(d));
+    if (br.consumed_bits() > nbits) { if (!eof) { *resume_bit = t0; return BR_AWAIT; } return DCMP_UNEXPECTED_END_OF_INPUT; }
+    if (e_base(d) == 0) return DCMP_INVALID_DISTANCE_CODE;                      // de.ml:1044
+    if (dd > (out.pos < 32768 ? out.pos : 32768)) return DCMP_INVALID_DISTANCE; // de.ml:1045: d > WInf.have
+    __syncwarp(); // earlier stores of every lane are visible to the loads below
+    for (int k = lane; k < len; k += 32) {
+      const int sk = dd >= len ? k : (int)(k % dd); // byte k repeats byte k mod dd: every source precedes out.pos
+      out.ring[(out.pos + k) & out.mask] = out.ring[(out.pos - dd + sk) & out.mask];
+    }
+    out.pos += len;
+  }
+}
+
+__global__ void __launch_bounds__(32)
+inflate_stream_kernel(const uint8_t *in, int64_t n_in, int eof, uint8_t *ring, int64_t max_out, InfStreamState *S) {
+  __shared__ WarpScratch ws;
+  const int lane = threadIdx.x;
+  BitCursor br;
+  br.init(in, n_in);
+  {
+    const int64_t b = S->bitpos;
+    br.pos = b >> 3;
+    br.refill();
+    br.drop((int)(b & 7)); // (a refill from pos loads 32 bits: 25..32 are left)
+  }
+  RingOut out{ring, STREAM_RING - 1, S->total_out, S->total_out + (max_out < STREAM_MAX_OUT ? max_out : STREAM_MAX_OUT)};
+  const int64_t out0 = out.pos;
+  int phase = S->phase, last = S->last, btype = S->btype, hlit = S->hlit, hdist = S->hdist;
+  int64_t stored_rem = S->stored_rem;
+  int64_t resume = S->bitpos;
+  int result = -1, status = DCMP_OK;
+  TableInfo li{0, 0}, di{0, 0};
+  if (phase == SP_CODED) { // the tables of the block in progress, from its saved code lengths
+    if (btype == 1) build_fixed_tables(ws, lane, li, di);
+    else {
+      for (int i = lane; i < hlit + hdist; i += 32) ws.lens[i] = S->lens[i];
+      status = build_dynamic_tables(ws, hlit, hdist, lane, li, di);
+      if (status != DCMP_OK) result = SR_ERROR; // (cannot happen: they were built from these lengths before)
+    }
+  }
+  while (result < 0) {
+    if (phase == SP_DONE) { result = SR_END; break; }
+    if (phase == SP_HEADER) {
+      resume = br.consumed_bits();
+      br.refill();
+      if (br.real_bits_left() < 3) {
+        if (!eof) result = SR_AWAIT; else { result = SR_ERROR; status = DCMP_UNEXPECTED_END_OF_INPUT; }
+        break;
+      }
+      last = (int)br.pop(1);
+      const uint32_t type = br.pop(2);
+      if (type == 3) { result = SR_ERROR; status = DCMP_INVALID_KIND_OF_BLOCK; break; }
+      if (type == 0) {
+        // de.ml:867-921: to the byte boundary, LEN, NLEN
+        const int64_t ip = (br.consumed_bits() + 7) >> 3;
+        if (n_in - ip < 4) {
+          if (!eof) result = SR_AWAIT; else { result = SR_ERROR; status = DCMP_UNEXPECTED_END_OF_INPUT; }
+          break;
+        }
+        const int len = in[ip] | (in[ip + 1] << 8), nlen = in[ip + 2] | (in[ip + 3] << 8);
+        if (nlen != 0xffff - len) { result = SR_ERROR; status = DCMP_INVALID_COMPLEMENT_OF_LENGTH; break; }
+        br.seek_byte(ip + 4);
+        stored_rem = len;
+        phase = SP_STORED;
+        resume = 8 * (ip + 4);
+      } else {
+        btype = (int)type;
+        if (type == 1) build_fixed_tables(ws, lane, li, di);
+        else {
+          status = decode_dynamic_header(br, ws, lane, li, di, &hlit, &hdist);
+          if (status == DCMP_UNEXPECTED_END_OF_INPUT && !eof) { status = DCMP_OK; result = SR_AWAIT; break; } // (resume: this header)
+          if (status != DCMP_OK) { result = SR_ERROR; break; }
+          __syncwarp();
+          for (int i = lane; i < hlit + hdist; i += 32) S->lens[i] = ws.lens[i];
+        }
+        phase = SP_CODED;
+        resume = br.consumed_bits();
+      }
+    }
+    if (phase == SP_STORED) {
+      // de.ml:837-865: raw bytes, as many as the input and this launch's budget hold
+      const int64_t ip = br.consumed_bits() >> 3;
+      int64_t m = stored_rem;
+      if (m > n_in - ip) m = n_in - ip;
+      if (m > out.limit - out.pos) m = out.limit - out.pos;
+      for (int64_t k = lane; k < m; k += 32) out.ring[(out.pos + k) & out.mask] = in[ip + k];
+      out.pos += m;
+      stored_rem -= m;
+      br.seek_byte(ip + m);
+      resume = 8 * (ip + m);
+      if (stored_rem > 0) {
+        if (out.pos >= out.limit) result = SR_FULL;
+        else if (!eof) result = SR_AWAIT;
+        else { result = SR_ERROR; status = DCMP_UNEXPECTED_END_OF_INPUT; }
+        break;
+      }
+      phase = last ? SP_DONE : SP_HEADER;
+      continue;
+    }
+    if (phase == SP_CODED) {
+      const int r = inflate_block_resumable(br, out, ws.lit, li.root, ws.dist, di.root, lane, eof != 0, &resume);
+      if (r == BR_EOB) { phase = last ? SP_DONE : SP_HEADER; resume = br.consumed_bits(); continue; }
+      if (r == BR_AWAIT) { result = SR_AWAIT; break; }
+      if (r == BR_FULL) { result = SR_FULL; break; }
+      result = SR_ERROR;
+      status = r;
+      break;
+    }
+  }
+  __syncwarp();
+  if (lane == 0) {
+    S->bitpos = (result == SR_END || result == SR_ERROR) ? br.consumed_bits() : resume;
+    if (result == SR_END) S->bitpos = resume;
+    S->total_out = out.pos;
+    S->produced = out.pos - out0;
+    S->phase = phase;
+    S->last = last;
+    S->btype = btype;
+    S->hlit = hlit;
+    S->hdist = hdist;
+    S->stored_rem = (int32_t)stored_rem;
+    S->result = result;
+    S->status = status;
+  }
+}
+
+#ifndef DCMP_EMU
+void launch_inflate_stream(const uint8_t *d_in, int64_t n_in, int eof, uint8_t *d_ring, int64_t max_out, void *d_state,
+                           cudaStream_t stream) {
+  inflate_stream_kernel<<<1, 32, 0, stream>>>(d_in, n_in, eof, d_ring, max_out, (InfStreamState *)d_state);
+}
+#endif
 
 #ifndef DCMP_EMU
 void launch_inflate_serial(int fmt, int64_t n, const uint8_t *src_base, const int64_t *src_off, const int64_t *src_len,

@@ -10,6 +10,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib, batch
+from . import stream as _stream
 from .de import _as_u8
 from .result import Error, Ok
 
@@ -50,15 +51,76 @@ def inflate_multi(buf, member_off, caps, engine=None):
     return inflate_members([m.tobytes() for m in members], caps, engine=engine)
 
 
-def inflate_multi_sequential(buf, cap_per_member, engine=None):
-    """The reference's way for a multi-member file without an index: decode a member, look at how much input it
-    consumed, start the next one there (the `End -> src_rem -> reset loop of lib/gz.ml:550, 582-610)."""
+def inflate_multi_sequential(buf, cap_per_member=None, engine=None, api=None, o_size=1 << 20):
+    """The reference's way for a multi-member file without an index (lib/gz.ml:550, 582-610): Gz.Inf answers `End after
+    ONE member; the caller looks at `src_rem` — how much of the input follows it —, resets the decoder and feeds the rest.
+    One pass over the input with the streaming decoder: nothing is decoded or uploaded twice."""
     buf = np.ascontiguousarray(_as_u8(buf))
-    pos, out = 0, []
-    while pos < buf.size:
-        st, cons, prod, data = inflate_members([buf[pos:].tobytes()], [cap_per_member], engine=engine)[0]
-        if st != 0:
-            return Error(_MSG.get(st, st)), out
-        out.append(data)
-        pos += cons
-    return Ok(len(out)), out
+    o = np.zeros(o_size, dtype=np.uint8)
+    d = _stream.InfDecoder("Manual", o, FMT_GZIP, api=api, engine=engine)
+    pos, out, cur = 0, [], bytearray()
+    step = 1 << 22
+    fed_end = 0          # input handed over so far
+    while True:
+        r = d.decode()
+        if r == "Await":
+            n = min(step, buf.size - fed_end)
+            d.src(buf, fed_end, n)   # n = 0: the end of the input
+            fed_end += n
+        elif r == "Flush":
+            cur += o[:len(o) - d.dst_rem()].tobytes()
+            d.flush()
+        elif r == "End":
+            out.append(bytes(cur))
+            cur = bytearray()
+            pos = fed_end - d.src_rem()   # where the next member starts
+            if pos >= buf.size:
+                return Ok(len(out)), out
+            d.reset()
+            fed_end = pos
+        else:
+            return Error(r[1].split(" (")[0]), out
+
+
+class Inf:
+    """Gz.Inf (gz.mli:56-149): decoder src ~o, decode, src, flush, reset, dst_rem, src_rem, write, filename, comment, os,
+    extra ~key — mirrors of dcmp_inf_* with DCMP_FMT_GZIP."""
+
+    @staticmethod
+    def decoder(src, o, engine=None, api=None):
+        return _stream.InfDecoder(src, o, FMT_GZIP, api=api, engine=engine)
+
+
+OS = ("FAT", "Amiga", "VMS", "Unix", "VM", "Atari", "HPFS", "Macintosh", "Z", "CPM", "TOPS20", "NTFS", "QDOS", "Acorn")  # gz.ml:231-246
+
+
+def os_of_int(v):
+    return OS[v] if 0 <= v < len(OS) else "Unknown"
+
+
+class Def:
+    """Gz.Def (gz.mli:160-265): encoder src dst ?ascii ?hcrc ?filename ?comment ~mtime os ~q ~w ~level."""
+
+    @staticmethod
+    def encoder(mtime, os, level, ascii=False, hcrc=False, filename=None, comment=None, q=None, w=None, engine=None, api=None):
+        os_v = OS.index(os) if isinstance(os, str) and os in OS else (255 if isinstance(os, str) else int(os))
+        gzp = dict(mtime=mtime, os=os_v, ascii=ascii, hcrc=hcrc, filename=filename, comment=comment)
+        return _stream.DefEncoder(FMT_GZIP, level, api=api, engine=engine, gz=gzp)
+
+
+class Higher:
+    """Gz.Higher (gz.mli:267-399): compress ?level (default 0... the reference's default is level 0, gz.ml:902-916) and
+    uncompress, which returns the member's metadata."""
+
+    @staticmethod
+    def compress(w, q, refill, flush, time, cfg, i, o, level=0, filename=None, comment=None, engine=None, api=None):
+        gzp = dict(mtime=int(time) & 0xFFFFFFFF, os=int(cfg.get("os", 255)) if isinstance(cfg, dict) else 255, ascii=False,
+                   hcrc=False, filename=filename, comment=comment)
+        _stream.compress(FMT_GZIP, level, refill, flush, i, o, api=api, engine=engine, gz=gzp)
+
+    @staticmethod
+    def uncompress(refill, flush, i, o, engine=None, api=None):
+        err, d = _stream.uncompress(FMT_GZIP, refill, flush, i, o, api=api, engine=engine)
+        if err is not None:
+            return Error(("Msg", err))
+        return Ok({"filename": d.filename(), "comment": d.comment(), "os": os_of_int(d.os())})

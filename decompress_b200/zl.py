@@ -4,6 +4,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
+from . import stream as _stream
 from .de import _as_u8
 from .result import Error, Ok
 
@@ -47,28 +48,32 @@ class Def:
             return Error(_lib.STATUS_TAG.get(st, st))
 
 
+def _inf_decoder(src, o, allocate=None, engine=None, api=None):
+    """Zl.Inf.decoder src ~o ~allocate (zl.mli:54-64).  The reference threads a persistent value through
+    decode / src / flush; here one mutable object plays every version of it.  `allocate` (the window) is accepted and
+    ignored: the window is a device ring."""
+    return _stream.InfDecoder(src, o, _lib.FMT_ZLIB, api=api, engine=engine)
+
+
+def _def_encoder(q, w, level, src=None, dst=None, dynamic=True, engine=None, api=None):
+    """Zl.Def.encoder ?dynamic ~q ~w ~level src dst (zl.mli:170-186); `q` / `w` are the reference's scratch for its serial
+    matcher and are ignored.  src / dst: "Manual" (use .src / .dst), as the C ABI's dcmp_def_*."""
+    return _stream.DefEncoder(_lib.FMT_ZLIB, level, api=api, engine=engine)
+
+
+Inf.decoder = staticmethod(_inf_decoder)
+Def.encoder = staticmethod(_def_encoder)
+
+
 class Higher:
-    """Zl.Higher (zl.mli:265-368): compress ?level (default 6, zl.ml:634) and uncompress over the batch engine."""
+    """Zl.Higher (zl.mli:265-368): compress ?level (default 6, zl.ml:634) and uncompress, the reference's refill / flush
+    loops over the streaming encoder / decoder."""
 
     @staticmethod
-    def compress(w, q, refill, flush, i, o, level=6, dynamic=True, engine=None):
-        from .de import _higher_compress
-        _higher_compress(_lib.FMT_ZLIB, level, refill, flush, i, o, engine)
+    def compress(w, q, refill, flush, i, o, level=6, dynamic=True, engine=None, api=None):
+        _stream.compress(_lib.FMT_ZLIB, level, refill, flush, i, o, api=api, engine=engine)
 
     @staticmethod
-    def uncompress(allocate, refill, flush, i, o, engine=None):
-        from .de import _InfDecoder
-        d = _InfDecoder("Manual", o, allocate(15) if allocate else None, engine, fmt=_lib.FMT_ZLIB)
-        while True:
-            r = d.decode()
-            if r == "Await":
-                n = refill(i)
-                d.src(i, 0, n)
-            elif r == "Flush":
-                flush(o, len(o) - d.dst_rem())
-                d.flush()
-            elif r == "End":
-                flush(o, len(o) - d.dst_rem())
-                return Ok(None)
-            else:
-                return Error(("Msg", r[1]))
+    def uncompress(allocate, refill, flush, i, o, engine=None, api=None):
+        err, _ = _stream.uncompress(_lib.FMT_ZLIB, refill, flush, i, o, api=api, engine=engine)
+        return Ok(None) if err is None else Error(("Msg", err))

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define DCMP_ABI_VERSION 1
+#define DCMP_ABI_VERSION 2
 
 /* ---- call-level return codes ------------------------------------------------ */
 enum {
@@ -75,6 +75,10 @@ enum {
                          parsed and checked on the device */
 };
 
+/* OR-ed into `fmt` of dcmp_deflate_batch_device (DCMP_FMT_RAW only): no block carries BFINAL and the output ends on a byte
+ * boundary — one segment of a stream the caller closes itself (what the streaming encoders below do). */
+#define DCMP_DEFLATE_NO_FINAL 0x100
+
 typedef struct dcmp_engine dcmp_engine;
 
 /* ---- engine ------------------------------------------------------------------
@@ -88,6 +92,7 @@ const char *dcmp_last_error(void);
 const char *dcmp_status_string(int status); /* lib/de.ml:1557-1567, lib/zl.ml:177-183 */
 /* Number of kernels this engine has launched since creation (bench.py's gpu_launches). */
 int64_t dcmp_engine_launch_count(const dcmp_engine *e);
+int dcmp_engine_device(const dcmp_engine *e);   /* the CUDA device ordinal the engine was created on */
 /* Counters of the two-stage dispatch since the engine was created (synchronises the device).  The fast kernels
  * (one CTA per stream / block) hand what they cannot finish — malformed or truncated input, output windows that
  * are too small, exotic code sets — to the general kernels; a benchmark whose streams are all valid must see
@@ -154,12 +159,14 @@ int dcmp_lzo_uncompress(dcmp_engine *e, const uint8_t *src, int64_t src_len, uin
  * pair De.Lz77.compress + De.Def.encode (lib/de.ml:4294-4515, 2465-3038) as driven by
  * De.Higher.compress / Zl.Higher.compress (lib/de.ml:4517-4560, lib/zl.ml:634-648).
  * level: 0 = stored blocks only, 1..12 = compressed (out of range: every status is
- * DCMP_INVALID_COMPRESSION_LEVEL, lib/de.ml:3930).  written[k] = bytes of the deflate (or zlib)
+ * DCMP_INVALID_COMPRESSION_LEVEL, lib/de.ml:3930).  fmt: DCMP_FMT_RAW, DCMP_FMT_ZLIB (header lib/zl.ml:511-522, Adler-32
+ * trailer) or DCMP_FMT_GZIP (Gz.Def's member: header lib/gz.ml:794-813 with FLG = 0, MTIME = 0, OS = Unix; CRC-32 + ISIZE
+ * trailer lib/gz.ml:725-733; both written on the device).  written[k] = bytes of the deflate (or zlib / gzip)
  * stream; a dst_cap[k] that is too small gives DCMP_UNEXPECTED_END_OF_OUTPUT (lib/de.ml:3061-3076);
  * dcmp_deflate_bound(len, fmt) is always enough.  The compressed bytes are NOT those of the
  * reference (its parse is sequential, lib/de.ml:4351-4410): the contract is that De.Inf and system
  * zlib inflate them back to the input. */
-int64_t dcmp_deflate_bound(int64_t len, int fmt); /* De.Def.Ns.compress_bound, lib/de.ml:3993-3996 (+6: lib/zl.ml:598) */
+int64_t dcmp_deflate_bound(int64_t len, int fmt); /* De.Def.Ns.compress_bound, lib/de.ml:3993-3996 (+6: lib/zl.ml:598; +18 gzip) */
 int dcmp_deflate_batch(dcmp_engine *e, int level, int fmt, int64_t n,
                        const uint8_t *src_base, const int64_t *src_off, const int64_t *src_len,
                        uint8_t *dst_base, const int64_t *dst_off, const int64_t *dst_cap,
@@ -176,6 +183,70 @@ int dcmp_def_ns_deflate(dcmp_engine *e, int level, const uint8_t *src, int64_t s
                         uint8_t *dst, int64_t dst_len, int64_t *written);
 int dcmp_zl_def_ns_deflate(dcmp_engine *e, int level, const uint8_t *src, int64_t src_len,
                            uint8_t *dst, int64_t dst_len, int64_t *written);
+
+/* ---- streaming decoders ---------------------------------------------------------
+ * The non-blocking half of the reference's interface: De.Inf.decoder / decode / src / flush / dst_rem / src_rem /
+ * checksum / reset (lib/de.mli:82-148, lib/de.ml:651-753, 1427-1532) for fmt = DCMP_FMT_RAW, Zl.Inf (lib/zl.mli:30-124,
+ * lib/zl.ml:141-309) for DCMP_FMT_ZLIB, Gz.Inf (lib/gz.mli:56-149, lib/gz.ml:248-634) for DCMP_FMT_GZIP.  A decoder is
+ * a host state machine over a resumable device kernel (csrc/inflate_serial.cu: inflate_stream_kernel): `decode` runs it
+ * on the input handed over so far, so output appears before the end of the input and memory is bounded — one
+ * undecodable tail of input (a block header, a token), one launch's worth of output (<= 1 MiB) and the 32 KiB window.
+ * Protocol, as in the reference (README.md:93-109):
+ *   DCMP_AWAIT      the input is used up: dcmp_inf_src(d, buf, len), len = 0 for the end of the input (de.ml:739)
+ *   DCMP_FLUSH      `o` holds o_len - dcmp_inf_dst_rem(d) bytes; take them and call dcmp_inf_flush(d).  For zlib / gzip
+ *                   the answer repeats until flush is called (lib/zl.ml:288-291, test/test.ml:1536-1568), and the bytes
+ *                   that sit in `o` when the DEFLATE data ends leave with a DCMP_FLUSH before DCMP_END (zl.ml:295-306)
+ *   DCMP_END        the stream is complete (trailer checked); `o` holds the last o_len - dst_rem bytes (raw) or nothing
+ *   DCMP_MALFORMED  dcmp_inf_status(d) is the DCMP_* code, dcmp_inf_error(d) the reference's message ("Invalid
+ *                   checksum (expect:…, has:…)", "Invalid Zlib header", … lib/zl.ml:177-183, lib/gz.ml:285-296); the
+ *                   decoder then answers DCMP_END for ever (continuation `final`, de.ml:700)
+ * `buf` of dcmp_inf_src must stay valid until the next DCMP_AWAIT.  dcmp_inf_src_rem at DCMP_END = bytes of the last
+ * input that follow the stream (Gz.Inf.src_rem, gz.ml:550: where a next member would start).  dcmp_inf_checksum:
+ * Adler-32 (CRC-32 for gzip) of everything written to `o`; dcmp_inf_write: their count (Zl.Inf.write). */
+enum { DCMP_AWAIT = 0, DCMP_FLUSH = 1, DCMP_END = 2, DCMP_MALFORMED = 3 };
+typedef struct dcmp_inf dcmp_inf;
+int dcmp_inf_new(dcmp_engine *e, int fmt, uint8_t *o, int64_t o_len, dcmp_inf **out);
+void dcmp_inf_free(dcmp_inf *d);
+int dcmp_inf_src(dcmp_inf *d, const uint8_t *buf, int64_t len);
+int dcmp_inf_dst(dcmp_inf *d, uint8_t *o, int64_t o_len);   /* a new output buffer (Zl.Inf has none: convenience) */
+int dcmp_inf_decode(dcmp_inf *d);                           /* DCMP_AWAIT .. DCMP_MALFORMED, or DCMP_API_* < 0 */
+int dcmp_inf_status(const dcmp_inf *d);
+const char *dcmp_inf_error(const dcmp_inf *d);
+int64_t dcmp_inf_dst_rem(const dcmp_inf *d);
+int64_t dcmp_inf_src_rem(const dcmp_inf *d);
+void dcmp_inf_flush(dcmp_inf *d);
+void dcmp_inf_reset(dcmp_inf *d);
+uint32_t dcmp_inf_checksum(const dcmp_inf *d);
+int64_t dcmp_inf_write(const dcmp_inf *d);
+int64_t dcmp_inf_launches(const dcmp_inf *d);               /* kernels this decoder has launched */
+int64_t dcmp_inf_buffered(const dcmp_inf *d);               /* bytes it holds: undecoded input + undelivered output */
+/* Gz.Inf.os / filename / comment / extra (lib/gz.ml:612-633).  which: 0 FNAME, 1 FCOMMENT, 2 the raw FEXTRA payload
+ * (sub-fields: 2-byte key, big-endian 16-bit length, gz.ml:628); returns the length, -1 for None. */
+int dcmp_gz_inf_os(const dcmp_inf *d);
+uint32_t dcmp_gz_inf_mtime(const dcmp_inf *d);
+int64_t dcmp_gz_inf_field(const dcmp_inf *d, int which, const uint8_t **p);
+
+/* ---- streaming encoders ---------------------------------------------------------
+ * Zl.Def.encoder / encode / src / dst (lib/zl.mli:141-263, lib/zl.ml:421-592), Gz.Def (lib/gz.mli:160-265,
+ * lib/gz.ml:636-900) and, for DCMP_FMT_RAW, the pair De.Lz77.compress + De.Def.encode as De.Higher.compress glues
+ * it (lib/de.ml:4517-4560).  Input is gathered into segments of 4 MiB that the batch deflate kernels compress
+ * (every block BFINAL = 0 and a byte-aligned end, until the last segment); framing and its checksums are host work.
+ *   DCMP_AWAIT  dcmp_def_src(d, buf, len), len = 0 for the end of the input
+ *   DCMP_FLUSH  `o` is full, or the trailer has been written: take o_len - dcmp_def_dst_rem(d) bytes, then dcmp_def_dst
+ *   DCMP_END    everything has been flushed (`o` is empty: test/test.ml:1597-1625)
+ * level 0..9 (De.Lz77.state, de.ml:4431-4437).  dcmp_def_gz_header: Gz.Def.encoder's ?ascii ?hcrc ?filename ?comment
+ * ~mtime os, before the first encode (header bytes as lib/gz.ml:794-813: MTIME big-endian, FHCRC = upper half of the
+ * CRC-32 of the fixed bytes + FNAME + FCOMMENT). */
+typedef struct dcmp_def dcmp_def;
+int dcmp_def_new(dcmp_engine *e, int fmt, int level, dcmp_def **out);
+void dcmp_def_free(dcmp_def *d);
+int dcmp_def_gz_header(dcmp_def *d, uint32_t mtime, int os, int ascii, int hcrc, const uint8_t *filename,
+                       int64_t filename_len, const uint8_t *comment, int64_t comment_len);
+int dcmp_def_src(dcmp_def *d, const uint8_t *buf, int64_t len);
+int dcmp_def_dst(dcmp_def *d, uint8_t *buf, int64_t len);
+int dcmp_def_encode(dcmp_def *d);                           /* DCMP_AWAIT, DCMP_FLUSH, DCMP_END, or DCMP_API_* < 0 */
+int64_t dcmp_def_src_rem(const dcmp_def *d);
+int64_t dcmp_def_dst_rem(const dcmp_def *d);
 
 /* ---- checksums (host; checkseum's Adler32 / Crc32 as used at lib/zl.ml:231-245,
  * lib/gz.ml:344-356) ------------------------------------------------------------ */

@@ -84,3 +84,43 @@ def deflate_streams(inputs, caps, level=6, fmt=0):
     L.emu_deflate_batch.argtypes = [C.c_int, C.c_int, C.c_int64] + [C.c_void_p] * 8
     L.emu_deflate_batch(level, fmt, n, p(src), p(so), p(sl), p(dst), p(do), p(dc), p(wr), p(st))
     return [(int(st[k]), int(wr[k]), dst[do[k]:do[k] + int(wr[k])].tobytes()) for k in range(n)]
+
+
+class StreamApi:
+    """The streaming state machines of the product (csrc/stream_core.h) instantiated over the emulator back ends
+    (tests/simt_emu/emu_stream.h): same entry points as decompress_b200.stream.ProductApi, prefix emu_ instead of dcmp_."""
+    _SIG = {
+        "inf_new": (C.c_void_p, [C.c_int, C.c_void_p, C.c_int64]), "inf_free": (None, [C.c_void_p]),
+        "inf_src": (None, [C.c_void_p, C.c_void_p, C.c_int64]), "inf_decode": (C.c_int, [C.c_void_p]),
+        "inf_status": (C.c_int, [C.c_void_p]), "inf_error": (C.c_char_p, [C.c_void_p]), "inf_dst_rem": (C.c_int64, [C.c_void_p]),
+        "inf_src_rem": (C.c_int64, [C.c_void_p]), "inf_flush": (None, [C.c_void_p]), "inf_reset": (None, [C.c_void_p]),
+        "inf_checksum": (C.c_uint32, [C.c_void_p]), "inf_write": (C.c_int64, [C.c_void_p]), "inf_launches": (C.c_int64, [C.c_void_p]),
+        "inf_buffered": (C.c_int64, [C.c_void_p]), "gz_inf_os": (C.c_int, [C.c_void_p]),
+        "gz_inf_field": (C.c_int64, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]),
+        "def_new": (C.c_void_p, [C.c_int, C.c_int, C.c_int64]), "def_free": (None, [C.c_void_p]),
+        "def_gz_header": (None, [C.c_void_p, C.c_uint32, C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_int64, C.c_char_p, C.c_int64]),
+        "def_src": (None, [C.c_void_p, C.c_void_p, C.c_int64]), "def_dst": (None, [C.c_void_p, C.c_void_p, C.c_int64]),
+        "def_encode": (C.c_int, [C.c_void_p]), "def_src_rem": (C.c_int64, [C.c_void_p]), "def_dst_rem": (C.c_int64, [C.c_void_p]),
+    }
+
+    def __init__(self, seg_bytes=1 << 18):
+        self.L = lib()
+        self.seg_bytes = seg_bytes
+        for name, (res, args) in self._SIG.items():
+            fn = getattr(self.L, "emu_" + name)
+            fn.restype, fn.argtypes = res, args
+
+    def inf_new(self, fmt, o_ptr, o_len):
+        return C.c_void_p(self.L.emu_inf_new(fmt, o_ptr, o_len))
+
+    def inf_src(self, h, p, n):
+        self.L.emu_inf_src(h, p, n)
+        return 0
+
+    def def_new(self, fmt, level):
+        if not 0 <= level <= 9:
+            raise ValueError("Invalid level")
+        return C.c_void_p(self.L.emu_def_new(fmt, level, self.seg_bytes))
+
+    def __getattr__(self, name):
+        return getattr(self.L, "emu_" + name)

@@ -9,6 +9,11 @@
 #include "../../decompress_b200/csrc/lzo_parallel.cu"
 #include "../../decompress_b200/csrc/deflate.cu"
 
+static int64_t dcmp_deflate_bound_emu(int64_t len) { // De.Def.Ns.compress_bound (de.ml:3993-3996)
+  int64_t blocks = std::max<int64_t>(1, (len + 9999) / 10000);
+  return 5 * blocks + len + 1 + 8;
+}
+
 extern "C" {
 
 // mode 0: parallel kernel, then the general kernel on the streams it gave up (like engine.cu)
@@ -65,6 +70,8 @@ int emu_lzo_batch(int mode, int64_t n, const uint8_t *src, const int64_t *soff, 
 int emu_deflate_batch(int level, int fmt, int64_t n, const uint8_t *src, const int64_t *soff, const int64_t *slen, uint8_t *dst,
                       const int64_t *doff, const int64_t *dcap, int64_t *written, int32_t *status) {
   using namespace dcmp;
+  const bool no_final = (fmt & DCMP_DEFLATE_NO_FINAL) != 0; // (engine.cu: one segment of a stream the caller closes)
+  fmt &= ~DCMP_DEFLATE_NO_FINAL;
   std::vector<DfChunk> chunks;
   std::vector<int64_t> first(n + 1);
   for (int64_t k = 0; k < n; k++) {
@@ -72,7 +79,7 @@ int emu_deflate_batch(int level, int fmt, int64_t n, const uint8_t *src, const i
     int64_t pos = 0;
     do {
       int64_t m = std::min<int64_t>(DF_CHUNK, slen[k] - pos);
-      chunks.push_back(DfChunk{soff[k] + pos, (int32_t)m, (int32_t)k, (pos + m == slen[k]) ? 1 : 0, (int32_t)std::min<int64_t>(pos, 32768)});
+      chunks.push_back(DfChunk{soff[k] + pos, (int32_t)m, (int32_t)k, (!no_final && pos + m == slen[k]) ? 1 : 0, (int32_t)std::min<int64_t>(pos, 32768)});
       pos += m;
     } while (pos < slen[k]);
   }
@@ -98,5 +105,19 @@ int emu_deflate_batch(int level, int fmt, int64_t n, const uint8_t *src, const i
 }
 
 long emu_switches() { return simt::g_switches; }
+} // extern "C"
+#include "emu_stream.h"
+int EmuDefBackend::deflate(int level, const uint8_t *in, int64_t n, bool final, std::vector<uint8_t> &out) {
+  int64_t zero = 0, len = n, cap = dcmp_deflate_bound_emu(n) + 64 * ((n >> 16) + 2), written = 0;
+  int32_t status = -1;
+  std::vector<uint8_t> dst((size_t)cap + 16);
+  std::vector<uint8_t> src(in, in + n);
+  src.resize((size_t)n + 16);
+  emu_deflate_batch(level, DCMP_FMT_RAW | (final ? 0 : DCMP_DEFLATE_NO_FINAL), 1, src.data(), &zero, &len, dst.data(), &zero, &cap, &written, &status);
+  if (status != DCMP_OK) return DCMP_API_CUDA_ERROR;
+  out.insert(out.end(), dst.begin(), dst.begin() + written);
+  return DCMP_API_OK;
+}
+extern "C" {
 void emu_stats(long *out) { memcpy(out, &dcmp::g_stats, sizeof(dcmp::g_stats)); memset(&dcmp::g_stats, 0, sizeof(dcmp::g_stats)); }
 }

@@ -20,6 +20,7 @@
 #include <string.h>
 #include <ucontext.h>
 #include <functional>
+#include <string>
 #include <vector>
 
 #define __global__

@@ -18,7 +18,7 @@ def test_exports_every_declared_symbol():
 
 def test_abi_version_and_strings():
     lib = _lib.lib()
-    assert lib.dcmp_abi_version() == 1
+    assert lib.dcmp_abi_version() == 2
     # de.ml:1557-1567
     want = {1: "Unexpected end of input", 2: "Unexpected end of output", 3: "Invalid kind of block",
             4: "Invalid dictionary", 5: "Invalid complement of length", 6: "Invalid distance",

@@ -9,7 +9,8 @@ import numpy as np
 import pytest
 
 import workloads
-from decompress_b200 import Error, Ok, _lib, gz
+from decompress_b200 import Error, Ok, _lib, batch, gz
+from tests import oracle
 
 pytestmark = pytest.mark.gpu
 
@@ -90,3 +91,24 @@ def test_python_gzip_interop_and_multi_member_c4(eng):
     py = gzip.compress(members[0][1], 6)
     d = np.zeros(len(members[0][1]), dtype=np.uint8)
     assert gz.inflate_member(py, d, engine=eng) == Ok((len(py), len(members[0][1]))) and d.tobytes() == members[0][1]
+
+
+def test_gzip_deflate_batch_members_on_the_device(eng):
+    """DCMP_FMT_GZIP in dcmp_deflate_batch (Gz.Def's framing, lib/gz.ml:794-813, 725-733, written on the device): Python's
+    gzip module, the oracle's CRC-32 and our own gzip inflate take the members back."""
+    txt = workloads.text(900000, 31)
+    ins = [txt, b"", b"a", txt[:65536], txt[:70001], bytes(200000)]
+    for level in (0, 6, 9):
+        res = batch.deflate_streams(ins, level=level, fmt=_lib.FMT_GZIP, engine=eng)
+        comps = []
+        for k, (st, wr, comp) in enumerate(res):
+            assert st == 0 and wr == len(comp) <= _lib.lib().dcmp_deflate_bound(len(ins[k]), _lib.FMT_GZIP), (level, k)
+            assert comp[:10] == bytes([0x1f, 0x8b, 8, 0, 0, 0, 0, 0, 2 if level >= 9 else 0, 3])
+            assert gzip.decompress(comp) == ins[k], (level, k)
+            assert comp[-8:] == (oracle.crc32(ins[k]) & 0xFFFFFFFF).to_bytes(4, "little") + len(ins[k]).to_bytes(4, "little")
+            comps.append(comp)
+        back = batch.inflate_streams(comps, [len(x) for x in ins], fmt=_lib.FMT_GZIP, engine=eng)
+        for k, (st, cons, prod, out) in enumerate(back):
+            assert (st, cons, prod) == (0, len(comps[k]), len(ins[k])) and out == ins[k], (level, k)
+    st, wr, comp = batch.deflate_streams([txt], [17], level=6, fmt=_lib.FMT_GZIP, engine=eng)[0]
+    assert st == 2 and wr == 0      # Unexpected_end_of_output: no room for the framing

@@ -8,7 +8,8 @@ import numpy as np
 import pytest
 
 import workloads
-from decompress_b200 import Ok, _lib, de
+from decompress_b200 import Ok, _lib, de, stream
+from tests import test_stream_protocol as P
 
 pytestmark = pytest.mark.gpu
 G = os.path.join(os.path.dirname(__file__), "golden")
@@ -17,6 +18,26 @@ G = os.path.join(os.path.dirname(__file__), "golden")
 @pytest.fixture(scope="module")
 def eng():
     return _lib.Engine(0)
+
+
+@pytest.fixture(scope="module")
+def api(eng):
+    """The product's entry points (dcmp_inf_* / dcmp_def_* on the B200) for the protocol cases of test_stream_protocol.py."""
+    return stream.ProductApi(eng)
+
+
+# the reference's sequences and golden bytes (test/test.ml:1450-1496, 1536-1758, 1906-1989), through libdcmp_b200.so
+test_kats_c_abi = P.test_stream_kats
+test_multiple_flush_zlib = P.test_multiple_flush_zlib
+test_empty_zlib = P.test_empty_zlib_end_at_once_small_output_and_byte_per_byte
+test_git_object_two_manual_chunks = P.test_git_object_two_manual_chunks
+test_output_before_the_end_of_input_and_bounded_memory = P.test_output_before_the_end_of_input_and_bounded_memory
+test_de_inf_truncated_and_trailing_input = P.test_de_inf_truncated_and_trailing_input
+test_gzip_reference_vectors = P.test_gzip_reference_vectors
+test_multi_member_gzip_sequential_loop = P.test_multi_member_gzip_sequential_loop
+test_zl_def_encoder_streams = P.test_zl_def_encoder_streams
+test_gz_def_encoder_header_bytes_and_roundtrip = P.test_gz_def_encoder_header_bytes_and_roundtrip
+test_higher_loops = P.test_higher_loops
 
 
 def _vectors():
