@@ -59,6 +59,8 @@ _SIGNATURES = {
     "dcmp_def_ns_deflate": (C.c_int, [C.c_void_p, C.c_int, p_u8, C.c_int64, p_u8, C.c_int64, C.POINTER(C.c_int64)]),
     "dcmp_zl_def_ns_deflate": (C.c_int, [C.c_void_p, C.c_int, p_u8, C.c_int64, p_u8, C.c_int64, C.POINTER(C.c_int64)]),
     "dcmp_engine_device": (C.c_int, [C.c_void_p]),
+    "dcmp_host_register": (C.c_int, [C.c_void_p, C.c_int64]),
+    "dcmp_host_unregister": (C.c_int, [C.c_void_p]),
     # streaming decoders / encoders (csrc/stream.cu)
     "dcmp_inf_new": (C.c_int, [C.c_void_p, C.c_int, p_u8, C.c_int64, C.POINTER(C.c_void_p)]),
     "dcmp_inf_free": (None, [C.c_void_p]),

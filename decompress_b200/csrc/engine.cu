@@ -615,6 +615,23 @@ int dcmp_zl_def_ns_deflate(dcmp_engine *e, int level, const uint8_t *src, int64_
   return def_ns(e, level, DCMP_FMT_ZLIB, src, src_len, dst, dst_len, written);
 }
 
+// Page-lock a caller's buffer (an OCaml Bigarray is pageable malloc memory): host<->device copies of a registered
+// buffer run at the PCIe rate and asynchronously, those of a pageable one go through the driver's staging buffer.
+int dcmp_host_register(void *p, int64_t n) {
+  if (!p || n <= 0) return DCMP_API_INVALID_ARGUMENT;
+  cudaError_t e = cudaHostRegister(p, (size_t)n, cudaHostRegisterDefault);
+  if (e == cudaErrorHostMemoryAlreadyRegistered) { cudaGetLastError(); return DCMP_API_OK; }
+  CU(e);
+  return DCMP_API_OK;
+}
+int dcmp_host_unregister(void *p) {
+  if (!p) return DCMP_API_INVALID_ARGUMENT;
+  cudaError_t e = cudaHostUnregister(p);
+  if (e == cudaErrorHostMemoryNotRegistered) { cudaGetLastError(); return DCMP_API_OK; }
+  CU(e);
+  return DCMP_API_OK;
+}
+
 uint32_t dcmp_adler32(uint32_t adler, const uint8_t *p, int64_t n) {
   uint32_t a = adler & 0xffff, b = (adler >> 16) & 0xffff;
   while (n > 0) {

@@ -248,6 +248,12 @@ int dcmp_def_encode(dcmp_def *d);                           /* DCMP_AWAIT, DCMP_
 int64_t dcmp_def_src_rem(const dcmp_def *d);
 int64_t dcmp_def_dst_rem(const dcmp_def *d);
 
+/* ---- caller buffers ----------------------------------------------------------------
+ * The *_batch calls take host pointers.  A `bigstring` (Bigarray.Array1, lib/de.mli:45) is pageable malloc memory:
+ * register long-lived io buffers once (cudaHostRegister) and the copies run at the PCIe rate, asynchronously. */
+int dcmp_host_register(void *p, int64_t n);
+int dcmp_host_unregister(void *p);
+
 /* ---- checksums (host; checkseum's Adler32 / Crc32 as used at lib/zl.ml:231-245,
  * lib/gz.ml:344-356) ------------------------------------------------------------ */
 uint32_t dcmp_adler32(uint32_t adler, const uint8_t *p, int64_t n);

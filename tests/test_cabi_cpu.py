@@ -1,5 +1,6 @@
 """CPU-only checks of the drop-in boundary: the C-ABI library loads, exports every symbol
 include/dcmp.h declares, and refuses to compute without a CUDA device (no CPU fallback)."""
+import os
 import ctypes as C
 
 import pytest
@@ -47,3 +48,20 @@ def test_no_device_is_a_loud_failure():
         _lib.Engine(0)
     h = C.c_void_p()
     assert _lib.lib().dcmp_engine_create(0, C.byref(h)) == _lib.API_NO_DEVICE
+
+
+def test_ocaml_shim_is_consistent_with_the_c_abi():
+    """ocaml/ cannot be compiled here (no OCaml toolchain): hold it to the header at least — every dcmp_* call of the
+    stubs is a declared entry point, every `external` of dcmp.ml has its CAMLprim (native and bytecode names)."""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    stubs = open(os.path.join(root, "ocaml", "dcmp_stubs.c")).read()
+    ml = open(os.path.join(root, "ocaml", "dcmp.ml")).read()
+    declared = set(_lib.declared_symbols())
+    called = set(re.findall(r"\b(dcmp_(?!stub_)[a-z0-9_]+)\s*\(", stubs))
+    assert called <= declared, sorted(called - declared)
+    prims = set(re.findall(r"CAMLprim value (dcmp_stub_[a-z0-9_]+)", stubs))
+    wanted = set(re.findall(r'"(dcmp_stub_[a-z0-9_]+)"', ml))
+    assert wanted <= prims, sorted(wanted - prims)
+    for f in ("de.ml", "zl.ml", "gz.ml", "lzo.ml", "dune"):
+        assert os.path.exists(os.path.join(root, "ocaml", f))
