@@ -233,6 +233,182 @@ def run_reference(args, rank):
     print(json.dumps(line), flush=True)
 
 
+
+def run_c4(args, rank, local_rank, world):
+    """BASELINE config C4 — Gz.Inf of concatenated gzip members (16..256 KiB payloads), STRONG scaling over the GPUs of
+    one node: the whole file lives on rank 0's GPU; per step the member index is broadcast, every rank receives the
+    contiguous slab of members `shard.partition` gives it (NCCL point-to-point over NVLink), inflates it with CRC-32 /
+    ISIZE checked on the device, and its output slab goes back to rank 0 — in pieces, each sent while the next one is
+    being decoded.  value = inflated bytes of the whole file / step time (max over ranks)."""
+    import torch
+    import torch.distributed as dist
+
+    from decompress_b200 import _lib, batch, shard
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    eng = _lib.Engine(local_rank)
+    total = args.c4_mib << 20
+    pieces_per_rank = max(1, args.c4_pieces)
+    # ---- rank 0: the file and its index, resident in HBM before the timed region
+    if rank == 0:
+        t0 = time.time()
+        members, sizes = workloads.c4_blob(total, seed=0)
+        lens = np.array([len(m) for m in members], dtype=np.int64)
+        offs = np.concatenate([[0], np.cumsum(lens)[:-1]]).astype(np.int64)
+        blob_h = np.frombuffer(b"".join(members), dtype=np.uint8)
+        del members
+        index = np.stack([offs, lens, sizes], axis=1)
+        blob = torch.from_numpy(blob_h.copy()).to(dev)
+        out_full = torch.empty(int(sizes.sum()) + 64, dtype=torch.uint8, device=dev)
+        gen_s = time.time() - t0
+    else:
+        index, blob, out_full, gen_s = None, None, None, 0.0
+
+    def one_step(timers=None):
+        ev = lambda: torch.cuda.Event(enable_timing=True)
+        marks = [ev() for _ in range(4)]
+        marks[0].record()
+        idx = shard.broadcast_index(index, 0, dev) if world > 1 else index
+        n = idx.shape[0]
+        parts = shard.partition(idx[:, 1] + idx[:, 2], world)
+        ends_c = np.concatenate([[0], np.cumsum(idx[:, 1])])
+        ends_o = np.concatenate([[0], np.cumsum(idx[:, 2])])
+        ranges_c = [(int(ends_c[a]), int(ends_c[b])) for a, b in parts]
+        ranges_o = [(int(ends_o[a]), int(ends_o[b])) for a, b in parts]
+        if world > 1:
+            local, works = shard.scatter_slab(blob, ranges_c, 0, None, dev)
+            for w in works:
+                w.wait()
+        else:
+            local = blob[ranges_c[0][0]:ranges_c[0][1]]
+        marks[1].record()
+        a, b = parts[rank]
+        m = b - a
+        so = torch.from_numpy((idx[a:b, 0] - ends_c[a]).astype(np.int64)).to(dev)
+        sl = torch.from_numpy(idx[a:b, 1].astype(np.int64)).to(dev)
+        do_h = (ends_o[a:b] - ends_o[a]).astype(np.int64)
+        do = torch.from_numpy(do_h).to(dev)
+        dc = torch.from_numpy(idx[a:b, 2].astype(np.int64)).to(dev)
+        my_out = out_full[ranges_o[0][0]:ranges_o[0][1]] if rank == 0 else torch.empty(ranges_o[rank][1] - ranges_o[rank][0] + 64, dtype=torch.uint8, device=dev)
+        cons = torch.zeros(max(m, 1), dtype=torch.int64, device=dev)
+        prod = torch.zeros(max(m, 1), dtype=torch.int64, device=dev)
+        st = torch.zeros(max(m, 1), dtype=torch.int32, device=dev)
+        # pieces: contiguous member ranges of about equal output; a piece leaves for rank 0 as soon as it is decoded
+        def cuts_of(r):
+            ra, rb = parts[r]
+            if rb == ra:
+                return []
+            w = idx[ra:rb, 2]
+            ps = shard.partition(w, min(pieces_per_rank, rb - ra))
+            return [(x, y) for x, y in ps if y > x]
+        my_cuts = cuts_of(rank)
+        all_cuts = [cuts_of(r) for r in range(world)]
+        works = []
+        npieces = max(len(c) for c in all_cuts) if all_cuts else 0
+        for p in range(npieces):
+            if p < len(my_cuts):
+                x, y = my_cuts[p]
+                batch.inflate_device(_lib.FMT_GZIP, local, so[x:y], sl[x:y], my_out, do[x:y], dc[x:y], cons[x:y], prod[x:y], st[x:y], engine=eng)
+            if world > 1:
+                ops = []
+                if rank == 0:
+                    for r in range(1, world):
+                        if p < len(all_cuts[r]):
+                            x, y = all_cuts[r][p]
+                            ra = parts[r][0]
+                            lo = int(ends_o[ra + x]); hi = int(ends_o[ra + y])
+                            ops.append(dist.P2POp(dist.irecv, out_full[lo:hi], r))
+                elif p < len(my_cuts):
+                    x, y = my_cuts[p]
+                    lo = int(do_h[x]); hi = int(do_h[y - 1] + idx[a + y - 1, 2])
+                    ops.append(dist.P2POp(dist.isend, my_out[lo:hi], 0))
+                if ops:
+                    works += dist.batch_isend_irecv(ops)
+        marks[2].record()
+        for w in works:
+            w.wait()
+        marks[3].record()
+        if timers is not None:
+            torch.cuda.synchronize()
+            timers.append([marks[k].elapsed_time(marks[k + 1]) for k in range(3)])
+        return st, prod, m, n, int(ends_c[-1]), int(ends_o[-1])
+
+    W = max(3, args.warmup)
+    for _ in range(W):
+        st, prod, m, n, job_src, job_out = one_step()
+    torch.cuda.synchronize()
+    assert m == 0 or int(st[:m].abs().sum().item()) == 0, "a gzip member failed (CRC-32 / ISIZE are checked on the device)"
+    s0 = eng.stats()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler.arm()
+    l0 = eng.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        st, prod, m, n, job_src, job_out = one_step()
+    ev1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms = ev0.elapsed_time(ev1)
+    launches = eng.launch_count() - l0
+    clocks = sampler.stop()
+    s1 = eng.stats()
+    assert m == 0 or (int(st[:m].abs().sum().item()) == 0 and int(prod[:m].sum().item()) > 0)
+    assert s1["inflate_redone"] == s0["inflate_redone"], "a valid member fell back to the general kernel"
+    phases = []
+    for _ in range(3):
+        one_step(phases)     # untimed: where a step's time goes (scatter | decode (+ overlapped sends) | waiting for the last pieces)
+    ph = np.median(np.array(phases), axis=0)
+    if rank == 0:  # every byte of the gathered file is checked once, after the timed region: CRC-32 of each member's payload
+        import zlib
+        outh = out_full[:job_out].cpu().numpy()
+        e_o = np.concatenate([[0], np.cumsum(index[:, 2])])
+        step = max(1, n // 512)
+        for k in list(range(0, n, step)) + [n - 1]:
+            tr = blob_h[index[k, 0] + index[k, 1] - 8: index[k, 0] + index[k, 1] - 4]
+            assert zlib.crc32(outh[e_o[k]:e_o[k + 1]].tobytes()) == int.from_bytes(tr.tobytes(), "little"), "member %d" % k
+    if world > 1:
+        tt = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms = float(tt[0])
+        pp = torch.tensor(ph, dtype=torch.float64, device=dev)
+        dist.all_reduce(pp, op=dist.ReduceOp.MAX)
+        ph = pp.cpu().numpy()
+    if rank == 0:
+        peak, peak_src = load_peaks()
+        ms_step = ms / args.steps
+        value = job_out / (ms_step * 1e-3) / 1e9
+        line = {"metric": "inflate_uncompressed_GBps", "value": round(value, 3), "unit": "GB/s", "n_gpus": world, "steps": args.steps,
+                "warmup": W, "ms_per_step": round(ms_step, 4), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "u8", "data": "synthetic",
+                "config": {"workload": "C4: Gz.Inf of %d MiB of concatenated gzip members (%d members, 16..256 KiB payloads of "
+                                       "synthetic text, ratio %.2f:1), the file resident on rank 0's GPU, sharded over %d GPU(s) by member "
+                                       "ranges" % (args.c4_mib, n, job_out / job_src, world),
+                           "members": int(n), "compressed_bytes": int(job_src), "inflated_bytes": int(job_out),
+                           "parallelism": "index broadcast + NCCL point-to-point scatter of compressed slabs + gather of output slabs "
+                                          "in %d pieces per rank, each sent while the next is decoded" % pieces_per_rank,
+                           "l2": "working set %d MiB per step > 126 MB L2" % ((job_src + job_out) >> 20)},
+                "roofline": {"bound": "hbm", "achieved": round((job_src + job_out) / world / (ph[1] * 1e-3) / 1e9, 2), "peak": peak, "unit": "GB/s",
+                             "frac": round((job_src + job_out) / world / (ph[1] * 1e-3) / 1e9 / peak, 4), "traffic": None,
+                             "kernel": "gzip_header + inflate_parallel + gzip_trailer over one rank's share, timed as the decode phase "
+                                       "of a step (median of 3 untimed steps)", "peak_source": peak_src},
+                "phases_ms": {"index_broadcast_and_scatter": round(float(ph[0]), 3), "decode_with_overlapped_sends": round(float(ph[1]), 3),
+                              "waiting_for_the_last_pieces": round(float(ph[2]), 3)},
+                "collective_share": round(float(ph[0] + ph[2]) / float(ph.sum()), 3),
+                "gpu_launches": int(launches), "clocks": clocks, "generated_in_s": round(gen_s, 1)}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -241,6 +417,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--streams", type=int, default=4096, help="streams per GPU (C2 = 4096)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="c2", choices=["c2", "c4"], help="c2: BASELINE's quoted config (default); c4: multi-member gzip, strong scaling")
+    ap.add_argument("--c4-mib", type=int, default=8192, help="inflated size of the C4 file (BASELINE: 8 GiB)")
+    ap.add_argument("--c4-pieces", type=int, default=4, help="output pieces per rank (a piece is sent while the next is decoded)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -248,6 +427,9 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "reference":
         run_reference(args, rank)
+        return
+    if args.workload == "c4":
+        run_c4(args, rank, local_rank, world)
         return
 
     import torch

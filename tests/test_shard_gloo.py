@@ -85,3 +85,66 @@ def test_bench_reference_arm_two_ranks():
     line = json.loads(outs[0].splitlines()[-1])
     assert line["impl"] == "reference" and line["value"] > 0 and line["cpu_baseline"]["kind"] == "port"
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and outs[1] == ""
+
+
+def _worker_c4(rank, world, port, q):
+    """A batch that lives on rank 0 (BASELINE C4): index broadcast, scatter of compressed slabs, decode, gather of the
+    output slabs in pieces — shard.py's collectives over gloo; the CPU oracle stands in for the GPU (test infrastructure)."""
+    import torch
+    import torch.distributed as dist
+
+    sys.path.insert(0, ROOT)
+    from tests import oracle
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    index = blob = out_full = None
+    if rank == 0:
+        members = workloads.c4_members(400000, seed=3, lo=8000, hi=60000)
+        lens = np.array([len(m) for m, _ in members], dtype=np.int64)
+        sizes = np.array([len(p) for _, p in members], dtype=np.int64)
+        offs = np.concatenate([[0], np.cumsum(lens)[:-1]])
+        index = np.stack([offs, lens, sizes], axis=1)
+        blob = torch.from_numpy(np.frombuffer(b"".join(m for m, _ in members), dtype=np.uint8).copy())
+        out_full = torch.zeros(int(sizes.sum()), dtype=torch.uint8)
+    idx = shard.broadcast_index(index, 0)
+    parts = shard.partition(idx[:, 1] + idx[:, 2], world)
+    ec, eo = np.concatenate([[0], np.cumsum(idx[:, 1])]), np.concatenate([[0], np.cumsum(idx[:, 2])])
+    rc_ = [(int(ec[a]), int(ec[b])) for a, b in parts]
+    ro = [(int(eo[a]), int(eo[b])) for a, b in parts]
+    local, works = shard.scatter_slab(blob, rc_, 0)
+    for w in works:
+        w.wait()
+    a, b = parts[rank]
+    mine = torch.zeros(ro[rank][1] - ro[rank][0], dtype=torch.uint8)
+    lb = local.numpy().tobytes()
+    for k in range(a, b):
+        body = lb[idx[k, 0] - ec[a] + 10: idx[k, 0] - ec[a] + idx[k, 1] - 8]          # (no optional header fields)
+        st, cons, prod, out = oracle.inflate_ns(body, int(idx[k, 2]))
+        assert st == 0 and prod == idx[k, 2]
+        mine[eo[k] - eo[a]: eo[k + 1] - eo[a]] = torch.from_numpy(np.frombuffer(out, dtype=np.uint8).copy())
+    half = (ro[1][1] - ro[1][0]) // 2
+    pieces = [[(0, ro[0][1] - ro[0][0])], [(0, half), (half, ro[1][1] - ro[1][0])]]
+    for w in shard.gather_slab(mine, out_full, ro, 0, pieces=pieces):
+        w.wait()
+    dist.barrier()
+    if rank == 0:
+        q.put((out_full.numpy().tobytes() == b"".join(p for _, p in members), [list(p) for p in parts]))
+    dist.destroy_process_group()
+
+
+def test_two_ranks_gloo_scatter_decode_gather():
+    import torch.multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    world, port = 2, 31500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_worker_c4, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    same, parts = q.get(timeout=180)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert same and parts[0][1] == parts[1][0] and parts[0][0] == 0 and parts[0][1] > 0

@@ -129,6 +129,31 @@ def c4_members(total_plain, seed=0, lo=16 << 10, hi=256 << 10):
     return out
 
 
+def _c4_one(args):
+    size, seed = args
+    return gzip_member(text(size, seed))
+
+
+def c4_blob(total_plain, seed=0, lo=16 << 10, hi=256 << 10, workers=None):
+    """BASELINE config C4 at full size: gzip members with log-uniform 16..256 KiB payloads of the C3 text until
+    `total_plain` bytes, generated by a process pool.  Returns (list of member bytes, int64 array of payload sizes);
+    the plaintexts are not kept — a member's CRC-32 and ISIZE trailer is what the decoder is checked against."""
+    rng = np.random.default_rng(seed)
+    sizes, have = [], 0
+    while have < total_plain:
+        size = min(int(np.exp(rng.uniform(np.log(lo), np.log(hi)))), total_plain - have)
+        sizes.append(size)
+        have += size
+    jobs = [(sz, seed * 1000003 + k) for k, sz in enumerate(sizes)]
+    workers = workers or min(32, os.cpu_count() or 1)
+    if workers > 1 and len(jobs) >= 64:
+        with ProcessPoolExecutor(workers) as ex:
+            members = list(ex.map(_c4_one, jobs, chunksize=max(1, len(jobs) // (workers * 8))))
+    else:
+        members = [_c4_one(j) for j in jobs]
+    return members, np.array(sizes, dtype=np.int64)
+
+
 _MINILZO = None
 
 
