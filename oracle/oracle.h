@@ -74,6 +74,10 @@ int orc_lzo_uncompress(const uint8_t *src, int64_t src_len, uint8_t *dst,
 int orc_lzo_uncompress_with_buffer(const uint8_t *src, int64_t src_len, uint8_t *dst,
                                    int64_t dst_len, int64_t *consumed, int64_t *produced);
 
+/* deflate_t.c: De.T.make (de.ml:2013-2068) and one Dynamic block of Def over Queue commands (de.ml:2387-2407, 2583-2897) */
+int orc_t_make(int length, int max_length, int *freqs, int *tree_lengths, int *tree_codes, int *bl_count);
+int64_t orc_def_encode_dynamic(const int32_t *cmds, int64_t n, int last, uint8_t *out, int64_t cap, int *h);
+
 #ifdef __cplusplus
 }
 #endif

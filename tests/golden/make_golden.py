@@ -421,6 +421,49 @@ def manual_lzo(path):
     return out
 
 
+def extract_encoder(path):
+    """The encoder-side known answers of test/test.ml: huffman_length_extra (507-531: commands -> 16 bytes), tree_0
+    (1169-1190), the rfc5322 histogram and the two (length, code) pairs it pins (1192-1237), the level-0 Ns block
+    (test_ns.ml:1189-1222 is in inflate_ns.json's neighbourhood; its bytes are pinned in tests/test_gpu_deflate.py)."""
+    text = open(path).read()
+    lines = text.split("\n")
+
+    def line_of(needle):
+        return next(i + 1 for i, l in enumerate(lines) if needle in l)
+
+    out = {}
+    a = text.index('Alcotest.test_case "huffman length extra"')
+    blk = text[a:text.index("let fuzz10 ()", a)]
+    m = re.search(r'"encoding" res "((?:[^"\\]|\\.)*)"', blk)
+    raw = m.group(1)
+    # OCaml string escapes: \ddd is DECIMAL
+    b = bytearray()
+    i = 0
+    while i < len(raw):
+        if raw[i] == "\\" and raw[i + 1].isdigit():
+            b.append(int(raw[i + 1:i + 4])); i += 4
+        elif raw[i] == "\\":
+            b.append({"n": 10, "t": 9, "\\": 92, '"': 34}[raw[i + 1]]); i += 2
+        else:
+            b.append(ord(raw[i])); i += 1
+    assert "`Literal '\\000'; `Literal '\\000'; `Copy (1, 258); `Copy (1, 256)" in " ".join(blk.split())
+    copy = lambda off, ln: 0x2000000 | ((ln - 3) << 16) | (off - 1)   # Queue.cmd, lib/de.ml:2245-2266
+    out["huffman_length_extra"] = {"cite": "test/test.ml:%d" % line_of('"huffman length extra"'),
+                                   "cmds": [0, 0, copy(1, 258), copy(1, 256), 256], "last": True, "bytes": bytes(b).hex()}
+    a = text.index('Alcotest.test_case "rfc5322 corpus literals/lengths freqs"')
+    blk = text[a:text.index("let compress_and_uncompress", a)]
+    arr = blk[blk.index("[|") + 2:blk.index("|]")]
+    freqs = [int(x) for x in re.split(r"[;\s]+", arr.strip()) if x]
+    assert len(freqs) == 2 * 286 + 1
+    m6 = re.search(r'"literal 6" \((\d+), (0x[0-9a-f]+)\)', blk)
+    me = re.search(r'"eob" \((\d+), (0x[0-9a-f]+)\)', blk)
+    out["tree_rfc5322"] = {"cite": "test/test.ml:%d" % line_of('"rfc5322 corpus literals/lengths freqs"'), "freqs": freqs,
+                           "literal_6": [int(m6.group(1)), int(m6.group(2), 16)], "eob": [int(me.group(1)), int(me.group(2), 16)]}
+    out["tree_0"] = {"cite": "test/test.ml:%d" % line_of('"empty literals/lengths freqs"'), "lengths": [[0, 1], [256, 1]],
+                     "codes": [[0, 0], [256, 1]]}
+    return out
+
+
 def main():
     ns, ns_skip = extract_ns(os.path.join(REF, "test/test_ns.ml"))
     st, st_skip = extract_stream(os.path.join(REF, "test/test.ml"))
@@ -438,6 +481,10 @@ def main():
         print("%s: %d vectors, %d skipped" % (fn, len(vec), len(sk)))
         for s in sk:
             print("   skipped %-34s %s (%s)" % (s["name"], s["cite"], s["reason"]))
+    enc = extract_encoder(os.path.join(REF, "test/test.ml"))
+    with open(os.path.join(HERE, "encoder.json"), "w") as f:
+        json.dump({"source": "mirage/decompress v1.6.0 (1b61f758), extracted by tests/golden/make_golden.py", "kats": enc}, f, indent=1)
+    print("encoder.json: %d known answers" % len(enc))
 
 
 if __name__ == "__main__":

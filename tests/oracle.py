@@ -76,3 +76,36 @@ def bench_batch(fmt, src, src_off, src_len, dst, dst_off, dst_cap, threads):
     secs = L.orc_bench_batch(fmt, n, p(src), p(src_off), p(src_len), p(dst), p(dst_off), p(dst_cap), p(cons), p(prod),
                              p(status), int(threads))
     return secs, status, prod
+
+
+def t_make(freqs, length, max_length=15):
+    """De.T.make ~length ?max_length freqs (oracle/deflate_t.c): (lengths[0..length), codes[0..length), max_code)."""
+    import numpy as np
+
+    L = lib()
+    L.orc_t_make.restype = C.c_int
+    L.orc_t_make.argtypes = [C.c_int, C.c_int] + [C.c_void_p] * 4
+    f = np.zeros(2 * 286 + 1, dtype=np.int32)
+    f[:len(freqs)] = np.asarray(freqs, dtype=np.int32)[:2 * 286 + 1]
+    lens = np.zeros(2 * 286 + 2, dtype=np.int32)
+    codes = np.zeros(2 * 286 + 2, dtype=np.int32)
+    blc = np.zeros(16, dtype=np.int32)
+    mc = L.orc_t_make(length, max_length, C.c_void_p(f.ctypes.data), C.c_void_p(lens.ctypes.data), C.c_void_p(codes.ctypes.data),
+                      C.c_void_p(blc.ctypes.data))
+    return lens[:length].tolist(), codes[:length].tolist(), mc
+
+
+def def_encode_dynamic(cmds, last=True):
+    """One Dynamic block of De.Def over Queue commands (oracle/deflate_t.c): (bytes, (h_lit, h_dst, h_len))."""
+    import numpy as np
+
+    L = lib()
+    L.orc_def_encode_dynamic.restype = C.c_int64
+    L.orc_def_encode_dynamic.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_int64, C.c_void_p]
+    a = np.asarray(cmds, dtype=np.int32)
+    out = np.zeros(8 * len(a) + 1024, dtype=np.uint8)
+    h = np.zeros(3, dtype=np.int32)
+    n = L.orc_def_encode_dynamic(C.c_void_p(a.ctypes.data), len(a), int(bool(last)), C.c_void_p(out.ctypes.data), len(out),
+                                 C.c_void_p(h.ctypes.data))
+    assert n >= 0
+    return out[:n].tobytes(), tuple(h.tolist())
