@@ -59,10 +59,12 @@ struct DfChunkOut {
   uint32_t pad;
 };
 
-struct DfTree {            // Huffman construction scratch; only alive after tokenising, so it overlays the hash table
-  uint32_t sortbuf[512];
-  uint32_t weight[2 * 288];
-  uint16_t parent[2 * 288];
+constexpr int DF_HEAP = 2 * 286 + 1;   // zlib's HEAP_SIZE (de.ml:233)
+struct DfTree {            // De.T.make's state (de.ml:2013-2026); only alive after tokenising, so it overlays the hash table
+  uint32_t freq[DF_HEAP + 3];   // leaves [0, length), then the internal nodes
+  uint16_t heap[DF_HEAP + 3];
+  uint16_t dad[DF_HEAP + 3];
+  uint16_t depth[DF_HEAP + 3];  // depth of a subtree while the tree is built (up to 285), then the bit length of every node
 };
 template <int HB>
 struct DfSmemT {
@@ -177,92 +179,105 @@ struct DfBits {
   }
 };
 
-// ---- Huffman code construction (one warp) ------------------------------------------------------
-// freq[0..n) -> len[0..n) (<= max_bits) and bit-reversed canonical codes.  Follows the shape of
-// De.T.make / zlib build_tree (de.ml:2013-2068): at least two codes, overflow repair as in gen_bitlen.
+// ---- Huffman code construction ------------------------------------------------------------------
+// freq[0..n) -> len[0..n) (<= max_bits) and bit-reversed canonical codes: De.T.make (de.ml:2013-2068), i.e. zlib's
+// build_tree / gen_bitlen / gen_codes step for step — heap ordered by (frequency, depth), at least two codes (de.ml:1862-1874),
+// overflow repair (de.ml:1978-2009) — so the code lengths are the REFERENCE's, not just valid ones (test/test.ml:1169-1237:
+// "the same tree as zlib").  The merge loop is a chain of dependent heap moves: one lane runs it (a few hundred
+// microseconds per 64 KiB chunk at most, ~2 % of a chunk's time; the other lanes of the SM's warps fill the gaps).
+// Returns max_code (the highest symbol with a code), the same in every lane.
 template <class SM>
-__device__ void df_build_code(SM &S, const uint32_t *freq, int n, int max_bits, uint8_t *len, uint16_t *code, int lane) {
+__device__ int df_build_code(SM &S, const uint32_t *freq, int n, int max_bits, uint8_t *len, uint16_t *code, int lane) {
+  DfTree &T = S.tree;
   __syncwarp();
-  // keys (freq << 9 | sym) of the used symbols, padded for the sorting network
-  for (int i = lane; i < 512; i += 32) S.tree.sortbuf[i] = 0xffffffffu;
-  for (int i = lane; i < n; i += 32) len[i] = 0;
+  for (int i = lane; i < n; i += 32) { T.freq[i] = freq[i]; len[i] = 0; code[i] = 0; }
   __syncwarp();
+  int max_code = -1;
   if (lane == 0) {
-    int m = 0;
-    for (int s = 0; s < n; s++)
-      if (freq[s]) S.tree.sortbuf[m++] = (freq[s] << 9) | (uint32_t)s;
-    // the pkzip rule (de.ml:1863-1874): force at least two codes
-    if (m == 0) { S.tree.sortbuf[0] = (1u << 9) | 0u; S.tree.sortbuf[1] = (1u << 9) | 1u; m = 2; }
-    else if (m == 1) { uint32_t s0 = S.tree.sortbuf[0] & 511u; S.tree.sortbuf[1] = (1u << 9) | (s0 == 0 ? 1u : 0u); m = 2; }
-    S.n_rle = m; // (reused as a scratch scalar: number of leaves)
-  }
-  __syncwarp();
-  const int m = S.n_rle;
-  // bitonic sort of 512 keys, 16 per lane
-  for (int k = 2; k <= 512; k <<= 1) {
-    for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int t = lane; t < 256; t += 32) {
-        const int i = ((t / j) * 2 * j) + (t % j); // lower index of the pair
-        const int p = i + j;
-        const bool up = (i & k) == 0;
-        const uint32_t a = S.tree.sortbuf[i], b = S.tree.sortbuf[p];
-        if ((a > b) == up) { S.tree.sortbuf[i] = b; S.tree.sortbuf[p] = a; }
+    auto smaller = [&](int a, int b) { return T.freq[a] < T.freq[b] || (T.freq[a] == T.freq[b] && T.depth[a] <= T.depth[b]); };
+    int heap_len = 0, heap_max = DF_HEAP;
+    auto down = [&](int k) { // pqdownheap, de.ml:1879-1898
+      const int v = T.heap[k];
+      int j = k << 1;
+      while (j <= heap_len) {
+        if (j < heap_len && smaller(T.heap[j + 1], T.heap[j])) j++;
+        if (smaller(v, T.heap[j])) break;
+        T.heap[k] = T.heap[j];
+        k = j;
+        j <<= 1;
       }
-      __syncwarp();
+      T.heap[k] = (uint16_t)v;
+    };
+    for (int s = 0; s < n; s++) {
+      T.depth[s] = 0; // (a symbol that is not used keeps length 0, de.ml:1849-1853)
+      if (T.freq[s] != 0) { T.heap[++heap_len] = (uint16_t)s; max_code = s; }
     }
-  }
-  if (lane == 0) {
-    // two-queue Huffman: leaves 0..m-1 (ascending), internal nodes m..2m-2 (created in ascending weight)
-    for (int i = 0; i < m; i++) S.tree.weight[i] = S.tree.sortbuf[i] >> 9;
-    int li = 0, ii = m, nn = m;
-    while (nn < 2 * m - 1) {
-      uint32_t w = 0;
-      for (int k = 0; k < 2; k++) {
-        int pick;
-        if (li < m && (ii >= nn || S.tree.weight[li] <= S.tree.weight[ii])) pick = li++;
-        else pick = ii++;
-        w += S.tree.weight[pick];
-        S.tree.parent[pick] = (uint16_t)nn;
-      }
-      S.tree.weight[nn++] = w;
+    while (heap_len < 2) { // the pkzip rule
+      const int node = max_code < 2 ? ++max_code : 0;
+      T.freq[node] = 1;
+      T.heap[++heap_len] = (uint16_t)node;
+      T.depth[node] = 0;
     }
-    // depths (a parent always has a larger index), folded into bl_count with the overflow repair of gen_bitlen
+    for (int k = heap_len / 2; k >= 1; k--) down(k);
+    int node = n;
+    do {
+      const int a = T.heap[1];
+      T.heap[1] = T.heap[heap_len--];
+      down(1);
+      const int b = T.heap[1];
+      T.heap[--heap_max] = (uint16_t)a;
+      T.heap[--heap_max] = (uint16_t)b;
+      T.freq[node] = T.freq[a] + T.freq[b];
+      T.depth[node] = (uint16_t)((T.depth[a] >= T.depth[b] ? T.depth[a] : T.depth[b]) + 1);
+      T.dad[a] = (uint16_t)node;
+      T.dad[b] = (uint16_t)node;
+      T.heap[1] = (uint16_t)node++;
+      down(1);
+    } while (heap_len >= 2);
+    T.heap[--heap_max] = T.heap[1];
+    // generate_lengths (de.ml:1952-2009); depth[] becomes the bit length of every node
     int bl_count[16];
-    for (int b = 0; b < 16; b++) bl_count[b] = 0;
-    S.tree.weight[2 * m - 2] = 0; // weight[] now holds depths
+    for (int bq = 0; bq < 16; bq++) bl_count[bq] = 0;
+    T.depth[T.heap[heap_max]] = 0;
     int overflow = 0;
-    for (int i = 2 * m - 3; i >= 0; i--) {
-      uint32_t d = S.tree.weight[S.tree.parent[i]] + 1;
-      S.tree.weight[i] = d;
-      if (i < m) {
-        if ((int)d > max_bits) { d = (uint32_t)max_bits; overflow++; }
-        bl_count[d]++;
+    for (int h = heap_max + 1; h < DF_HEAP; h++) {
+      const int m = T.heap[h];
+      int bits = T.depth[T.dad[m]] + 1;
+      if (bits > max_bits) { bits = max_bits; overflow++; }
+      T.depth[m] = (uint16_t)bits;
+      if (m <= max_code) bl_count[bits]++;
+    }
+    if (overflow != 0) {
+      do {
+        int bits = max_bits - 1;
+        while (bl_count[bits] == 0) bits--;
+        bl_count[bits]--;
+        bl_count[bits + 1] += 2;
+        bl_count[max_bits]--;
+        overflow -= 2;
+      } while (overflow > 0);
+      int h = DF_HEAP;
+      for (int bits = max_bits; bits >= 1; bits--) {
+        int c = bl_count[bits];
+        while (c != 0) {
+          const int m = T.heap[--h];
+          if (m <= max_code) { T.depth[m] = (uint16_t)bits; c--; }
+        }
       }
     }
-    while (overflow > 0) {
-      int bits = max_bits - 1;
-      while (bl_count[bits] == 0) bits--;
-      bl_count[bits]--;
-      bl_count[bits + 1] += 2;
-      bl_count[max_bits]--;
-      overflow -= 2;
-    }
-    // longest codes to the least frequent symbols
-    int i = 0;
-    for (int bits = max_bits; bits >= 1; bits--)
-      for (int c = bl_count[bits]; c > 0; c--) len[S.tree.sortbuf[i++] & 511u] = (uint8_t)bits;
-    // canonical codes, bit-reversed (de.ml:1910-1924)
+    // generate_codes (de.ml:1926-1950): canonical, bit-reversed
     uint32_t next_code[16];
     uint32_t c = 0;
     next_code[0] = 0;
     for (int bits = 1; bits <= max_bits; bits++) { c = (c + (uint32_t)bl_count[bits - 1]) << 1; next_code[bits] = c; }
-    // (bl_count[0] is 0 here: unused symbols do not take part)
-    for (int s = 0; s < n; s++) {
-      const int l = len[s];
+    for (int s = 0; s <= max_code; s++) {
+      const int l = T.depth[s];
+      len[s] = (uint8_t)l;
       code[s] = l ? (uint16_t)(__brev(next_code[l]++) >> (32 - l)) : 0;
     }
   }
   __syncwarp();
+  return __shfl_sync(0xffffffffu, max_code, 0);
 }
 
 // Adler-32 partials of p[0..n): sum of bytes and sum of (n - j) * p[j], both mod 65521.
@@ -415,35 +430,44 @@ __device__ void df_compress_chunk(SM &S, const uint8_t *d, int len, int hist, bo
     if (lane == 0) { S.freq_l[256] = 1; S.extra_bits = my_extra; }
     __syncwarp();
     // ---------------------------------------------------------------- 2 build
-    df_build_code(S, S.freq_l, 286, 15, S.len_l, S.code_l, lane);
-    df_build_code(S, S.freq_d, 30, 15, S.len_d, S.code_d, lane);
+    const int l_max = df_build_code(S, S.freq_l, 286, 15, S.len_l, S.code_l, lane);
+    const int d_max = df_build_code(S, S.freq_d, 30, 15, S.len_d, S.code_d, lane);
     if (lane == 0) {
-      // code-length RLE (zlib scan_tree / send_tree; the reference's T.scan / T.symbols, de.ml:2100-2192)
-      int hlit = 286, hdist = 30;
-      while (hlit > 257 && S.len_l[hlit - 1] == 0) hlit--;
-      while (hdist > 1 && S.len_d[hdist - 1] == 0) hdist--;
+      // code-length RLE: T.scan + T.symbols (de.ml:2070-2190, zlib's scan_tree / send_tree), the literal/length tree and
+      // the distance tree one after the other — a run never crosses from one into the other
       for (int i = 0; i < 19; i++) S.freq_bl[i] = 0;
-      const int total = hlit + hdist;
-      int nr = 0, i = 0;
-      while (i < total) {
-        const int l = i < hlit ? S.len_l[i] : S.len_d[i - hlit];
-        int run = 1;
-        while (i + run < total && (i + run < hlit ? S.len_l[i + run] : S.len_d[i + run - hlit]) == l) run++;
-        int left = run;
-        if (l == 0) {
-          while (left >= 11) { int c = left > 138 ? 138 : left; S.rle_sym[nr] = 18; S.rle_extra[nr++] = (uint8_t)(c - 11); S.freq_bl[18]++; left -= c; }
-          if (left >= 3) { S.rle_sym[nr] = 17; S.rle_extra[nr++] = (uint8_t)(left - 3); S.freq_bl[17]++; left = 0; }
-          while (left > 0) { S.rle_sym[nr] = 0; S.rle_extra[nr++] = 0; S.freq_bl[0]++; left--; }
-        } else {
-          S.rle_sym[nr] = (uint8_t)l; S.rle_extra[nr++] = 0; S.freq_bl[l]++; left--;
-          while (left >= 3) { int c = left > 6 ? 6 : left; S.rle_sym[nr] = 16; S.rle_extra[nr++] = (uint8_t)(c - 3); S.freq_bl[16]++; left -= c; }
-          while (left > 0) { S.rle_sym[nr] = (uint8_t)l; S.rle_extra[nr++] = 0; S.freq_bl[l]++; left--; }
+      int nr = 0;
+      for (int which = 0; which < 2; which++) {
+        const uint8_t *tl = which ? S.len_d : S.len_l;
+        const int max_code = which ? d_max : l_max;
+        int prevlen = -1, nextlen = tl[0], count = 0, max_count = 7, min_count = 4;
+        if (nextlen == 0) { max_count = 138; min_count = 3; }
+        for (int n = 0; n <= max_code; n++) {
+          const int curlen = nextlen;
+          nextlen = n + 1 <= max_code ? tl[n + 1] : 0xffff; // (the guard of de.ml:2087)
+          count++;
+          if (count < max_count && curlen == nextlen) continue;
+          if (count < min_count) {
+            S.freq_bl[curlen] += (uint32_t)count;
+            do { S.rle_sym[nr] = (uint8_t)curlen; S.rle_extra[nr++] = 0; } while (--count != 0);
+          } else if (curlen != 0) {
+            if (curlen != prevlen) { S.rle_sym[nr] = (uint8_t)curlen; S.rle_extra[nr++] = 0; S.freq_bl[curlen]++; count--; }
+            S.rle_sym[nr] = 16; S.rle_extra[nr++] = (uint8_t)(count - 3); S.freq_bl[16]++;
+          } else if (count <= 10) {
+            S.rle_sym[nr] = 17; S.rle_extra[nr++] = (uint8_t)(count - 3); S.freq_bl[17]++;
+          } else {
+            S.rle_sym[nr] = 18; S.rle_extra[nr++] = (uint8_t)(count - 11); S.freq_bl[18]++;
+          }
+          count = 0;
+          prevlen = curlen;
+          if (nextlen == 0) { max_count = 138; min_count = 3; }
+          else if (curlen == nextlen) { max_count = 6; min_count = 3; }
+          else { max_count = 7; min_count = 4; }
         }
-        i += run;
       }
       S.n_rle = nr;
-      S.hlit = hlit;
-      S.hdist = hdist;
+      S.hlit = l_max + 1;
+      S.hdist = d_max + 1;
     }
     __syncwarp();
     const int n_rle = S.n_rle, hlit = S.hlit, hdist = S.hdist;
