@@ -276,6 +276,22 @@ def run_c4(args, rank, local_rank, world):
         gen_s = time.time() - t0
     else:
         index, blob, out_full, gen_s = None, None, None, 0.0
+    # peer transport: rank 0's two buffers are mapped into every other process (CUDA IPC); slabs then move with plain
+    # device-to-device copies — the copy engines over NVLink / NVSwitch, no SM spent on the transfer — and the only
+    # collectives left are the index broadcast and one barrier that closes the step
+    peer = world > 1 and args.c4_transport == "peer"
+    if peer:
+        handles = [None, None]
+        if rank == 0:
+            handles = [blob.untyped_storage()._share_cuda_(), out_full.untyped_storage()._share_cuda_()]
+        dist.broadcast_object_list(handles, src=0)
+        if rank != 0:
+            def _open(h):
+                st_ = torch.UntypedStorage._new_shared_cuda(*h)
+                return torch.empty(0, dtype=torch.uint8, device=st_.device).set_(st_)
+            blob, out_full = _open(handles[0]), _open(handles[1])
+        s_in, s_out = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+        token = torch.zeros(1, device=dev)
 
     def one_step(timers=None):
         ev = lambda: torch.cuda.Event(enable_timing=True)
@@ -302,7 +318,21 @@ def run_c4(args, rank, local_rank, world):
         my_cuts = all_cuts[rank]
         npieces = max(len(c) for c in all_cuts) if all_cuts else 0
         scatter_works = [[] for _ in range(npieces)]
-        if world > 1:
+        in_events = [None] * npieces
+        if peer:
+            if rank == 0:
+                local = blob[ranges_c[0][0]:ranges_c[0][1]]
+            else:
+                local = torch.empty(ranges_c[rank][1] - ranges_c[rank][0] + 64, dtype=torch.uint8, device=dev)
+                s_in.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(s_in):
+                    for p in range(len(my_cuts)):       # pull this rank's compressed slab out of rank 0's memory, piece by piece
+                        x, y = my_cuts[p]
+                        lo, hi = int(ends_c[a + x]), int(ends_c[a + y])
+                        local[lo - int(ends_c[a]):hi - int(ends_c[a])].copy_(blob[lo:hi], non_blocking=True)
+                        in_events[p] = torch.cuda.Event()
+                        in_events[p].record(s_in)
+        elif world > 1:
             if rank == 0:
                 local = blob[ranges_c[0][0]:ranges_c[0][1]]
             else:
@@ -336,11 +366,20 @@ def run_c4(args, rank, local_rank, world):
         for p in range(npieces):
             if p < len(my_cuts):
                 if rank != 0:
+                    if peer:
+                        torch.cuda.current_stream().wait_event(in_events[p])
                     for w in scatter_works[p]:
                         w.wait()           # (stream-ordered: the host does not block)
                 x, y = my_cuts[p]
                 batch.inflate_device(_lib.FMT_GZIP, local, so[x:y], sl[x:y], my_out, do[x:y], dc[x:y], cons[x:y], prod[x:y], st[x:y], engine=eng)
-            if world > 1:
+                if peer and rank != 0:                  # the decoded piece goes straight into its place in rank 0's memory
+                    evd = torch.cuda.Event()
+                    evd.record()
+                    s_out.wait_event(evd)
+                    lo, hi = int(do_h[x]), int(do_h[y - 1] + idx[a + y - 1, 2])
+                    with torch.cuda.stream(s_out):
+                        out_full[ranges_o[rank][0] + lo:ranges_o[rank][0] + hi].copy_(my_out[lo:hi], non_blocking=True)
+            if world > 1 and not peer:
                 ops = []
                 if rank == 0:
                     for r in range(1, world):
@@ -356,9 +395,14 @@ def run_c4(args, rank, local_rank, world):
         if rank == 0:
             for ws in scatter_works:
                 works += ws
+        if peer:  # the step is over when every rank's copies have landed: one collective, ordered after them on each rank
+            torch.cuda.current_stream().wait_stream(s_out)
+            torch.cuda.current_stream().wait_stream(s_in)
         marks[2].record()
         for w in works:
             w.wait()
+        if peer:
+            dist.all_reduce(token)
         marks[3].record()
         if timers is not None:
             torch.cuda.synchronize()
@@ -422,7 +466,9 @@ def run_c4(args, rank, local_rank, world):
                                        "synthetic text, ratio %.2f:1), the file resident on rank 0's GPU, sharded over %d GPU(s) by member "
                                        "ranges" % (args.c4_mib, n, job_out / job_src, world),
                            "members": int(n), "compressed_bytes": int(job_src), "inflated_bytes": int(job_out),
-                           "parallelism": "index broadcast + NCCL point-to-point scatter of compressed slabs + gather of output slabs, "
+                           "transport": args.c4_transport if world > 1 else "none",
+                           "parallelism": "index broadcast + scatter of compressed slabs + gather of output slabs (peer: copy engines over NVLink through "
+                                          "CUDA IPC mappings of rank 0's buffers; nccl: NCCL send/recv), "
                                           "both in %d pieces per rank: a piece is decoded as soon as it has arrived and sent back while "
                                           "the next one is decoded" % pieces_per_rank,
                            "l2": "working set %d MiB per step > 126 MB L2" % ((job_src + job_out) >> 20)},
@@ -450,6 +496,8 @@ def main():
     ap.add_argument("--workload", default="c2", choices=["c2", "c4"], help="c2: BASELINE's quoted config (default); c4: multi-member gzip, strong scaling")
     ap.add_argument("--c4-mib", type=int, default=8192, help="inflated size of the C4 file (BASELINE: 8 GiB)")
     ap.add_argument("--c4-pieces", type=int, default=4, help="output pieces per rank (a piece is sent while the next is decoded)")
+    ap.add_argument("--c4-transport", default="peer", choices=["peer", "nccl"],
+                    help="how slabs travel: peer = copy engines over NVLink through CUDA IPC mappings of rank 0's buffers; nccl = NCCL send/recv")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
