@@ -89,6 +89,8 @@ _SIGNATURES = {
     "dcmp_def_encode": (C.c_int, [C.c_void_p]),
     "dcmp_def_src_rem": (C.c_int64, [C.c_void_p]),
     "dcmp_def_dst_rem": (C.c_int64, [C.c_void_p]),
+    "dcmp_def_encode_queue": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, p_u8, C.c_int64, C.POINTER(C.c_int64)]),
+    "dcmp_t_make": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "dcmp_adler32": (C.c_uint32, [C.c_uint32, p_u8, C.c_int64]),
     "dcmp_crc32": (C.c_uint32, [C.c_uint32, p_u8, C.c_int64]),
 }

@@ -93,7 +93,7 @@ struct DfSmemT {
   uint32_t freq_bl[19];
   uint32_t extra_bits; // total extra bits of the tokens (for the stored/dynamic decision)
   int n_rle;
-  int hlit, hdist;
+  int hlit, hdist, hclen;
 };
 static_assert(sizeof(DfTree) + 2 * (288 + 32 + 19) + (288 + 32 + 19) + 640 + 16 <= sizeof(uint32_t) * (1 << DF_HASH_BITS_FAST), "what follows tokenising overlays the hash table");
 static_assert(sizeof(DfTree) <= sizeof(uint32_t) * (1 << DF_HASH_BITS_FAST), "tree scratch overlays the hash table");
@@ -296,6 +296,147 @@ __device__ void df_adler_partials(const uint8_t *p, int n, int lane, uint32_t *s
   *sum_b = (uint32_t)(b % 65521ull);
 }
 
+// ---- a Dynamic block from the tokens' frequencies ---------------------------------------------------
+// 2 build: the three codes (De.T.make each: Def.dynamic_of_frequencies, de.ml:2387-2407) and the header's RLE symbols;
+// returns the size of the block in bits.  S.freq_l / S.freq_d / S.extra_bits describe the tokens.
+template <class SM>
+__device__ uint32_t df_build_block(SM &S, bool marker, int lane) {
+  const int l_max = df_build_code(S, S.freq_l, 286, 15, S.len_l, S.code_l, lane);
+  const int d_max = df_build_code(S, S.freq_d, 30, 15, S.len_d, S.code_d, lane);
+  if (lane == 0) {
+    // code-length RLE: T.scan + T.symbols (de.ml:2070-2190, zlib's scan_tree / send_tree), the literal/length tree and
+    // the distance tree one after the other — a run never crosses from one into the other
+    for (int i = 0; i < 19; i++) S.freq_bl[i] = 0;
+    int nr = 0;
+    for (int which = 0; which < 2; which++) {
+      const uint8_t *tl = which ? S.len_d : S.len_l;
+      const int max_code = which ? d_max : l_max;
+      int prevlen = -1, nextlen = tl[0], count = 0, max_count = 7, min_count = 4;
+      if (nextlen == 0) { max_count = 138; min_count = 3; }
+      for (int n = 0; n <= max_code; n++) {
+        const int curlen = nextlen;
+        nextlen = n + 1 <= max_code ? tl[n + 1] : 0xffff; // (the guard of de.ml:2087)
+        count++;
+        if (count < max_count && curlen == nextlen) continue;
+        if (count < min_count) {
+          S.freq_bl[curlen] += (uint32_t)count;
+          do { S.rle_sym[nr] = (uint8_t)curlen; S.rle_extra[nr++] = 0; } while (--count != 0);
+        } else if (curlen != 0) {
+          if (curlen != prevlen) { S.rle_sym[nr] = (uint8_t)curlen; S.rle_extra[nr++] = 0; S.freq_bl[curlen]++; count--; }
+          S.rle_sym[nr] = 16; S.rle_extra[nr++] = (uint8_t)(count - 3); S.freq_bl[16]++;
+        } else if (count <= 10) {
+          S.rle_sym[nr] = 17; S.rle_extra[nr++] = (uint8_t)(count - 3); S.freq_bl[17]++;
+        } else {
+          S.rle_sym[nr] = 18; S.rle_extra[nr++] = (uint8_t)(count - 11); S.freq_bl[18]++;
+        }
+        count = 0;
+        prevlen = curlen;
+        if (nextlen == 0) { max_count = 138; min_count = 3; }
+        else if (curlen == nextlen) { max_count = 6; min_count = 3; }
+        else { max_count = 7; min_count = 4; }
+      }
+    }
+    S.n_rle = nr;
+    S.hlit = l_max + 1;
+    S.hdist = d_max + 1;
+  }
+  __syncwarp();
+  const int n_rle = S.n_rle;
+  __syncwarp();
+  df_build_code(S, S.freq_bl, 19, 7, S.len_bl, S.code_bl, lane);
+  // cost of the dynamic block vs stored blocks
+  uint32_t bits_dyn = 0;
+  for (int s = lane; s < 286; s += 32) bits_dyn += S.freq_l[s] * S.len_l[s];
+  if (lane < 30) bits_dyn += S.freq_d[lane] * S.len_d[lane];
+  if (lane < 19) bits_dyn += S.freq_bl[lane] * S.len_bl[lane];
+  bits_dyn = __reduce_add_sync(0xffffffffu, bits_dyn);
+  int hclen = 19;
+  while (hclen > 4 && S.len_bl[c_bl_order[hclen - 1]] == 0) hclen--;
+  uint32_t rle_extra_bits = 0;
+  for (int i = lane; i < n_rle; i += 32) rle_extra_bits += S.rle_sym[i] == 16 ? 2u : S.rle_sym[i] == 17 ? 3u : S.rle_sym[i] == 18 ? 7u : 0u;
+  rle_extra_bits = __reduce_add_sync(0xffffffffu, rle_extra_bits);
+  bits_dyn += 3 + 14 + 3 * (uint32_t)hclen + rle_extra_bits + S.extra_bits + (marker ? 3u + 7u + 32u : 0u);
+  if (lane == 0) S.hclen = hclen;
+  __syncwarp();
+  return bits_dyn;
+}
+
+// 3 pack: header (encode_dynamic_header / zigzag / huffman, de.ml:2583-2624), the tokens (Def.write, de.ml:2657-2897), the end
+// of block and — `marker` — an empty stored block that byte-aligns the output; returns the bytes written to out32.
+template <class SM>
+__device__ uint32_t df_pack_block(SM &S, const uint32_t *tok, int ntok, bool last, bool marker, uint32_t *out32, int lane) {
+  const int n_rle = S.n_rle, hlit = S.hlit, hdist = S.hdist, hclen = S.hclen;
+  for (int i = lane; i < DF_WIN; i += 32) S.win[i] = 0;
+  __syncwarp();
+  DfBits bw{S.win, out32, 0u, 0u};
+  if (lane == 0) {
+    uint32_t at = 0;
+    auto put = [&](uint32_t v, uint32_t n) { bw.put(v, n, at); at += n; };
+    put(last ? 1u : 0u, 1);
+    put(2u, 2);
+    put((uint32_t)(hlit - 257), 5);
+    put((uint32_t)(hdist - 1), 5);
+    put((uint32_t)(hclen - 4), 4);
+    for (int i = 0; i < hclen; i++) put(S.len_bl[c_bl_order[i]], 3);
+    for (int i = 0; i < n_rle; i++) {
+      const int s = S.rle_sym[i];
+      put(S.code_bl[s], S.len_bl[s]);
+      if (s == 16) put(S.rle_extra[i], 2);
+      else if (s == 17) put(S.rle_extra[i], 3);
+      else if (s == 18) put(S.rle_extra[i], 7);
+    }
+    S.n_rle = (int)at;
+  }
+  __syncwarp();
+  bw.bitpos = (uint32_t)S.n_rle;
+  bw.drain(lane, false);
+  for (int g = 0; g < ntok; g += 32) {
+    const int i = g + lane;
+    uint64_t v = 0;
+    uint32_t nb = 0;
+    if (i < ntok) {
+      const uint32_t t = tok[i];
+      if ((t >> 23) & 1u) {
+        uint32_t eb, ev, eb2, ev2;
+        const uint32_t ls = df_len_sym((t & 0xffu) + 3u, &eb, &ev), ds = df_dist_sym(((t >> 8) & 0x7fffu) + 1u, &eb2, &ev2);
+        v = S.code_l[ls];
+        nb = S.len_l[ls];
+        v |= (uint64_t)ev << nb; nb += eb;
+        v |= (uint64_t)S.code_d[ds] << nb; nb += S.len_d[ds];
+        v |= (uint64_t)ev2 << nb; nb += eb2;
+      } else {
+        v = S.code_l[t];
+        nb = S.len_l[t];
+      }
+    }
+    uint32_t incl = nb;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t u = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += u;
+    }
+    bw.put(v, nb, bw.bitpos + incl - nb);
+    bw.bitpos += __shfl_sync(0xffffffffu, incl, 31);
+    bw.drain(lane, false);
+  }
+  if (lane == 0) {
+    uint32_t at = bw.bitpos;
+    bw.put(S.code_l[256], S.len_l[256], at); at += S.len_l[256];
+    if (marker) {
+      // empty stored block: byte-aligns the chunk so that chunk outputs concatenate
+      at += 3;                       // BFINAL=0, BTYPE=00
+      at = (at + 7u) & ~7u;
+      bw.put(0xffff0000ull, 32, at); // LEN=0, NLEN=0xffff
+      at += 32;
+    }
+    S.n_rle = (int)at;
+  }
+  __syncwarp();
+  bw.bitpos = (uint32_t)S.n_rle;
+  bw.drain(lane, true);
+  return (bw.bitpos + 7u) >> 3;
+}
+
 // ---- one chunk ----------------------------------------------------------------------------------
 template <class SM>
 __device__ void df_compress_chunk(SM &S, const uint8_t *d, int len, int hist, bool last, int level, uint32_t *tok,
@@ -430,134 +571,13 @@ __device__ void df_compress_chunk(SM &S, const uint8_t *d, int len, int hist, bo
     if (lane == 0) { S.freq_l[256] = 1; S.extra_bits = my_extra; }
     __syncwarp();
     // ---------------------------------------------------------------- 2 build
-    const int l_max = df_build_code(S, S.freq_l, 286, 15, S.len_l, S.code_l, lane);
-    const int d_max = df_build_code(S, S.freq_d, 30, 15, S.len_d, S.code_d, lane);
-    if (lane == 0) {
-      // code-length RLE: T.scan + T.symbols (de.ml:2070-2190, zlib's scan_tree / send_tree), the literal/length tree and
-      // the distance tree one after the other — a run never crosses from one into the other
-      for (int i = 0; i < 19; i++) S.freq_bl[i] = 0;
-      int nr = 0;
-      for (int which = 0; which < 2; which++) {
-        const uint8_t *tl = which ? S.len_d : S.len_l;
-        const int max_code = which ? d_max : l_max;
-        int prevlen = -1, nextlen = tl[0], count = 0, max_count = 7, min_count = 4;
-        if (nextlen == 0) { max_count = 138; min_count = 3; }
-        for (int n = 0; n <= max_code; n++) {
-          const int curlen = nextlen;
-          nextlen = n + 1 <= max_code ? tl[n + 1] : 0xffff; // (the guard of de.ml:2087)
-          count++;
-          if (count < max_count && curlen == nextlen) continue;
-          if (count < min_count) {
-            S.freq_bl[curlen] += (uint32_t)count;
-            do { S.rle_sym[nr] = (uint8_t)curlen; S.rle_extra[nr++] = 0; } while (--count != 0);
-          } else if (curlen != 0) {
-            if (curlen != prevlen) { S.rle_sym[nr] = (uint8_t)curlen; S.rle_extra[nr++] = 0; S.freq_bl[curlen]++; count--; }
-            S.rle_sym[nr] = 16; S.rle_extra[nr++] = (uint8_t)(count - 3); S.freq_bl[16]++;
-          } else if (count <= 10) {
-            S.rle_sym[nr] = 17; S.rle_extra[nr++] = (uint8_t)(count - 3); S.freq_bl[17]++;
-          } else {
-            S.rle_sym[nr] = 18; S.rle_extra[nr++] = (uint8_t)(count - 11); S.freq_bl[18]++;
-          }
-          count = 0;
-          prevlen = curlen;
-          if (nextlen == 0) { max_count = 138; min_count = 3; }
-          else if (curlen == nextlen) { max_count = 6; min_count = 3; }
-          else { max_count = 7; min_count = 4; }
-        }
-      }
-      S.n_rle = nr;
-      S.hlit = l_max + 1;
-      S.hdist = d_max + 1;
-    }
-    __syncwarp();
-    const int n_rle = S.n_rle, hlit = S.hlit, hdist = S.hdist;
-    __syncwarp();
-    df_build_code(S, S.freq_bl, 19, 7, S.len_bl, S.code_bl, lane);
-    // cost of the dynamic block vs stored blocks
-    uint32_t bits_dyn = 0;
-    for (int s = lane; s < 286; s += 32) bits_dyn += S.freq_l[s] * S.len_l[s];
-    if (lane < 30) bits_dyn += S.freq_d[lane] * S.len_d[lane];
-    if (lane < 19) bits_dyn += S.freq_bl[lane] * S.len_bl[lane];
-    bits_dyn = __reduce_add_sync(0xffffffffu, bits_dyn);
-    int hclen = 19;
-    while (hclen > 4 && S.len_bl[c_bl_order[hclen - 1]] == 0) hclen--;
-    uint32_t rle_extra_bits = 0;
-    for (int i = lane; i < n_rle; i += 32) rle_extra_bits += S.rle_sym[i] == 16 ? 2u : S.rle_sym[i] == 17 ? 3u : S.rle_sym[i] == 18 ? 7u : 0u;
-    rle_extra_bits = __reduce_add_sync(0xffffffffu, rle_extra_bits);
-    bits_dyn += 3 + 14 + 3 * (uint32_t)hclen + rle_extra_bits + S.extra_bits + (last ? 0u : 3u + 7u + 32u);
+    const uint32_t bits_dyn = df_build_block(S, !last, lane);
     const uint32_t bits_stored = 8u * ((uint32_t)len + 5u * (uint32_t)((len + 65534) / 65535));
     if (bits_dyn >= bits_stored) stored = true;
     if (!stored) {
       // ---------------------------------------------------------------- 3 pack
-      for (int i = lane; i < DF_WIN; i += 32) S.win[i] = 0;
-      __syncwarp();
-      DfBits bw{S.win, out32, 0u, 0u};
-      if (lane == 0) {
-        uint32_t at = 0;
-        auto put = [&](uint32_t v, uint32_t n) { bw.put(v, n, at); at += n; };
-        put(last ? 1u : 0u, 1);
-        put(2u, 2);
-        put((uint32_t)(hlit - 257), 5);
-        put((uint32_t)(hdist - 1), 5);
-        put((uint32_t)(hclen - 4), 4);
-        for (int i = 0; i < hclen; i++) put(S.len_bl[c_bl_order[i]], 3);
-        for (int i = 0; i < n_rle; i++) {
-          const int s = S.rle_sym[i];
-          put(S.code_bl[s], S.len_bl[s]);
-          if (s == 16) put(S.rle_extra[i], 2);
-          else if (s == 17) put(S.rle_extra[i], 3);
-          else if (s == 18) put(S.rle_extra[i], 7);
-        }
-        S.n_rle = (int)at;
-      }
-      __syncwarp();
-      bw.bitpos = (uint32_t)S.n_rle;
-      bw.drain(lane, false);
-      for (int g = 0; g < ntok; g += 32) {
-        const int i = g + lane;
-        uint64_t v = 0;
-        uint32_t nb = 0;
-        if (i < ntok) {
-          const uint32_t t = tok[i];
-          if ((t >> 23) & 1u) {
-            uint32_t eb, ev, eb2, ev2;
-            const uint32_t ls = df_len_sym((t & 0xffu) + 3u, &eb, &ev), ds = df_dist_sym(((t >> 8) & 0x7fffu) + 1u, &eb2, &ev2);
-            v = S.code_l[ls];
-            nb = S.len_l[ls];
-            v |= (uint64_t)ev << nb; nb += eb;
-            v |= (uint64_t)S.code_d[ds] << nb; nb += S.len_d[ds];
-            v |= (uint64_t)ev2 << nb; nb += eb2;
-          } else {
-            v = S.code_l[t];
-            nb = S.len_l[t];
-          }
-        }
-        uint32_t incl = nb;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          const uint32_t u = __shfl_up_sync(0xffffffffu, incl, o);
-          if (lane >= o) incl += u;
-        }
-        bw.put(v, nb, bw.bitpos + incl - nb);
-        bw.bitpos += __shfl_sync(0xffffffffu, incl, 31);
-        bw.drain(lane, false);
-      }
-      if (lane == 0) {
-        uint32_t at = bw.bitpos;
-        bw.put(S.code_l[256], S.len_l[256], at); at += S.len_l[256];
-        if (!last) {
-          // empty stored block: byte-aligns the chunk so that chunk outputs concatenate
-          at += 3;                       // BFINAL=0, BTYPE=00
-          at = (at + 7u) & ~7u;
-          bw.put(0xffff0000ull, 32, at); // LEN=0, NLEN=0xffff
-          at += 32;
-        }
-        S.n_rle = (int)at;
-      }
-      __syncwarp();
-      bw.bitpos = (uint32_t)S.n_rle;
-      bw.drain(lane, true);
-      if (lane == 0) { res->bytes = (bw.bitpos + 7u) >> 3; res->sum_a = sum_a; res->sum_b = sum_b; }
+      const uint32_t nbytes = df_pack_block(S, tok, ntok, last, !last, out32, lane);
+      if (lane == 0) { res->bytes = nbytes; res->sum_a = sum_a; res->sum_b = sum_b; }
       return;
     }
   }
@@ -579,6 +599,74 @@ __device__ void df_compress_chunk(SM &S, const uint8_t *d, int len, int hist, bo
     } while (pos < len);
     if (lane == 0) { res->bytes = o; res->sum_a = sum_a; res->sum_b = sum_b; }
   }
+}
+
+// ---- De.Def.encode over a Queue, De.T.make: the command-level half of the reference's encoder on the device -----------
+// One Dynamic block from a list of Queue commands (de.ml:2245-2266: literal = byte, end of block = 256, copy =
+// 0x2000000 | (len - 3) << 16 | (off - 1)): frequencies counted as De.Lz77 counts them (succ_literal / succ_length /
+// succ_distance, de.ml:2333-2351; the end of block starts at 1), Def.dynamic_of_frequencies, the header, the codes.
+// The bytes are the reference's (test/test.ml:507-531).  One warp.
+__global__ void __launch_bounds__(32)
+deflate_queue_kernel(const int32_t *cmds, int64_t n, int last, uint32_t *tok, uint32_t *slot, uint8_t *dst, int64_t cap,
+                     int64_t *written, int32_t *status) {
+  DCMP_DYN_SMEM(smem_raw);
+  typedef DfSmemT<DF_HASH_BITS_FAST> DfSmem;
+  DfSmem &S = *reinterpret_cast<DfSmem *>(smem_raw);
+  const int lane = threadIdx.x & 31;
+  for (int i = lane; i < 288; i += 32) S.freq_l[i] = 0;
+  S.freq_d[lane] = 0;
+  __syncwarp();
+  uint32_t my_extra = 0;
+  int ntok = 0;
+  for (int64_t base = 0; base < n; base += 32) {
+    const int64_t k = base + lane;
+    const int32_t c = k < n ? cmds[k] : 256;
+    const bool is_tok = k < n && c != 256;
+    const uint32_t m = __ballot_sync(0xffffffffu, is_tok);
+    if (is_tok) {
+      uint32_t t;
+      if (c & 0x2000000) {
+        const uint32_t len = (uint32_t)((c >> 16) & 0x1ff) + 3u, dist = (uint32_t)(c & 0xffff) + 1u;
+        uint32_t eb, ev, eb2, ev2;
+        atomicAdd(&S.freq_l[df_len_sym(len, &eb, &ev)], 1u);
+        atomicAdd(&S.freq_d[df_dist_sym(dist, &eb2, &ev2)], 1u);
+        my_extra += eb + eb2;
+        t = (1u << 23) | ((dist - 1u) << 8) | (len - 3u);
+      } else {
+        t = (uint32_t)c & 0xffu;
+        atomicAdd(&S.freq_l[t], 1u);
+      }
+      tok[ntok + __popc(m & ((1u << lane) - 1u))] = t;
+    }
+    ntok += __popc(m);
+  }
+  my_extra = __reduce_add_sync(0xffffffffu, my_extra);
+  if (lane == 0) { S.freq_l[256] = 1; S.extra_bits = my_extra; }
+  __syncwarp();
+  df_build_block(S, false, lane);
+  const uint32_t nbytes = df_pack_block(S, tok, ntok, last != 0, false, slot, lane);
+  __syncwarp();
+  if ((int64_t)nbytes > cap) {
+    if (lane == 0) { *written = 0; *status = DCMP_UNEXPECTED_END_OF_OUTPUT; }
+    return;
+  }
+  const uint8_t *sb = reinterpret_cast<const uint8_t *>(slot);
+  for (uint32_t i = lane; i < nbytes; i += 32) dst[i] = sb[i];
+  if (lane == 0) { *written = nbytes; *status = DCMP_OK; }
+}
+
+// De.T.make ~length ?max_length freqs (de.ml:2013-2068) for one alphabet: lengths and bit-reversed codes per symbol, max_code.
+__global__ void __launch_bounds__(32)
+deflate_tmake_kernel(const int32_t *freqs, int length, int max_bits, int32_t *lens_out, int32_t *codes_out, int32_t *max_code_out) {
+  DCMP_DYN_SMEM(smem_raw);
+  typedef DfSmemT<DF_HASH_BITS_FAST> DfSmem;
+  DfSmem &S = *reinterpret_cast<DfSmem *>(smem_raw);
+  const int lane = threadIdx.x & 31;
+  for (int i = lane; i < 288; i += 32) S.freq_l[i] = i < length ? (uint32_t)freqs[i] : 0u;
+  __syncwarp();
+  const int mc = df_build_code(S, S.freq_l, length, max_bits, S.len_l, S.code_l, lane);
+  for (int i = lane; i < length; i += 32) { lens_out[i] = S.len_l[i]; codes_out[i] = S.code_l[i]; }
+  if (lane == 0) *max_code_out = mc;
 }
 
 template <int HB>
@@ -734,6 +822,13 @@ int configure_deflate() { // per device (see configure_inflate_parallel)
   if (e == cudaSuccess)
     e = cudaFuncSetAttribute(deflate_chunk_kernel<DF_HASH_BITS_BEST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)deflate_smem_bytes(9));
   return (int)e;
+}
+void launch_deflate_queue(const int32_t *cmds, int64_t n, int last, uint32_t *tok, uint32_t *slot, uint8_t *dst, int64_t cap, int64_t *written,
+                          int32_t *status, cudaStream_t stream) {
+  deflate_queue_kernel<<<1, 32, sizeof(DfSmemT<DF_HASH_BITS_FAST>) + 128, stream>>>(cmds, n, last, tok, slot, dst, cap, written, status);
+}
+void launch_deflate_tmake(const int32_t *freqs, int length, int max_bits, int32_t *lens, int32_t *codes, int32_t *max_code, cudaStream_t stream) {
+  deflate_tmake_kernel<<<1, 32, sizeof(DfSmemT<DF_HASH_BITS_FAST>) + 128, stream>>>(freqs, length, max_bits, lens, codes, max_code);
 }
 int launch_deflate(int level, int fmt, int64_t nstreams, int64_t nchunks, const uint8_t *src_base, const void *chunks,
                    const int64_t *first_chunk, void *outs, uint8_t *slots, int64_t *chunk_dst, uint32_t *tok_scratch,

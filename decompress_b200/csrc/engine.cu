@@ -47,6 +47,9 @@ int launch_deflate(int level, int fmt, int64_t nstreams, int64_t nchunks, const 
 void launch_gzip_wrap(int64_t n, int level, int os, const uint8_t *src_base, const int64_t *src_off, const int64_t *src_len,
                       uint8_t *dst_base, const int64_t *dst_off, const int64_t *dst_cap, int64_t *written, int32_t *status,
                       cudaStream_t stream);
+void launch_deflate_queue(const int32_t *cmds, int64_t n, int last, uint32_t *tok, uint32_t *slot, uint8_t *dst, int64_t cap, int64_t *written,
+                          int32_t *status, cudaStream_t stream);
+void launch_deflate_tmake(const int32_t *freqs, int length, int max_bits, int32_t *lens, int32_t *codes, int32_t *max_code, cudaStream_t stream);
 size_t deflate_tok_bytes_per_cta();
 int deflate_ctas_per_sm();
 size_t deflate_slot_bytes();
@@ -595,6 +598,53 @@ int dcmp_deflate_batch(dcmp_engine *e, int level, int fmt, int64_t n, const uint
   for (int64_t k = 0; k < n; k++)
     if (status[k] == DCMP_OK && written[k] > 0)
       CU(cudaMemcpyAsync(dst_base + dst_off[k], d_dst + dof[k], (size_t)written[k], cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  return DCMP_API_OK;
+}
+
+// De.Def.encode over a De.Queue (one Dynamic block) and De.T.make, on the device: the command-level half of the encoder,
+// held to the reference's encoder KATs (test/test.ml:507-531, 1169-1237)
+int dcmp_def_encode_queue(dcmp_engine *e, const int32_t *cmds, int64_t n, int last, uint8_t *dst, int64_t dst_len, int64_t *written) {
+  if (!e || n < 0 || dst_len < 0 || !written || (n > 0 && !cmds) || (dst_len > 0 && !dst)) return DCMP_API_INVALID_ARGUMENT;
+  CU(cudaSetDevice(e->device));
+  const size_t o_tok = align_up((size_t)n * 4 + 16, 256), o_slot = align_up(o_tok + (size_t)n * 4 + 16, 256);
+  const size_t slot_bytes = align_up((size_t)n * 8 + 2048, 256), o_dst = o_slot + slot_bytes, o_res = align_up(o_dst + (size_t)dst_len + 16, 256);
+  int rc = e->reserve(o_res + 64);
+  if (rc != DCMP_API_OK) return rc;
+  uint8_t *B = e->d_buf;
+  cudaStream_t st = e->stream;
+  if (n > 0) CU(cudaMemcpyAsync(B, cmds, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+  dcmp::launch_deflate_queue((const int32_t *)B, n, last, (uint32_t *)(B + o_tok), (uint32_t *)(B + o_slot), B + o_dst, dst_len,
+                             (int64_t *)(B + o_res), (int32_t *)(B + o_res + 8), st);
+  e->launches += 1;
+  CU(cudaGetLastError());
+  int64_t res[2] = {0, 0};
+  CU(cudaMemcpyAsync(res, B + o_res, 12, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  const int status = (int)(int32_t)(res[1] & 0xffffffff);
+  *written = res[0];
+  if (status == DCMP_OK && res[0] > 0) {
+    CU(cudaMemcpyAsync(dst, B + o_dst, (size_t)res[0], cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+  }
+  return status;
+}
+
+int dcmp_t_make(dcmp_engine *e, int length, int max_length, const int32_t *freqs, int32_t *lengths, int32_t *codes, int32_t *max_code) {
+  if (!e || length < 1 || length > 286 || max_length < 1 || max_length > 15 || !freqs || !lengths || !codes || !max_code)
+    return DCMP_API_INVALID_ARGUMENT;
+  CU(cudaSetDevice(e->device));
+  int rc = e->reserve(4096 * 4);
+  if (rc != DCMP_API_OK) return rc;
+  int32_t *B = (int32_t *)e->d_buf;
+  cudaStream_t st = e->stream;
+  CU(cudaMemcpyAsync(B, freqs, (size_t)length * 4, cudaMemcpyHostToDevice, st));
+  dcmp::launch_deflate_tmake(B, length, max_length, B + 512, B + 1024, B + 1536, st);
+  e->launches += 1;
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(lengths, B + 512, (size_t)length * 4, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(codes, B + 1024, (size_t)length * 4, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(max_code, B + 1536, 4, cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
   return DCMP_API_OK;
 }

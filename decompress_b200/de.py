@@ -77,6 +77,70 @@ class Def:
             return Error(_lib.STATUS_TAG.get(st, st))
 
 
+# ---- the command-level encoder: De.Queue commands, De.T, De.Def.encode over a Queue --------------------------------------
+class Queue:
+    """De.Queue's command encoding (de.mli:188-263, de.ml:2245-2266)."""
+    EOB = 256
+
+    @staticmethod
+    def literal(chr_):
+        return chr_ if isinstance(chr_, int) else ord(chr_)
+
+    @staticmethod
+    def copy(off, length):
+        if not (1 <= off <= 32768 and 3 <= length <= 258):
+            raise ValueError("Invalid copy (off: %d, len: %d)" % (off, length))
+        return 0x2000000 | ((length - 3) << 16) | (off - 1)
+
+    @staticmethod
+    def of_list(cmds):
+        """[("Literal", c) | ("Copy", off, len) | "End"] -> commands (Queue.of_list, de.ml:2321-2327)."""
+        out = []
+        for c in cmds:
+            if c == "End":
+                out.append(Queue.EOB)
+            elif c[0] == "Literal":
+                out.append(Queue.literal(c[1]))
+            else:
+                out.append(Queue.copy(c[1], c[2]))
+        return out
+
+
+class T:
+    """De.T (de.mli:677-682): make ~length ?max_length freqs -> (lengths, codes, max_code), built on the device exactly as
+    the reference builds it (zlib's tree)."""
+
+    @staticmethod
+    def make(length, freqs, max_length=15, engine=None):
+        eng = engine or _lib.default_engine()
+        f = np.zeros(length, dtype=np.int32)
+        fr = np.asarray(freqs, dtype=np.int32)[:length]
+        f[:len(fr)] = fr
+        lens, codes, mc = np.zeros(length, dtype=np.int32), np.zeros(length, dtype=np.int32), C.c_int32(0)
+        rc = _lib.lib().dcmp_t_make(eng.handle, length, max_length, C.c_void_p(f.ctypes.data), C.c_void_p(lens.ctypes.data),
+                                    C.c_void_p(codes.ctypes.data), C.byref(mc))
+        _lib.check(rc, "dcmp_t_make")
+        return lens.tolist(), codes.tolist(), mc.value
+
+
+def _encode_queue(cmds, last=True, cap=None, engine=None):
+    """De.Def.encode over a Queue with a Dynamic block of its own frequencies (Def.dynamic_of_frequencies + encode,
+    de.ml:2387-2407, 2583-2897), on the device: Ok(bytes) or Error(tag)."""
+    eng = engine or _lib.default_engine()
+    a = np.asarray(cmds, dtype=np.int32)
+    cap = 8 * len(a) + 1024 if cap is None else cap
+    out = np.zeros(max(cap, 1), dtype=np.uint8)
+    wr = C.c_int64(0)
+    st = _lib.lib().dcmp_def_encode_queue(eng.handle, C.c_void_p(a.ctypes.data if a.size else 0), a.size, int(bool(last)),
+                                          C.c_void_p(out.ctypes.data), cap, C.byref(wr))
+    if st < 0:
+        _lib.check(st, "dcmp_def_encode_queue")
+    return Ok(out[:wr.value].tobytes()) if st == 0 else Error(_lib.STATUS_TAG.get(st, st))
+
+
+Def.encode_queue = staticmethod(_encode_queue)
+
+
 # ---- streaming facade ---------------------------------------------------------------------------------------------
 class Window:
     """De.window (de.mli:59-75).  The GPU engine keeps its own sliding window; the value only carries `bits`."""

@@ -184,6 +184,17 @@ int dcmp_def_ns_deflate(dcmp_engine *e, int level, const uint8_t *src, int64_t s
 int dcmp_zl_def_ns_deflate(dcmp_engine *e, int level, const uint8_t *src, int64_t src_len,
                            uint8_t *dst, int64_t dst_len, int64_t *written);
 
+/* ---- the command-level encoder: De.Queue -> De.Def, De.T (lib/de.mli:188-263, 300-445, 677-682) -------------------------
+ * dcmp_def_encode_queue: what De.Def.encode does with a De.Queue and a Dynamic block (lib/de.ml:2387-2407, 2583-2897): one
+ * Dynamic-Huffman block from n commands in the Queue's own encoding (lib/de.ml:2245-2266: literal = the byte, end of
+ * block = 256 (implied at the end), copy = 0x2000000 | (len - 3) << 16 | (off - 1)); BFINAL = last.  Frequencies are
+ * counted from the commands (succ_literal / succ_length / succ_distance, lib/de.ml:2333-2351); trees, header and codes
+ * are the reference's bit for bit (test/test.ml:507-531).  Returns the status; *written = the block's bytes.
+ * dcmp_t_make: De.T.make ~length ?max_length freqs (lib/de.ml:2013-2068): per symbol the code length and the bit-reversed
+ * canonical code — zlib's tree (test/test.ml:1169-1237). */
+int dcmp_def_encode_queue(dcmp_engine *e, const int32_t *cmds, int64_t n, int last, uint8_t *dst, int64_t dst_len, int64_t *written);
+int dcmp_t_make(dcmp_engine *e, int length, int max_length, const int32_t *freqs, int32_t *lengths, int32_t *codes, int32_t *max_code);
+
 /* ---- streaming decoders ---------------------------------------------------------
  * The non-blocking half of the reference's interface: De.Inf.decoder / decode / src / flush / dst_rem / src_rem /
  * checksum / reset (lib/de.mli:82-148, lib/de.ml:651-753, 1427-1532) for fmt = DCMP_FMT_RAW, Zl.Inf (lib/zl.mli:30-124,

@@ -86,6 +86,32 @@ def deflate_streams(inputs, caps, level=6, fmt=0):
     return [(int(st[k]), int(wr[k]), dst[do[k]:do[k] + int(wr[k])].tobytes()) for k in range(n)]
 
 
+def t_make(freqs, length, max_length=15):
+    """deflate_tmake_kernel on the emulator: (lengths, codes, max_code)."""
+    L = lib()
+    f = np.zeros(288, dtype=np.int32)
+    fr = np.asarray(freqs, dtype=np.int32)[:length]
+    f[:len(fr)] = fr
+    lens, codes = np.zeros(288, dtype=np.int32), np.zeros(288, dtype=np.int32)
+    L.emu_t_make.restype = C.c_int
+    L.emu_t_make.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    mc = L.emu_t_make(length, max_length, C.c_void_p(f.ctypes.data), C.c_void_p(lens.ctypes.data), C.c_void_p(codes.ctypes.data))
+    return lens[:length].tolist(), codes[:length].tolist(), mc
+
+
+def def_encode_queue(cmds, last=True, cap=None):
+    """deflate_queue_kernel on the emulator: (status, bytes)."""
+    L = lib()
+    a = np.asarray(cmds, dtype=np.int32)
+    cap = 8 * len(a) + 1024 if cap is None else cap
+    out = np.zeros(max(cap, 1), dtype=np.uint8)
+    wr = C.c_int64(0)
+    L.emu_def_encode_queue.restype = C.c_int
+    L.emu_def_encode_queue.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]
+    st = L.emu_def_encode_queue(C.c_void_p(a.ctypes.data), len(a), int(bool(last)), C.c_void_p(out.ctypes.data), cap, C.byref(wr))
+    return st, out[:wr.value].tobytes()
+
+
 class StreamApi:
     """The streaming state machines of the product (csrc/stream_core.h) instantiated over the emulator back ends
     (tests/simt_emu/emu_stream.h): same entry points as decompress_b200.stream.ProductApi, prefix emu_ instead of dcmp_."""

@@ -104,6 +104,25 @@ int emu_deflate_batch(int level, int fmt, int64_t n, const uint8_t *src, const i
   return 0;
 }
 
+// De.Def.encode over a Queue / De.T.make on the emulator (deflate_queue_kernel, deflate_tmake_kernel)
+int emu_def_encode_queue(const int32_t *cmds, int64_t n, int last, uint8_t *dst, int64_t cap, int64_t *written) {
+  using namespace dcmp;
+  std::vector<uint32_t> tok((size_t)n + 8), slot((size_t)n * 2 + 1024);
+  int32_t status = -1;
+  simt::launch(simt::dim3(1), simt::dim3(32), sizeof(DfSmemT<DF_HASH_BITS_FAST>) + 128, [&]() {
+    deflate_queue_kernel(cmds, n, last, tok.data(), slot.data(), dst, cap, written, &status);
+  });
+  return status;
+}
+int emu_t_make(int length, int max_bits, const int32_t *freqs, int32_t *lens, int32_t *codes) {
+  using namespace dcmp;
+  int32_t mc = -1;
+  simt::launch(simt::dim3(1), simt::dim3(32), sizeof(DfSmemT<DF_HASH_BITS_FAST>) + 128, [&]() {
+    deflate_tmake_kernel(freqs, length, max_bits, lens, codes, &mc);
+  });
+  return mc;
+}
+
 long emu_switches() { return simt::g_switches; }
 } // extern "C"
 #include "emu_stream.h"

@@ -108,3 +108,45 @@ def test_deflate_round_trip(emu):
         for (st, written, comp), x in zip(res, ins):
             assert st == 0 and zlib.decompress(comp) == x
             assert oracle.zl_inflate_ns(comp, len(x))[:3] == (0, written, len(x))
+
+
+def test_encoder_kats_on_the_device_kernels(emu):
+    """De.T.make and De.Def.encode over a Queue as the DEVICE builds them (deflate_tmake_kernel, deflate_queue_kernel), held to
+    the reference's encoder known answers (test/test.ml:507-531, 1169-1237) and to the CPU oracle on random histograms."""
+    k = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "encoder.json")))["kats"]
+    st, out = emu.def_encode_queue(k["huffman_length_extra"]["cmds"], k["huffman_length_extra"]["last"])
+    assert st == 0 and out.hex() == k["huffman_length_extra"]["bytes"]
+    r = k["tree_rfc5322"]
+    lens, codes, mc = emu.t_make(r["freqs"], 286)
+    assert [lens[ord("6")], codes[ord("6")]] == r["literal_6"] and [lens[256], codes[256]] == r["eob"]
+    assert (lens, codes, mc) == oracle.t_make(r["freqs"], 286)
+    lens, codes, mc = emu.t_make([0] * 256 + [1], 286)
+    assert [[n, l] for n, l in enumerate(lens) if l] == k["tree_0"]["lengths"]
+    import random
+    rng = random.Random(11)
+    for length, maxl in ((286, 15), (30, 15), (19, 7)):
+        for trial in range(12):
+            f = [rng.choice([0, 0, 1, 2, 3, 50, 1000, rng.randrange(1 << 20)]) for _ in range(length)]
+            if trial == 0:
+                f = [0] * length
+            if trial == 1:
+                f = [0] * length; f[1] = 7
+            if trial == 2:
+                f = [1 << k2 for k2 in range(length)] if length <= 30 else [1 << (k2 % 22) for k2 in range(length)]  # skewed: overflow repair
+            assert emu.t_make(f, length, maxl) == oracle.t_make(f, length, maxl), (length, trial)
+    # a block of random commands: same bytes as the oracle's restatement of De.Def
+    data, cmds = bytearray(), []
+    for _ in range(1500):
+        if data and rng.random() < 0.45:
+            off = rng.randint(1, min(len(data), 32768)); ln = rng.randint(3, 258)
+            for j in range(ln):
+                data.append(data[-off])
+            cmds.append(0x2000000 | ((ln - 3) << 16) | (off - 1))
+        else:
+            b = rng.choice(b"abcdefgh \n")
+            data.append(b); cmds.append(b)
+    cmds.append(256)
+    st, out = emu.def_encode_queue(cmds, True)
+    want, h = oracle.def_encode_dynamic(cmds, True)
+    assert st == 0 and out == want and zlib.decompress(out, -15) == bytes(data)
+    assert emu.def_encode_queue(cmds, True, cap=len(want) - 1)[0] == 2

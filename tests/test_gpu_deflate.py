@@ -83,3 +83,46 @@ def test_many_small_inputs_in_one_batch(eng):
     inputs = [workloads.text(int(n), 100 + k) for k, n in enumerate(rng.integers(0, 9000, 500))]
     res = batch.deflate_streams(inputs, level=6, fmt=batch.FMT_ZLIB, engine=eng)
     _roundtrip(inputs, res, batch.FMT_ZLIB, eng)
+
+
+def test_encoder_known_answers_on_the_gpu(eng):
+    """SURVEY §8(f4) / VERDICT r1 item 7: De.T.make and De.Def.encode over a De.Queue, built ON THE DEVICE, against the
+    reference's encoder known answers (test/test.ml:507-531 huffman_length_extra: 16 bytes; 1169-1237: tree_0 and the
+    rfc5322 histogram — "the same tree as zlib") and against the CPU oracle's restatement on random input."""
+    import json
+    import os
+    import random
+    k = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "encoder.json")))["kats"]
+    h = k["huffman_length_extra"]
+    cmds = de.Queue.of_list([("Literal", 0), ("Literal", 0), ("Copy", 1, 258), ("Copy", 1, 256), "End"])
+    assert cmds == h["cmds"]
+    r = de.Def.encode_queue(cmds, last=h["last"], engine=eng)
+    assert r.is_ok() and r.value.hex() == h["bytes"] == "edc101010000004020ff571b42c1ea04"
+    t = k["tree_rfc5322"]
+    lens, codes, mc = de.T.make(286, t["freqs"], engine=eng)
+    assert [lens[ord("6")], codes[ord("6")]] == t["literal_6"] == [10, 0x35f] and [lens[256], codes[256]] == t["eob"] == [15, 0x6fff]
+    assert (lens, codes, mc) == oracle.t_make(t["freqs"], 286)
+    lens, codes, mc = de.T.make(286, [0] * 256 + [1], engine=eng)
+    assert [[n, l] for n, l in enumerate(lens) if l] == k["tree_0"]["lengths"] and [[n, codes[n]] for n, l in enumerate(lens) if l] == k["tree_0"]["codes"]
+    rng = random.Random(23)
+    for length, maxl in ((286, 15), (30, 15), (19, 7)):
+        for trial in range(20):
+            f = [rng.choice([0, 0, 1, 2, 3, 50, 1000, rng.randrange(1 << 18)]) for _ in range(length)]
+            if trial == 0:
+                f = [1 << (j % 22) for j in range(length)]      # skewed: the overflow repair of gen_bitlen
+            assert de.T.make(length, f, maxl, engine=eng) == oracle.t_make(f, length, maxl), (length, trial)
+    data, cmds = bytearray(), []
+    for _ in range(20000):
+        if data and rng.random() < 0.45:
+            off = rng.randint(1, min(len(data), 32768)); ln = rng.randint(3, 258)
+            for j in range(ln):
+                data.append(data[-off])
+            cmds.append(de.Queue.copy(off, ln))
+        else:
+            b = rng.choice(b"abcdefgh \n") if rng.random() < 0.9 else rng.randrange(256)
+            data.append(b); cmds.append(b)
+    cmds.append(de.Queue.EOB)
+    r = de.Def.encode_queue(cmds, engine=eng)
+    want, _ = oracle.def_encode_dynamic(cmds, True)
+    assert r.is_ok() and r.value == want and zlib.decompress(r.value, -15) == bytes(data)
+    assert de.Def.encode_queue(cmds, cap=len(want) - 1, engine=eng) == Error("Unexpected_end_of_output")
