@@ -596,11 +596,48 @@ def main():
     hv = h_dst.numpy()
     assert zlib.adler32(hv[do[n - 1]:do[n - 1] + STREAM_BYTES].tobytes()) == int(adler[n - 1])
 
+    # ---- what the box allows: the same bytes as plain pinned copies, both directions at once, all ranks at the same time.
+    # e2e cannot beat this: it is the PCIe / host-memory ceiling of THIS box at THIS number of ranks.
+    s_h2d, s_d2h = torch.cuda.Stream(), torch.cuda.Stream()
+    d_tmp_in = torch.empty(h_src.numel(), dtype=torch.uint8, device=dev)
+
+    def step_copy():
+        with torch.cuda.stream(s_h2d):
+            d_tmp_in.copy_(h_src, non_blocking=True)
+        with torch.cuda.stream(s_d2h):
+            h_dst[:total_out].copy_(d_dst[:total_out], non_blocking=True)
+        s_h2d.synchronize()
+        s_d2h.synchronize()
+
+    step_copy()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        step_copy()
+    copy_s = time.perf_counter() - t0
+    # ---- the same call on PAGEABLE buffers (what an OCaml Bigarray is unless it is registered with dcmp_host_register)
+    p_src, p_dst = src.copy(), np.zeros(int(do[-1] + dc[-1]) + 64, dtype=np.uint8)
+
+    def step_pageable():
+        rc = _lib.lib().dcmp_inflate_batch(eng.handle, batch.FMT_ZLIB, n, P(p_src), P(so), P(sl), P(p_dst), P(do), P(dc), P(cons), P(prod), P(stat))
+        _lib.check(rc, "dcmp_inflate_batch")
+
+    step_pageable()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(3):
+        step_pageable()
+    page_s = (time.perf_counter() - t0) / 3
+    assert int(np.abs(stat).sum()) == 0 and zlib.adler32(p_dst[do[0]:do[0] + STREAM_BYTES].tobytes()) == int(adler[0])
+
     # ---- reduce over ranks (max time) ------------------------------------------------------------
     if world > 1:
-        tt = torch.tensor([ms, e2e_s], dtype=torch.float64, device=dev)
+        tt = torch.tensor([ms, e2e_s, copy_s, page_s], dtype=torch.float64, device=dev)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        ms, e2e_s = float(tt[0]), float(tt[1])
+        ms, e2e_s, copy_s, page_s = float(tt[0]), float(tt[1]), float(tt[2]), float(tt[3])
         tb = torch.tensor([float(total_src), float(total_out)], dtype=torch.float64, device=dev)
         dist.all_reduce(tb, op=dist.ReduceOp.SUM)
         job_src, job_out = float(tb[0]), float(tb[1])
@@ -631,7 +668,11 @@ def main():
                          "peak_source": peak_src},
             "e2e": {"value": round(job_out / (e2e_s / e2e_steps) / 1e9, 3), "unit": "GB/s",
                     "h2d_bytes_per_step": int(total_src + 4 * 8 * n), "d2h_bytes_per_step": int(total_out + 20 * n),
-                    "steps": e2e_steps, "api": "dcmp_inflate_batch (pinned host buffers)"},
+                    "steps": e2e_steps, "api": "dcmp_inflate_batch (pinned host buffers)",
+                    "pcie_ceiling": round(job_out / (copy_s / e2e_steps) / 1e9, 3),
+                    "pcie_ceiling_how": "the step's H2D and D2H bytes as plain pinned cudaMemcpyAsync on two streams, every rank at the same "
+                                        "time: the same metric with no kernel at all",
+                    "pageable": round(job_out / page_s / 1e9, 3)},
             "gpu_launches": int(launches), "clocks": clocks,
         }
         if not args.no_cpu_baseline:

@@ -991,7 +991,9 @@ inflate_parallel_kernel(int fmt, int64_t nstreams, const uint8_t *src_base, cons
         for (int span = 1; span < PT; span <<= 1) {
           const int j = M.jump[cur][tid];
           if (j < PT) {
-            if (M.mark[tid]) M.mark[j] = 1; // (racy on purpose: a mark that lands early only marks members of the orbit sooner)
+            // (a mark may land while another thread reads it in the same pass: early only marks members of the orbit
+            // sooner — relaxed atomics, see simt.cuh)
+            if (ld_relaxed_u8(&M.mark[tid])) st_relaxed_u8(&M.mark[j], 1);
             M.jump[cur ^ 1][tid] = M.jump[cur][j];
           } else {
             M.jump[cur ^ 1][tid] = (uint16_t)PT;
