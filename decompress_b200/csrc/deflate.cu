@@ -364,12 +364,31 @@ __device__ uint32_t df_build_block(SM &S, bool marker, int lane) {
 // 3 pack: header (encode_dynamic_header / zigzag / huffman, de.ml:2583-2624), the tokens (Def.write, de.ml:2657-2897), the end
 // of block and — `marker` — an empty stored block that byte-aligns the output; returns the bytes written to out32.
 template <class SM>
-__device__ uint32_t df_pack_block(SM &S, const uint32_t *tok, int ntok, bool last, bool marker, uint32_t *out32, int lane) {
+__device__ uint32_t df_pack_block(SM &S, const uint32_t *tok, int ntok, bool last, bool marker, uint32_t *out32, int lane,
+                                  bool fixed = false) {
   const int n_rle = S.n_rle, hlit = S.hlit, hdist = S.hdist, hclen = S.hclen;
+  if (fixed) {
+    // the Fixed codes (de.ml:821-833, RFC1951 3.2.6) in place of the block's own: no tree in the header
+    __syncwarp();
+    for (int s2 = lane; s2 < 288; s2 += 32) {
+      const uint32_t l = s2 < 144 ? 8u : s2 < 256 ? 9u : s2 < 280 ? 7u : 8u;
+      const uint32_t c = s2 < 144 ? 0x30u + (uint32_t)s2 : s2 < 256 ? 0x190u + (uint32_t)(s2 - 144) : s2 < 280 ? (uint32_t)(s2 - 256) : 0xc0u + (uint32_t)(s2 - 280);
+      S.len_l[s2] = (uint8_t)l;
+      S.code_l[s2] = (uint16_t)(__brev(c) >> (32 - l));
+    }
+    S.len_d[lane] = 5;
+    S.code_d[lane] = (uint16_t)(__brev((uint32_t)lane) >> 27);
+    __syncwarp();
+  }
   for (int i = lane; i < DF_WIN; i += 32) S.win[i] = 0;
   __syncwarp();
   DfBits bw{S.win, out32, 0u, 0u};
-  if (lane == 0) {
+  if (lane == 0 && fixed) {
+    bw.put(last ? 1u : 0u, 1, 0);
+    bw.put(1u, 2, 1);
+    S.n_rle = 3;
+  }
+  if (lane == 0 && !fixed) {
     uint32_t at = 0;
     auto put = [&](uint32_t v, uint32_t n) { bw.put(v, n, at); at += n; };
     put(last ? 1u : 0u, 1);
@@ -446,7 +465,7 @@ __device__ void df_compress_chunk(SM &S, const uint8_t *d, int len, int hist, bo
   uint32_t *out32 = reinterpret_cast<uint32_t *>(slot);
   // ---------------------------------------------------------------- 1 tokenise
   int ntok = 0;
-  bool stored = level == 0 || len < 16;
+  bool stored = level == 0;
   if (!stored) {
     for (int i = lane; i < (1 << SM::HASH_BITS); i += 32) S.head[i] = 0;
     for (int i = lane; i < 288; i += 32) S.freq_l[i] = 0;
@@ -572,11 +591,18 @@ __device__ void df_compress_chunk(SM &S, const uint8_t *d, int len, int hist, bo
     __syncwarp();
     // ---------------------------------------------------------------- 2 build
     const uint32_t bits_dyn = df_build_block(S, !last, lane);
+    // the same tokens under the Fixed codes (Def.block_of_frequencies weighs the two as well, de.ml:2411-2449): small inputs
+    // do not pay for a tree in the header
+    uint32_t bits_fixed = 0;
+    for (int s2 = lane; s2 < 286; s2 += 32) bits_fixed += S.freq_l[s2] * (s2 < 144 ? 8u : s2 < 256 ? 9u : s2 < 280 ? 7u : 8u);
+    if (lane < 30) bits_fixed += S.freq_d[lane] * 5u;
+    bits_fixed = __reduce_add_sync(0xffffffffu, bits_fixed) + 3u + S.extra_bits + (last ? 0u : 3u + 7u + 32u);
+    const bool fixed = bits_fixed < bits_dyn;
     const uint32_t bits_stored = 8u * ((uint32_t)len + 5u * (uint32_t)((len + 65534) / 65535));
-    if (bits_dyn >= bits_stored) stored = true;
+    if ((fixed ? bits_fixed : bits_dyn) >= bits_stored) stored = true;
     if (!stored) {
       // ---------------------------------------------------------------- 3 pack
-      const uint32_t nbytes = df_pack_block(S, tok, ntok, last, !last, out32, lane);
+      const uint32_t nbytes = df_pack_block(S, tok, ntok, last, !last, out32, lane, fixed);
       if (lane == 0) { res->bytes = nbytes; res->sum_a = sum_a; res->sum_b = sum_b; }
       return;
     }

@@ -100,6 +100,16 @@ def test_lzo_long_overlapping_copy_general_kernel(emu):
             assert rc == 0 and r[0] == 0 and r[2] == prod and r[3] == out, (which, len(out))
 
 
+def test_deflate_fixed_blocks_and_the_level_1_known_answer(emu):
+    """test/test_ns.ml:1203-1222 (`encoder 1`): 56 zero bytes at level 1 are the five bytes 63 20 13 00 00 (a Fixed block)."""
+    ins = [bytes(56), b"a", b"ab", b"abc", workloads.text(15, 1), workloads.text(16, 1), bytes(range(256))]
+    res = emu.deflate_streams(ins, [len(x) + 64 for x in ins], level=1, fmt=batch.FMT_RAW)
+    assert res[0][2].hex() == "6320130000"
+    for x, (st, wr, comp) in zip(ins, res):
+        assert st == 0 and zlib.decompress(comp, -15) == x and oracle.inflate_ns(comp, len(x))[:3] == (0, wr, len(x))
+    assert all((res[k][2][0] >> 1) & 3 == 1 for k in range(6)) and (res[6][2][0] >> 1) & 3 == 0
+
+
 def test_deflate_round_trip(emu):
     txt = workloads.text(150000, 2)
     ins = [txt, b"", txt[:100], bytes(70000), txt[:65537]]

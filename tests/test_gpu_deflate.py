@@ -126,3 +126,17 @@ def test_encoder_known_answers_on_the_gpu(eng):
     want, _ = oracle.def_encode_dynamic(cmds, True)
     assert r.is_ok() and r.value == want and zlib.decompress(r.value, -15) == bytes(data)
     assert de.Def.encode_queue(cmds, cap=len(want) - 1, engine=eng) == Error("Unexpected_end_of_output")
+
+
+def test_def_ns_known_answers_and_fixed_blocks(eng):
+    """test/test_ns.ml:1189-1222: `encoder 0` (level 0, one stored block) and `encoder 1` (level 1: 56 zero bytes -> the five
+    bytes 63 20 13 00 00: a Fixed block holding a literal, one match of 55 at distance 1, the end of block) byte for byte.
+    Small inputs leave as Fixed blocks (Def.block_of_frequencies weighs Fixed against Dynamic, lib/de.ml:2411-2449)."""
+    dst = de.bigstring_create(64)
+    assert de.Def.Ns.deflate(b"\x01", dst, level=0, engine=eng) == Ok(6) and dst[:6].tobytes() == bytes.fromhex("010100feff01")
+    assert de.Def.Ns.deflate(bytes(56), dst, level=1, engine=eng) == Ok(5) and dst[:5].tobytes() == bytes.fromhex("6320130000")
+    small = [b"a", b"ab", b"abc", b"hello hello hello", workloads.text(15, 1), workloads.text(60, 2)]
+    res = batch.deflate_streams(small, level=6, engine=eng)
+    for x, (st, wr, comp) in zip(small, res):
+        assert st == 0 and (comp[0] >> 1) & 3 == 1 and wr <= len(x) + 3, x       # BTYPE = 01
+        assert zlib.decompress(comp, -15) == x and oracle.inflate_ns(comp, len(x))[:3] == (0, wr, len(x))
