@@ -14,6 +14,7 @@ HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "dcmp.h")
 
 API_OK, API_NO_DEVICE, API_CUDA_ERROR, API_INVALID_ARGUMENT, API_OUT_OF_MEMORY = 0, -1, -2, -3, -4
 FMT_RAW, FMT_ZLIB, FMT_GZIP = 0, 1, 2
+GZIP_RFC_XLEN = 0x200  # OR-ed into FMT_GZIP: FEXTRA XLEN little-endian (RFC1952, BGZF) instead of the reference's big-endian
 
 # De.Inf.Ns.error / Zl.Inf.Ns.error / Lzo.error constructors by status code (include/dcmp.h)
 STATUS_TAG = {
@@ -59,6 +60,7 @@ _SIGNATURES = {
     "dcmp_def_ns_deflate": (C.c_int, [C.c_void_p, C.c_int, p_u8, C.c_int64, p_u8, C.c_int64, C.POINTER(C.c_int64)]),
     "dcmp_zl_def_ns_deflate": (C.c_int, [C.c_void_p, C.c_int, p_u8, C.c_int64, p_u8, C.c_int64, C.POINTER(C.c_int64)]),
     "dcmp_engine_device": (C.c_int, [C.c_void_p]),
+    "dcmp_gz_bgzf_index": (C.c_int64, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]),
     "dcmp_host_register": (C.c_int, [C.c_void_p, C.c_int64]),
     "dcmp_host_unregister": (C.c_int, [C.c_void_p]),
     # streaming decoders / encoders (csrc/stream.cu)

@@ -29,7 +29,7 @@ int configure_lzo_decode();
 int configure_deflate();
 int inflate_parallel_ctas_per_sm();
 void launch_gzip_header(int64_t n, const uint8_t *src_base, const int64_t *src_off, const int64_t *src_len, int64_t *body_off,
-                        int64_t *body_len, int32_t *pre_status, cudaStream_t stream);
+                        int64_t *body_len, int32_t *pre_status, int rfc_xlen, cudaStream_t stream);
 void launch_gzip_trailer(int64_t n, const uint8_t *src_base, const int64_t *src_off, const int64_t *body_off, const int64_t *body_len,
                          const int32_t *pre_status, const uint8_t *dst_base, const int64_t *dst_off, int64_t *consumed,
                          int64_t *produced, int32_t *status, cudaStream_t stream);
@@ -84,6 +84,20 @@ struct dcmp_engine {
   int mode = 0;                      // 0 = parallel + general, 1 = general kernel only (DCMP_INFLATE_MODE=serial)
   uint8_t *d_gz = nullptr;           // gzip: rebased body offsets / lengths / header status per member
   size_t gz_cap = 0;
+  std::vector<void *> retired;       // scratch that was outgrown while launches on other streams might still read it: freed with the engine
+  // The *_batch_device calls share per-engine scratch (work counters, token scratch, the gzip tables, the deflate arena):
+  // every call waits for the previous one — whatever stream that was enqueued on — before it touches them, and records
+  // where it ends.  Two calls on two streams are therefore serialised on the device, never corrupted.
+  cudaEvent_t ev_last = nullptr;
+  int chain_begin(cudaStream_t st) {
+    if (!ev_last) CU(cudaEventCreateWithFlags(&ev_last, cudaEventDisableTiming));
+    else CU(cudaStreamWaitEvent(st, ev_last, 0));
+    return DCMP_API_OK;
+  }
+  int chain_end(cudaStream_t st) {
+    CU(cudaEventRecord(ev_last, st));
+    return DCMP_API_OK;
+  }
   // deflate: persistent CTAs (3 per SM), their token scratch, and a growable arena for the per-chunk state
   int def_ctas = 0;
   uint8_t *d_def_scratch = nullptr;  // [work counter (256 B) | token scratch of every CTA]
@@ -174,6 +188,8 @@ void dcmp_engine_destroy(dcmp_engine *e) {
   if (e->d_buf) cudaFree(e->d_buf);
   if (e->d_scratch) cudaFree(e->d_scratch);
   if (e->d_gz) cudaFree(e->d_gz);
+  for (void *p : e->retired) cudaFree(p);
+  if (e->ev_last) cudaEventDestroy(e->ev_last);
   if (e->d_def_scratch) cudaFree(e->d_def_scratch);
   if (e->d_def_arena) cudaFree(e->d_def_arena);
   if (e->pipeline_ready) {
@@ -205,11 +221,14 @@ int dcmp_inflate_batch_device(dcmp_engine *e, int fmt, int64_t n, const uint8_t 
                               const int64_t *d_dst_cap, int64_t *d_consumed, int64_t *d_produced, int32_t *d_status,
                               void *cuda_stream) {
   if (!e) return DCMP_API_INVALID_ARGUMENT;
+  const int rfc_xlen = (fmt & DCMP_GZIP_RFC_XLEN) ? 1 : 0;
+  fmt &= ~DCMP_GZIP_RFC_XLEN;
   if (fmt != DCMP_FMT_RAW && fmt != DCMP_FMT_ZLIB && fmt != DCMP_FMT_GZIP) return DCMP_API_INVALID_ARGUMENT;
   if (n < 0) return DCMP_API_INVALID_ARGUMENT;
   if (n == 0) return DCMP_API_OK;
   CU(cudaSetDevice(e->device));
   cudaStream_t st = (cudaStream_t)cuda_stream; // NULL = the legacy default stream, as everywhere in CUDA
+  { const int rc0 = e->chain_begin(st); if (rc0 != DCMP_API_OK) return rc0; }
   // gzip: one member per unit.  The header is parsed on the device, the DEFLATE body goes through the raw
   // kernels with rebased offset tables, then CRC-32 / ISIZE are checked on the device (gzip_frame.cu).
   const int64_t *g_src_off = d_src_off;
@@ -218,15 +237,15 @@ int dcmp_inflate_batch_device(dcmp_engine *e, int fmt, int64_t n, const uint8_t 
   if (fmt == DCMP_FMT_GZIP) {
     const size_t need = (size_t)n * 20 + 256;
     if (need > e->gz_cap) {
-      // (stream-ordered free: earlier launches on other streams may still read the old scratch)
-      if (e->d_gz) { CU(cudaDeviceSynchronize()); CU(cudaFree(e->d_gz)); e->d_gz = nullptr; e->gz_cap = 0; }
+      // (earlier launches may still read the old tables: they are kept until the engine goes, no device-wide synchronise)
+      if (e->d_gz) { e->retired.push_back(e->d_gz); e->d_gz = nullptr; e->gz_cap = 0; }
       CU(cudaMalloc(&e->d_gz, need * 2));
       e->gz_cap = need * 2;
     }
     gz_off = (int64_t *)e->d_gz;
     gz_len = gz_off + n;
     gz_pre = (int32_t *)(gz_len + n);
-    dcmp::launch_gzip_header(n, d_src_base, d_src_off, d_src_len, gz_off, gz_len, gz_pre, st);
+    dcmp::launch_gzip_header(n, d_src_base, d_src_off, d_src_len, gz_off, gz_len, gz_pre, rfc_xlen, st);
     e->launches += 1;
     d_src_off = gz_off;
     d_src_len = gz_len;
@@ -257,7 +276,7 @@ int dcmp_inflate_batch_device(dcmp_engine *e, int fmt, int64_t n, const uint8_t 
     e->launches += 1;
   }
   CU(cudaGetLastError());
-  return DCMP_API_OK;
+  return e->chain_end(st);
 }
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -386,7 +405,8 @@ static int host_batch(dcmp_engine *e, device_batch_fn launch, int fmt, int64_t n
 int dcmp_inflate_batch(dcmp_engine *e, int fmt, int64_t n, const uint8_t *src_base, const int64_t *src_off,
                        const int64_t *src_len, uint8_t *dst_base, const int64_t *dst_off, const int64_t *dst_cap,
                        int64_t *consumed, int64_t *produced, int32_t *status) {
-  if (fmt != DCMP_FMT_RAW && fmt != DCMP_FMT_ZLIB && fmt != DCMP_FMT_GZIP) return DCMP_API_INVALID_ARGUMENT;
+  if ((fmt & ~DCMP_GZIP_RFC_XLEN) != DCMP_FMT_RAW && (fmt & ~DCMP_GZIP_RFC_XLEN) != DCMP_FMT_ZLIB && (fmt & ~DCMP_GZIP_RFC_XLEN) != DCMP_FMT_GZIP)
+    return DCMP_API_INVALID_ARGUMENT;
   return host_batch(e, dcmp_inflate_batch_device, fmt, n, src_base, src_off, src_len, dst_base, dst_off, dst_cap,
                     consumed, produced, status);
 }
@@ -398,6 +418,7 @@ int dcmp_lzo_uncompress_batch_device(dcmp_engine *e, int mode, int64_t n, const 
   if (!e || n < 0 || (mode != 0 && mode != 1)) return DCMP_API_INVALID_ARGUMENT;
   if (n == 0) return DCMP_API_OK;
   CU(cudaSetDevice(e->device));
+  { const int rc0 = e->chain_begin((cudaStream_t)cuda_stream); if (rc0 != DCMP_API_OK) return rc0; }
   if (e->mode == 0) {
     // stage 1: one CTA per block (serial opcode parse, CTA-wide copies); stage 2: the one-warp-per-block
     // kernel on exactly the blocks stage 1 gave up (malformed input, short output window, ...)
@@ -417,7 +438,7 @@ int dcmp_lzo_uncompress_batch_device(dcmp_engine *e, int mode, int64_t n, const 
     e->launches += 1;
   }
   CU(cudaGetLastError());
-  return DCMP_API_OK;
+  return e->chain_end((cudaStream_t)cuda_stream);
 }
 
 int dcmp_lzo_uncompress_batch(dcmp_engine *e, int mode, int64_t n, const uint8_t *src_base, const int64_t *src_off,
@@ -515,6 +536,7 @@ int dcmp_deflate_batch_device(dcmp_engine *e, int level, int fmt, int64_t n, con
     e->def_ctas = dcmp::deflate_ctas_per_sm() * (e->sm_count > 0 ? e->sm_count : 148);
     CU(cudaMalloc(&e->d_def_scratch, 256 + (size_t)e->def_ctas * dcmp::deflate_tok_bytes_per_cta()));
   }
+  { const int rc0 = e->chain_begin(st); if (rc0 != DCMP_API_OK) return rc0; }
   const size_t slot = dcmp::deflate_slot_bytes();
   size_t o_chunks = 0;
   size_t o_outs = align_up(o_chunks + (size_t)nc * sizeof(dcmp::DfChunkHost), 256);
@@ -529,7 +551,7 @@ int dcmp_deflate_batch_device(dcmp_engine *e, int level, int fmt, int64_t n, con
   size_t o_slots = align_up(o_gcap + (gz ? (size_t)n * 8 : 0), 256);
   size_t need = o_slots + (size_t)nc * slot + 256;
   if (need > e->def_arena_cap) {
-    if (e->d_def_arena) { CU(cudaFree(e->d_def_arena)); e->d_def_arena = nullptr; e->def_arena_cap = 0; }
+    if (e->d_def_arena) { e->retired.push_back(e->d_def_arena); e->d_def_arena = nullptr; e->def_arena_cap = 0; }
     CU(cudaMalloc(&e->d_def_arena, need + (need >> 3)));
     e->def_arena_cap = need + (need >> 3);
   }
@@ -558,6 +580,7 @@ int dcmp_deflate_batch_device(dcmp_engine *e, int level, int fmt, int64_t n, con
     e->launches += 1;
   }
   CU(cudaGetLastError());
+  { const int rc1 = e->chain_end(st); if (rc1 != DCMP_API_OK) return rc1; }
   // the uploads above read host vectors that die with this frame
   CU(cudaStreamSynchronize(st));
   return DCMP_API_OK;
@@ -663,6 +686,35 @@ int dcmp_def_ns_deflate(dcmp_engine *e, int level, const uint8_t *src, int64_t s
 int dcmp_zl_def_ns_deflate(dcmp_engine *e, int level, const uint8_t *src, int64_t src_len, uint8_t *dst, int64_t dst_len,
                            int64_t *written) {
   return def_ns(e, level, DCMP_FMT_ZLIB, src, src_len, dst, dst_len, written);
+}
+
+// A member index without decoding: BGZF — the blocked gzip of htslib / bgzip — stores every member's size in
+// an FEXTRA sub-field 'B','C' (BSIZE = member bytes - 1, little-endian as RFC1952 has it), so a multi-member file can be cut
+// into units on the host by hopping from header to header; ISIZE (the member's last four bytes) gives the output windows.
+// Host framing only.  Returns the number of members (an empty EOF member included), -1 if a member is not BGZF-framed.
+int64_t dcmp_gz_bgzf_index(const uint8_t *buf, int64_t len, int64_t *member_off, int64_t *member_len, int64_t *isize, int64_t max_members) {
+  if (!buf || len < 0) return -1;
+  int64_t pos = 0, n = 0;
+  while (pos < len) {
+    if (len - pos < 18 || buf[pos] != 0x1f || buf[pos + 1] != 0x8b || buf[pos + 2] != 8 || !(buf[pos + 3] & 4)) return -1;
+    const int64_t xlen = (int64_t)buf[pos + 10] | ((int64_t)buf[pos + 11] << 8);
+    if (len - pos < 12 + xlen) return -1;
+    int64_t bsize = -1;
+    for (int64_t i = pos + 12; i + 4 <= pos + 12 + xlen;) {
+      const int64_t slen = (int64_t)buf[i + 2] | ((int64_t)buf[i + 3] << 8);
+      if (buf[i] == 'B' && buf[i + 1] == 'C' && slen == 2 && i + 6 <= pos + 12 + xlen) bsize = ((int64_t)buf[i + 4] | ((int64_t)buf[i + 5] << 8)) + 1;
+      i += 4 + slen;
+    }
+    if (bsize < 12 + xlen + 8 || pos + bsize > len) return -1;
+    if (n < max_members) {
+      if (member_off) member_off[n] = pos;
+      if (member_len) member_len[n] = bsize;
+      if (isize) isize[n] = (int64_t)buf[pos + bsize - 4] | ((int64_t)buf[pos + bsize - 3] << 8) | ((int64_t)buf[pos + bsize - 2] << 16) | ((int64_t)buf[pos + bsize - 1] << 24);
+    }
+    n++;
+    pos += bsize;
+  }
+  return n;
 }
 
 // Page-lock a caller's buffer (an OCaml Bigarray is pageable malloc memory): host<->device copies of a registered

@@ -78,7 +78,7 @@ __device__ uint32_t crc_bytes8(const uint32_t (*T8)[256], uint32_t c, const uint
 
 // one thread per member
 __global__ void gzip_header_kernel(int64_t n, const uint8_t *src_base, const int64_t *src_off, const int64_t *src_len,
-                                   int64_t *body_off, int64_t *body_len, int32_t *pre_status) {
+                                   int64_t *body_off, int64_t *body_len, int32_t *pre_status, int rfc_xlen) {
   __shared__ uint32_t T[256];
   for (int i = threadIdx.x; i < 256; i += blockDim.x) {
     uint32_t c = (uint32_t)i;
@@ -99,7 +99,9 @@ __global__ void gzip_header_kernel(int64_t n, const uint8_t *src_base, const int
     if (flg & 4) {
       if (len - i < 2) st = DCMP_UNEXPECTED_END_OF_INPUT;
       else {
-        const int64_t xlen = ((int64_t)p[i] << 8) | p[i + 1];
+        // XLEN: big-endian in the reference (gz.ml:455); little-endian in RFC1952 and in every file other tools write
+        // (BGZF ...): DCMP_GZIP_RFC_XLEN picks the latter
+        const int64_t xlen = rfc_xlen ? ((int64_t)p[i + 1] << 8) | p[i] : ((int64_t)p[i] << 8) | p[i + 1];
         i += 2;
         if (len - i < xlen) st = DCMP_UNEXPECTED_END_OF_INPUT;
         else i += xlen;
@@ -219,8 +221,8 @@ gzip_wrap_kernel(int64_t n, int level, int os, const uint8_t *src_base, const in
 }
 #ifndef DCMP_EMU
 void launch_gzip_header(int64_t n, const uint8_t *src_base, const int64_t *src_off, const int64_t *src_len, int64_t *body_off,
-                        int64_t *body_len, int32_t *pre_status, cudaStream_t stream) {
-  gzip_header_kernel<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(n, src_base, src_off, src_len, body_off, body_len, pre_status);
+                        int64_t *body_len, int32_t *pre_status, int rfc_xlen, cudaStream_t stream) {
+  gzip_header_kernel<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(n, src_base, src_off, src_len, body_off, body_len, pre_status, rfc_xlen);
 }
 void launch_gzip_trailer(int64_t n, const uint8_t *src_base, const int64_t *src_off, const int64_t *body_off, const int64_t *body_len,
                          const int32_t *pre_status, const uint8_t *dst_base, const int64_t *dst_off, int64_t *consumed,

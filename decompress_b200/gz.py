@@ -51,6 +51,39 @@ def inflate_multi(buf, member_off, caps, engine=None):
     return inflate_members([m.tobytes() for m in members], caps, engine=engine)
 
 
+def bgzf_index(buf):
+    """Member boundaries of a BGZF file (bgzip / htslib) without decoding: every member carries its size in an FEXTRA
+    sub-field (dcmp_gz_bgzf_index).  Returns (offsets, lengths, isizes) as int64 arrays, or None if `buf` is not BGZF."""
+    b = np.ascontiguousarray(_as_u8(buf))
+    L = _lib.lib()
+    n = L.dcmp_gz_bgzf_index(C.c_void_p(b.ctypes.data if b.size else 0), b.size, None, None, None, 0)
+    if n < 0:
+        return None
+    off, ln, isz = (np.zeros(n, dtype=np.int64) for _ in range(3))
+    L.dcmp_gz_bgzf_index(C.c_void_p(b.ctypes.data if b.size else 0), b.size, C.c_void_p(off.ctypes.data), C.c_void_p(ln.ctypes.data),
+                         C.c_void_p(isz.ctypes.data), n)
+    return off, ln, isz
+
+
+def inflate_bgzf(buf, engine=None):
+    """A whole BGZF file in one batch: the index from the members' own size fields, every member an independent unit
+    (CRC-32 / ISIZE checked on the device).  Returns Ok(bytes) or Error(message)."""
+    b = np.ascontiguousarray(_as_u8(buf))
+    idx = bgzf_index(b)
+    if idx is None:
+        return Error("Invalid GZip header")
+    off, ln, isz = idx
+    n = len(off)
+    eng = engine or _lib.default_engine()
+    dst_off = np.concatenate([[0], np.cumsum(isz)[:-1]]).astype(np.int64) if n else np.zeros(0, dtype=np.int64)
+    dst = np.zeros(int(isz.sum()) + 16, dtype=np.uint8)
+    cons, prod, st = batch.inflate_host(FMT_GZIP | _lib.GZIP_RFC_XLEN, b, off, ln, dst, dst_off, isz, engine=eng)
+    bad = np.nonzero(st)[0]
+    if len(bad):
+        return Error(_MSG.get(int(st[bad[0]]), _lib.lib().dcmp_status_string(int(st[bad[0]])).decode()))
+    return Ok(dst[:int(isz.sum())].tobytes())
+
+
 def inflate_multi_sequential(buf, cap_per_member=None, engine=None, api=None, o_size=1 << 20):
     """The reference's way for a multi-member file without an index (lib/gz.ml:550, 582-610): Gz.Inf answers `End after
     ONE member; the caller looks at `src_rem` — how much of the input follows it —, resets the decoder and feeds the rest.

@@ -75,11 +75,19 @@ enum {
                          parsed and checked on the device */
 };
 
+/* OR-ed into DCMP_FMT_GZIP for inflate: XLEN of the FEXTRA field is little-endian, as RFC1952 and every other tool (gzip,
+ * bgzip ...) write it; without it the reference's big-endian reading is kept (lib/gz.ml:455). */
+#define DCMP_GZIP_RFC_XLEN 0x200
+
 /* OR-ed into `fmt` of dcmp_deflate_batch_device (DCMP_FMT_RAW only): no block carries BFINAL and the output ends on a byte
  * boundary — one segment of a stream the caller closes itself (what the streaming encoders below do). */
 #define DCMP_DEFLATE_NO_FINAL 0x100
 
 typedef struct dcmp_engine dcmp_engine;
+
+/* Streams: the *_batch_device entry points enqueue on the caller's CUDA stream and do not wait for the kernels.  They
+ * share per-engine scratch, so consecutive calls — on the same stream or on different ones — are ordered on the device
+ * one after the other (an event per engine); use several engines for concurrent batches. */
 
 /* ---- engine ------------------------------------------------------------------
  * One engine = one CUDA device + one stream + reusable device/pinned scratch.
@@ -258,6 +266,13 @@ int dcmp_def_dst(dcmp_def *d, uint8_t *buf, int64_t len);
 int dcmp_def_encode(dcmp_def *d);                           /* DCMP_AWAIT, DCMP_FLUSH, DCMP_END, or DCMP_API_* < 0 */
 int64_t dcmp_def_src_rem(const dcmp_def *d);
 int64_t dcmp_def_dst_rem(const dcmp_def *d);
+
+/* ---- multi-member gzip without decoding: a BGZF index -------------------------------------------
+ * Gz.Inf answers `End after ONE member and the reference has no way to find the next boundary without decoding (lib/gz.ml:550,
+ * 582-610).  BGZF members carry their own size (FEXTRA sub-field 'B','C'): this walks them on the host and fills member_off /
+ * member_len / isize (up to max_members); the members then go through dcmp_inflate_batch(DCMP_FMT_GZIP | DCMP_GZIP_RFC_XLEN)
+ * as independent units.  Returns the number of members, -1 if the buffer is not a sequence of BGZF members. */
+int64_t dcmp_gz_bgzf_index(const uint8_t *buf, int64_t len, int64_t *member_off, int64_t *member_len, int64_t *isize, int64_t max_members);
 
 /* ---- caller buffers ----------------------------------------------------------------
  * The *_batch calls take host pointers.  A `bigstring` (Bigarray.Array1, lib/de.mli:45) is pageable malloc memory:

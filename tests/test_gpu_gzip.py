@@ -112,3 +112,33 @@ def test_gzip_deflate_batch_members_on_the_device(eng):
             assert (st, cons, prod) == (0, len(comps[k]), len(ins[k])) and out == ins[k], (level, k)
     st, wr, comp = batch.deflate_streams([txt], [17], level=6, fmt=_lib.FMT_GZIP, engine=eng)[0]
     assert st == 2 and wr == 0      # Unexpected_end_of_output: no room for the framing
+
+
+def _bgzf(data, block=60000):
+    """A BGZF file as bgzip writes it: members of <= 64 KiB with the 'BC' size sub-field (XLEN little-endian), an empty EOF member."""
+    out = bytearray()
+    for pos in list(range(0, len(data), block)) + [None]:
+        chunk = b"" if pos is None else data[pos:pos + block]
+        co = zlib.compressobj(6, zlib.DEFLATED, -15)
+        body = co.compress(chunk) + co.flush()
+        bsize = 12 + 6 + len(body) + 8
+        out += bytes([0x1f, 0x8b, 8, 4, 0, 0, 0, 0, 0, 0xff]) + struct.pack("<H", 6) + b"BC" + struct.pack("<HH", 2, bsize - 1)
+        out += body + struct.pack("<II", zlib.crc32(chunk) & 0xFFFFFFFF, len(chunk))
+    return bytes(out)
+
+
+def test_bgzf_member_index_and_batch_inflate(eng):
+    """a multi-member file cut into units WITHOUT decoding — BGZF's own size fields (dcmp_gz_bgzf_index) — and
+    inflated as one batch; XLEN is little-endian there (DCMP_GZIP_RFC_XLEN), where the reference reads it big-endian."""
+    txt = workloads.text(1_000_000, 77)
+    blob = _bgzf(txt)
+    assert gzip.decompress(blob) == txt                   # what every other tool makes of it
+    off, ln, isz = gz.bgzf_index(blob)
+    assert len(off) == (len(txt) + 59999) // 60000 + 1 and int(isz.sum()) == len(txt) and off[0] == 0 and off[-1] + ln[-1] == len(blob)
+    assert gz.inflate_bgzf(blob, engine=eng) == Ok(txt)
+    bad = bytearray(blob); bad[int(off[3]) + 40] ^= 0x20
+    assert not gz.inflate_bgzf(bytes(bad), engine=eng).is_ok()
+    assert gz.bgzf_index(gzip.compress(txt[:1000])) is None   # a plain gzip member carries no size
+    # the reference's reading of the same bytes (XLEN big-endian, lib/gz.ml:455): 0x0600 bytes of "extra", then garbage
+    st, cons, prod, out = gz.inflate_members([blob[:int(ln[0])]], [int(isz[0])], engine=eng)[0]
+    assert st != 0
