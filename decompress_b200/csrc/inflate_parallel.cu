@@ -129,7 +129,12 @@ struct RoundMeta {
   uint8_t mark[PT];
   LaneDesc desc[PT];
 };
+#ifndef DCMP_WIN_OVERLAY
+#define DCMP_WIN_OVERLAY 0                // 1: the staged input window too lives in the symbol buffer (behind the round metadata):
+#endif                                    //    it is dead once phase D starts; buys the shared memory for a fourth CTA per SM
+constexpr int WIN_OVL_OFF = (int)((sizeof(RoundMeta) + 15) & ~(size_t)15); // byte offset of the overlaid window in `sym`
 static_assert(sizeof(RoundMeta) <= SYM_SLOTS * 2, "round metadata overlays the symbol buffer");
+static_assert(!DCMP_WIN_OVERLAY || WIN_OVL_OFF + WIN_BYTES + 16 <= SYM_SLOTS * 2, "metadata + window overlay the symbol buffer");
 static_assert(RSYM + 16 + 256 <= 65536, "markers are 16-bit");
 static_assert(HDR_BYTES <= WIN_BYTES, "");
 
@@ -194,7 +199,11 @@ struct ParSmem {
 #if !DCMP_HIST_GLOBAL
   __align__(16) uint8_t ring[HIST];        // last 32 KiB of output, indexed by (global address & HIST_MASK)
 #endif
+#if DCMP_WIN_OVERLAY
+  __align__(16) uint32_t nh_win[HDR_BYTES / 4 + 4]; // the bytes of a next-block header, saved before phase D overwrites the window
+#else
   __align__(16) uint32_t win[WIN_BYTES / 4 + 4]; // staged compressed input (TMA destination)
+#endif
   uint32_t tbl[LIT_N + DIST_N];  // literal/length table (root, then the sub-tables of codes longer than the root), distance table
   uint8_t lens[MAX_LENS];
   HuffMeta ml, md;
@@ -242,6 +251,14 @@ struct ParSmem {
 #endif
 // 227 KiB of shared memory per SM, 1 KiB reserved per resident CTA
 static_assert(sizeof(ParSmem) + 128 + 1024 <= 227 * 1024 / DCMP_CTAS_PER_SM, "shared memory per CTA for the intended residency");
+
+__device__ __forceinline__ uint32_t *win_of(ParSmem &S) {
+#if DCMP_WIN_OVERLAY
+  return reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(S.sym) + WIN_OVL_OFF);
+#else
+  return S.win;
+#endif
+}
 
 // ------------------------------------------------------------------------------------------
 // The decoder of phases A and B.  One STEP = one table lookup: a literal/length code or — when the step before
@@ -552,11 +569,11 @@ __device__ void stage_window(ParSmem &S, const uint8_t *g, int bytes, int valid,
   // previous readers of S.win are done (callers sync before)
   if (valid > bytes) valid = bytes;
   if (valid < 0) valid = 0;
-  for (int i = valid + tid * 16; i < bytes; i += PT * 16) *(uint4 *)((uint8_t *)S.win + i) = make_uint4(0, 0, 0, 0);
+  for (int i = valid + tid * 16; i < bytes; i += PT * 16) *(uint4 *)((uint8_t *)win_of(S) + i) = make_uint4(0, 0, 0, 0);
   if (valid > 0) {
     if (tid == 0) {
       mbar_expect_tx(&S.mbar, (uint32_t)valid);
-      tma_load_1d(S.win, g, (uint32_t)valid, &S.mbar);
+      tma_load_1d(win_of(S), g, (uint32_t)valid, &S.mbar);
     }
     mbar_wait(&S.mbar, phase & 1u);
     phase ^= 1u;
@@ -650,6 +667,7 @@ __device__ DCMP_PHASE_A_INLINE void phase_a_lane(ParSmem &S, uint32_t (*ckpt)[PT
                                           const bool lane_has_input) {
   const int lroot = S.ml.root, droot = S.md.root;
   const uint32_t lmask = (1u << lroot) - 1u, dmask = (1u << droot) - 1u;
+  const uint32_t *const win = win_of(S);
   int ns = 0;
   uint32_t out_s = 0;
   int xkind = X_ERR, xpos = 0;
@@ -663,7 +681,7 @@ __device__ DCMP_PHASE_A_INLINE void phase_a_lane(ParSmem &S, uint32_t (*ckpt)[PT
     // has often found the true token boundaries by the time its own bits begin (lane 0 starts on one).
     cu.start(q0 - imin(WARMUP_BITS, tid * SUB_BITS), lmask); // (never before lane 0's start, which is a token boundary)
     while (cu.q < q0 || !cu.at_token()) {
-      if (dec_step<false>(S.tbl, S.win, cu, lmask, dmask, lroot, droot, tok, no) >= STEP_EOB) { cu.start(q0, lmask); break; }
+      if (dec_step<false>(S.tbl, win, cu, lmask, dmask, lroot, droot, tok, no) >= STEP_EOB) { cu.start(q0, lmask); break; }
     }
     int tstart = 0;
     for (;;) {
@@ -682,7 +700,7 @@ __device__ DCMP_PHASE_A_INLINE void phase_a_lane(ParSmem &S, uint32_t (*ckpt)[PT
           last_ck = ck;
         }
       }
-      const int r = dec_step<true>(S.tbl, S.win, cu, lmask, dmask, lroot, droot, tok, no);
+      const int r = dec_step<true>(S.tbl, win, cu, lmask, dmask, lroot, droot, tok, no);
       if (r == STEP_NONE) continue;
       if (r == STEP_EOB) { xkind = X_EOB; xpos = cu.q - q0; break; }
       if (r == STEP_ERR) { xkind = X_ERR; xpos = tstart; break; }
@@ -711,6 +729,7 @@ inflate_parallel_kernel(int fmt, int64_t nstreams, const uint8_t *src_base, cons
   const int warp = tid >> 5;
   RoundMeta &M = *reinterpret_cast<RoundMeta *>(S.sym);
   uint32_t(*ckpt)[PT] = M.ckpt;
+  const uint32_t *const win = win_of(S);
 
   if (tid == 0) {
     mbar_init(&S.mbar, 1);
@@ -792,7 +811,7 @@ inflate_parallel_kernel(int fmt, int64_t nstreams, const uint8_t *src_base, cons
         if (tid == 0 && !ahead && !ahead2) {
           STAT(g_stats.hdr_rounds++;)
           HdrBits hb;
-          hb.init((const uint8_t *)S.win, bit0, HDR_BYTES);
+          hb.init((const uint8_t *)win_of(S), bit0, HDR_BYTES);
           int64_t avail = 8 * S.src_len - base_bit + bit0; // valid bits measured in window coordinates
           int nx = NEXT_CONTINUE;
           hb.refill();
@@ -821,7 +840,7 @@ inflate_parallel_kernel(int fmt, int64_t nstreams, const uint8_t *src_base, cons
               if (8 * S.src_len - sb < 32) nx = NEXT_RETRY;
               else {
                 HdrBits h2;
-                h2.init((const uint8_t *)S.win, (int)(sb - base_bit) + bit0, HDR_BYTES);
+                h2.init((const uint8_t *)win_of(S), (int)(sb - base_bit) + bit0, HDR_BYTES);
                 h2.refill();
                 const uint32_t len = h2.pop(16), nlen = h2.pop(16);
                 const int64_t payload = (sb >> 3) + 4;
@@ -964,7 +983,7 @@ inflate_parallel_kernel(int fmt, int64_t nstreams, const uint8_t *src_base, cons
                 }
                 if (nh == HEAD_CAP || out_h > (uint32_t)(LANE_BYTE_CAP - 258)) { hcat = H_TERM; hkind = X_CAP; hpos = p; break; }
               }
-              const int r = dec_step<true>(S.tbl, S.win, cu, lmask, dmask, lroot, droot, tok, no);
+              const int r = dec_step<true>(S.tbl, win, cu, lmask, dmask, lroot, droot, tok, no);
               if (r == STEP_NONE) continue;
               if (r == STEP_EOB) { hcat = H_TERM; hkind = X_EOB; hpos = cu.q - q0; break; }
               if (r == STEP_ERR) { hcat = H_TERM; hkind = X_ERR; hpos = tstart; break; }
@@ -1133,13 +1152,31 @@ inflate_parallel_kernel(int fmt, int64_t nstreams, const uint8_t *src_base, cons
       const uint32_t E = bias + round_out; // one past the last symbol of the slice
       // A block ended in this round and another one follows: the last warp, when the round left it no lanes to
       // replay, parses the next header out of the staged window while the other warps are in phase D.
-      if (s0 == 0 && S.next == NEXT_HEADER && tid == PT - 32 && n_valid <= PT - 32) {
-        const int64_t staged = 8 * (vend - v0 > WIN_BYTES ? (int64_t)WIN_BYTES : vend - v0); // window bits that hold input
-        const int64_t hbit = bit0 + (S.base_bit - base_bit);                              // where the header starts
+#if DCMP_WIN_OVERLAY
+      // (the window is about to be overwritten by symbols: the header's bytes are saved first; CTA-uniform condition)
+      const bool nh_try = s0 == 0 && S.next == NEXT_HEADER && n_valid <= PT - 32;
+      const int nh_w0 = (int)((bit0 + (S.base_bit - base_bit)) >> 5) & ~3; // first window word saved (16-byte aligned)
+      if (nh_try) {
+        for (int i = tid; i < HDR_BYTES / 4; i += PT) S.nh_win[i] = nh_w0 + i < WIN_BYTES / 4 ? win[nh_w0 + i] : 0u;
+        __syncthreads();
+      }
+#else
+      const bool nh_try = s0 == 0 && S.next == NEXT_HEADER && n_valid <= PT - 32;
+      const int nh_w0 = 0;
+#endif
+      if (nh_try && tid == PT - 32) {
+        int64_t staged = 8 * (vend - v0 > WIN_BYTES ? (int64_t)WIN_BYTES : vend - v0); // window bits that hold input
+        if (DCMP_WIN_OVERLAY && staged > 32 * (int64_t)nh_w0 + 8 * HDR_BYTES) staged = 32 * (int64_t)nh_w0 + 8 * HDR_BYTES;
+        staged -= 32 * (int64_t)nh_w0;                                                   // (coordinates of the saved copy)
+        const int64_t hbit = bit0 + (S.base_bit - base_bit) - 32 * (int64_t)nh_w0;       // where the header starts
         if (hbit + 64 < staged) {
           HdrBits hb;
-          hb.init((const uint8_t *)S.win, (int)hbit, WIN_BYTES);
-          int64_t avail = 8 * S.src_len - base_bit + bit0; // valid bits measured in window coordinates
+#if DCMP_WIN_OVERLAY
+          hb.init((const uint8_t *)S.nh_win, (int)hbit, HDR_BYTES);
+#else
+          hb.init((const uint8_t *)win, (int)hbit, WIN_BYTES);
+#endif
+          int64_t avail = 8 * S.src_len - base_bit + bit0 - 32 * (int64_t)nh_w0; // valid bits measured in the same coordinates
           if (avail > staged) avail = staged;
           hb.refill();
           const int last = (int)hb.pop(1);
