@@ -40,9 +40,9 @@ void launch_lzo_decode(int mode, int64_t n, const uint8_t *src_base, const int64
 int launch_lzo_parallel(int mode, int64_t n, const uint8_t *src_base, const int64_t *src_off, const int64_t *src_len,
                         uint8_t *dst_base, const int64_t *dst_off, const int64_t *dst_cap, int64_t *consumed,
                         int64_t *produced, int32_t *status, cudaStream_t stream);
-int launch_deflate(int level, int fmt, int64_t nstreams, int64_t nchunks, const uint8_t *src_base, const void *chunks,
-                   const int64_t *first_chunk, void *outs, uint8_t *slots, int64_t *chunk_dst, uint32_t *tok_scratch,
-                   unsigned long long *work_counter, int ctas, uint8_t *dst_base, const int64_t *dst_off,
+int launch_deflate(int level, int fmt, int64_t nstreams, int64_t nchunks, int64_t nsmall, const uint8_t *src_base, const void *chunks,
+                   const int64_t *first_chunk, void *outs, uint8_t *slots, int64_t *chunk_dst, uint8_t *scratch,
+                   int sm_count, uint8_t *dst_base, const int64_t *dst_off,
                    const int64_t *dst_cap, int64_t *written, int32_t *status, cudaStream_t stream);
 void launch_gzip_wrap(int64_t n, int level, int os, const uint8_t *src_base, const int64_t *src_off, const int64_t *src_len,
                       uint8_t *dst_base, const int64_t *dst_off, const int64_t *dst_cap, int64_t *written, int32_t *status,
@@ -50,8 +50,8 @@ void launch_gzip_wrap(int64_t n, int level, int os, const uint8_t *src_base, con
 void launch_deflate_queue(const int32_t *cmds, int64_t n, int last, uint32_t *tok, uint32_t *slot, uint8_t *dst, int64_t cap, int64_t *written,
                           int32_t *status, cudaStream_t stream);
 void launch_deflate_tmake(const int32_t *freqs, int length, int max_bits, int32_t *lens, int32_t *codes, int32_t *max_code, cudaStream_t stream);
-size_t deflate_tok_bytes_per_cta();
-int deflate_ctas_per_sm();
+size_t deflate_scratch_bytes(int sm_count);
+int deflate_small_chunk();
 size_t deflate_slot_bytes();
 int deflate_chunk_size();
 struct DfChunkHost { int64_t src_off; int32_t len; int32_t stream; int32_t flags; int32_t hist; }; // = deflate.cu's DfChunk
@@ -99,8 +99,7 @@ struct dcmp_engine {
     return DCMP_API_OK;
   }
   // deflate: persistent CTAs (3 per SM), their token scratch, and a growable arena for the per-chunk state
-  int def_ctas = 0;
-  uint8_t *d_def_scratch = nullptr;  // [work counter (256 B) | token scratch of every CTA]
+  uint8_t *d_def_scratch = nullptr;  // [work counters (256 B) | token scratch of every CTA of the two kernels]
   uint8_t *d_def_arena = nullptr;
   size_t def_arena_cap = 0;
   // host-facing calls: three-stage pipeline (H2D | kernels | D2H) over slices of the batch
@@ -532,10 +531,10 @@ int dcmp_deflate_batch_device(dcmp_engine *e, int level, int fmt, int64_t n, con
   }
   first[n] = (int64_t)chunks.size();
   const int64_t nc = (int64_t)chunks.size();
-  if (!e->d_def_scratch) {
-    e->def_ctas = dcmp::deflate_ctas_per_sm() * (e->sm_count > 0 ? e->sm_count : 148);
-    CU(cudaMalloc(&e->d_def_scratch, 256 + (size_t)e->def_ctas * dcmp::deflate_tok_bytes_per_cta()));
-  }
+  int64_t nsmall = 0; // small single-chunk streams: the warp-per-chunk kernel's share of the batch
+  for (const auto &c : chunks) nsmall += (c.len <= dcmp::deflate_small_chunk() && c.hist == 0) ? 1 : 0;
+  const int sms = e->sm_count > 0 ? e->sm_count : 148;
+  if (!e->d_def_scratch) CU(cudaMalloc(&e->d_def_scratch, dcmp::deflate_scratch_bytes(sms)));
   { const int rc0 = e->chain_begin(st); if (rc0 != DCMP_API_OK) return rc0; }
   const size_t slot = dcmp::deflate_slot_bytes();
   size_t o_chunks = 0;
@@ -566,11 +565,9 @@ int dcmp_deflate_batch_device(dcmp_engine *e, int level, int fmt, int64_t n, con
     CU(cudaMemcpyAsync(A + o_goff, h_dst_off, (size_t)n * 8, cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(A + o_gcap, h_dst_cap, (size_t)n * 8, cudaMemcpyHostToDevice, st));
   }
-  unsigned long long *counter = (unsigned long long *)e->d_def_scratch;
-  CU(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), st));
-  int rc = dcmp::launch_deflate(level, fmt, n, nc, d_src_base, A + o_chunks, (const int64_t *)(A + o_first), A + o_outs,
-                                A + o_slots, (int64_t *)(A + o_cdst), (uint32_t *)(e->d_def_scratch + 256), counter,
-                                e->def_ctas, d_dst_base, (const int64_t *)(A + o_doff), (const int64_t *)(A + o_dcap),
+  int rc = dcmp::launch_deflate(level, fmt, n, nc, nsmall, d_src_base, A + o_chunks, (const int64_t *)(A + o_first), A + o_outs,
+                                A + o_slots, (int64_t *)(A + o_cdst), e->d_def_scratch,
+                                sms, d_dst_base, (const int64_t *)(A + o_doff), (const int64_t *)(A + o_dcap),
                                 d_written, d_status, st);
   if (rc != 0) { set_err("launch_deflate", (cudaError_t)rc); return DCMP_API_CUDA_ERROR; }
   e->launches += 3;

@@ -97,3 +97,23 @@ def lzo_block(literals, off, length):
         o = off - 16384
         out += count(7, 0x10 | ((o >> 11) & 8)) + ((o & 0x3fff) << 2).to_bytes(2, "little")
     return bytes(out + b"\x11\x00\x00")
+
+
+def deflate_window_edge_stream():
+    """A stream whose only good match at the start of every 32 KiB half is the start of the half before last... except that
+    it is not: halves 1 and 2 begin with the same 16 bytes B, half 0 with 16 other bytes A whose first four hash (the
+    compressor's hash4, 11 bits) like B's.  The candidate for the start of half 1 is therefore the start of half 0, exactly
+    32768 back — the far end of the window — and the bytes there are A: a compressor that has let the staging of half 1
+    spill over them (they are followed in the ring by half 2's first bytes, B) emits a match the decoder resolves to A."""
+    def h(b4):
+        return ((int.from_bytes(b4, "little") * 0x9E3779B1) & 0xFFFFFFFF) >> 21
+    B = bytes(range(200, 216))
+    A = None
+    for x in range(1, 1 << 16):
+        cand = bytes([x & 255, x >> 8, 7, 9])
+        if h(cand) == h(B[:4]) and cand != B[:4]:
+            A = cand + bytes(range(100, 112))
+            break
+    assert A is not None and h(B[:4]) != h(bytes(4))
+    z = bytes(32768 - 16)
+    return A + z + B + z + B + z[:20000]

@@ -99,6 +99,19 @@ def t_make(freqs, length, max_length=15):
     return lens[:length].tolist(), codes[:length].tolist(), mc
 
 
+def t_make_fast(freqs, length, max_length=15):
+    """The CTA-per-chunk compressor's builder (df_build_code_fast) on the emulator: (lengths, codes, max_code)."""
+    L = lib()
+    f = np.zeros(288, dtype=np.int32)
+    fr = np.asarray(freqs, dtype=np.int32)[:length]
+    f[:len(fr)] = fr
+    lens, codes = np.zeros(288, dtype=np.int32), np.zeros(288, dtype=np.int32)
+    L.emu_t_make_fast.restype = C.c_int
+    L.emu_t_make_fast.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    mc = L.emu_t_make_fast(length, max_length, C.c_void_p(f.ctypes.data), C.c_void_p(lens.ctypes.data), C.c_void_p(codes.ctypes.data))
+    return lens[:length].tolist(), codes[:length].tolist(), mc
+
+
 def def_encode_queue(cmds, last=True, cap=None):
     """deflate_queue_kernel on the emulator: (status, bytes)."""
     L = lib()

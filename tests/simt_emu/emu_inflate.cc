@@ -88,13 +88,29 @@ int emu_deflate_batch(int level, int fmt, int64_t n, const uint8_t *src, const i
   std::vector<DfChunkOut> outs(nc);
   std::vector<uint8_t> slots((size_t)nc * DF_SLOT);
   std::vector<int64_t> cdst(nc);
+  // the two compressors share the batch as in launch_deflate: small single-chunk streams go to the warp-per-chunk kernel,
+  // everything else to the CTA-per-chunk kernel (DCMP_EMU_DEF_KERNEL=warp: all to the former)
+  const char *fk = getenv("DCMP_EMU_DEF_KERNEL");
+  const bool force_warp = fk && fk[0] == 'w';
+  int64_t nsmall = 0;
+  for (const auto &c : chunks) nsmall += (c.len <= DF_SMALL && c.hist == 0) ? 1 : 0;
+  if (force_warp) nsmall = nc;
   int ctas = 2;
-  std::vector<uint32_t> tok((size_t)ctas * DF_WARPS * DF_CHUNK);
-  unsigned long long counter = 0;
-  simt::launch(simt::dim3(ctas), simt::dim3(DF_WARPS * 32), deflate_smem_bytes(level), [&]() {
-    if (level >= 7) deflate_chunk_kernel<DF_HASH_BITS_BEST>(level, fmt == DCMP_FMT_ZLIB, nc, src, chunks.data(), outs.data(), slots.data(), tok.data(), &counter);
-    else deflate_chunk_kernel<DF_HASH_BITS_FAST>(level, fmt == DCMP_FMT_ZLIB, nc, src, chunks.data(), outs.data(), slots.data(), tok.data(), &counter);
-  });
+  unsigned long long counters[2] = {0, 0};
+  if (nc - nsmall > 0) {
+    std::vector<uint32_t> tokc((size_t)ctas * DF_CHUNK);
+    simt::launch(simt::dim3(ctas), simt::dim3(DC_T), deflate_cta_smem_bytes(level), [&]() {
+      if (level >= 7) deflate_cta_kernel<16>(level, fmt == DCMP_FMT_ZLIB, nc, src, chunks.data(), outs.data(), slots.data(), tokc.data(), &counters[0], 0);
+      else deflate_cta_kernel<8>(level, fmt == DCMP_FMT_ZLIB, nc, src, chunks.data(), outs.data(), slots.data(), tokc.data(), &counters[0], 0);
+    });
+  }
+  if (nsmall > 0) {
+    std::vector<uint32_t> tok((size_t)ctas * DF_WARPS * (force_warp ? DF_CHUNK : DF_SMALL));
+    simt::launch(simt::dim3(ctas), simt::dim3(DF_WARPS * 32), deflate_smem_bytes(level), [&]() {
+      if (level >= 7) deflate_chunk_kernel<DF_HASH_BITS_BEST>(level, fmt == DCMP_FMT_ZLIB, nc, src, chunks.data(), outs.data(), slots.data(), tok.data(), &counters[1], force_warp ? 0 : 1);
+      else deflate_chunk_kernel<DF_HASH_BITS_FAST>(level, fmt == DCMP_FMT_ZLIB, nc, src, chunks.data(), outs.data(), slots.data(), tok.data(), &counters[1], force_warp ? 0 : 1);
+    });
+  }
   simt::launch(simt::dim3((unsigned)((n + 3) / 4)), simt::dim3(128), 0, [&]() {
     deflate_plan_kernel(fmt, level, n, first.data(), outs.data(), chunks.data(), dst, doff, dcap, cdst.data(), written, status);
   });
@@ -109,7 +125,7 @@ int emu_def_encode_queue(const int32_t *cmds, int64_t n, int last, uint8_t *dst,
   using namespace dcmp;
   std::vector<uint32_t> tok((size_t)n + 8), slot((size_t)n * 2 + 1024);
   int32_t status = -1;
-  simt::launch(simt::dim3(1), simt::dim3(32), sizeof(DfSmemT<DF_HASH_BITS_FAST>) + 128, [&]() {
+  simt::launch(simt::dim3(1), simt::dim3(32), sizeof(DfSmemT<DF_HASH_BITS_BEST, uint64_t>) + 128, [&]() {
     deflate_queue_kernel(cmds, n, last, tok.data(), slot.data(), dst, cap, written, &status);
   });
   return status;
@@ -117,9 +133,16 @@ int emu_def_encode_queue(const int32_t *cmds, int64_t n, int last, uint8_t *dst,
 int emu_t_make(int length, int max_bits, const int32_t *freqs, int32_t *lens, int32_t *codes) {
   using namespace dcmp;
   int32_t mc = -1;
-  simt::launch(simt::dim3(1), simt::dim3(32), sizeof(DfSmemT<DF_HASH_BITS_FAST>) + 128, [&]() {
+  simt::launch(simt::dim3(1), simt::dim3(32), sizeof(DfSmemT<DF_HASH_BITS_BEST, uint64_t>) + 128, [&]() {
     deflate_tmake_kernel(freqs, length, max_bits, lens, codes, &mc);
   });
+  return mc;
+}
+
+int emu_t_make_fast(int length, int max_bits, const int32_t *freqs, int32_t *lens, int32_t *codes) {
+  using namespace dcmp;
+  int32_t mc = -1;
+  simt::launch(simt::dim3(1), simt::dim3(32), 16384, [&]() { deflate_tmake_fast_kernel(freqs, length, max_bits, lens, codes, &mc); });
   return mc;
 }
 

@@ -8,6 +8,8 @@ import os
 import shutil
 import zlib
 
+import numpy as np
+
 import pytest
 
 import workloads
@@ -118,6 +120,46 @@ def test_deflate_round_trip(emu):
         for (st, written, comp), x in zip(res, ins):
             assert st == 0 and zlib.decompress(comp) == x
             assert oracle.zl_inflate_ns(comp, len(x))[:3] == (0, written, len(x))
+
+
+def test_deflate_window_edge_at_distance_32768_in_an_unaligned_batch(emu):
+    """The far end of the window in streams that start at odd offsets of the batch: the compressor stages 16-byte granules,
+    and the bytes around a half are window, not padding (tests/cases.py: deflate_window_edge_stream)."""
+    edge = cases.deflate_window_edge_stream()
+    ins = [b"abc", edge, b"z" * 7, edge[5:], edge]
+    for level in (1, 6, 9):
+        res = emu.deflate_streams(ins, [len(x) + len(x) // 8 + 64 for x in ins], level=level, fmt=batch.FMT_ZLIB)
+        for (st, written, comp), x in zip(res, ins):
+            assert st == 0 and zlib.decompress(comp) == x
+            assert oracle.zl_inflate_ns(comp, len(x))[:3] == (0, written, len(x))
+
+
+def test_fast_code_builder_is_complete_limited_and_as_cheap_as_t_make(emu):
+    """df_build_code_fast (the CTA-per-chunk compressor's Huffman builder: sort, two-queue merge, pointer jumping, gen_bitlen's
+    repair) against De.T.make as the oracle restates it: every used symbol has a code, no code is longer than the limit, the
+    Kraft sum is exactly 1 (De.Inf.huffman rejects anything else, de.ml:544-550) and the block costs what zlib's tree costs —
+    flat, skewed (the overflow repair), sparse and empty histograms of the three alphabets."""
+    import random
+    rng = random.Random(5)
+    for n, mb in ((286, 15), (30, 15), (19, 7)):
+        for t in range(60):
+            kind = t % 6
+            if kind == 0: f = [rng.choice([0, 0, 1, 2, 3, 50, 1000, rng.randrange(1 << 16)]) for _ in range(n)]
+            elif kind == 1: f = [rng.randrange(1, 300) for _ in range(n)]
+            elif kind == 2: f = [1 << (j % 17) for j in range(n)]
+            elif kind == 3: f = [rng.randrange(200, 260) for _ in range(n)]
+            elif kind == 4:
+                f = [0] * n
+                for _ in range(rng.randrange(0, 3)): f[rng.randrange(n)] = rng.randrange(1, 5)
+            else: f = [rng.choice([0, 1]) for _ in range(n)]
+            l1, c1, m1 = emu.t_make_fast(f, n, mb)
+            l0, c0, m0 = oracle.t_make(f, n, mb)
+            assert m1 == m0 and max(l1) <= mb and all(l1[i] > 0 for i in range(n) if f[i]), (n, t)
+            assert sum(1 << (mb - l) for l in l1 if l) == 1 << mb, (n, t)
+            assert sum(a * b for a, b in zip(f, l1)) <= sum(a * b for a, b in zip(f, l0)) * 1.002 + 2, (n, t)
+            # canonical, bit-reversed codes: distinct and prefix-free follows from the Kraft equality + canonical order
+            seen = {(l, c) for l, c in zip(l1, c1) if l}
+            assert len(seen) == sum(1 for l in l1 if l), (n, t)
 
 
 def test_encoder_kats_on_the_device_kernels(emu):

@@ -54,6 +54,17 @@ def test_roundtrip_vs_oracle_zlib_and_gpu_inflate(level, fmt, eng):
         assert batch.deflate_streams([b"\x01"], level=0, engine=eng)[0][2] == bytes.fromhex("010100feff01")
 
 
+def test_window_edge_at_distance_32768_in_an_unaligned_batch(eng):
+    """The far end of the window in streams that start at odd offsets of the batch: the compressor stages whole 16-byte
+    granules by TMA and the ragged ends byte-wise; the bytes around a half are window, not padding
+    (tests/cases.py: deflate_window_edge_stream)."""
+    from tests import cases
+    edge = cases.deflate_window_edge_stream()
+    ins = [b"abc", edge, b"z" * 7, edge[5:], edge, bytes(9) + edge]
+    for level in (1, 6, 9):
+        _roundtrip(ins, batch.deflate_streams(ins, level=level, fmt=batch.FMT_ZLIB, engine=eng), batch.FMT_ZLIB, eng)
+
+
 def test_compresses_text(eng):
     txt = workloads.text(1 << 20, 9)
     st, wr, comp = batch.deflate_streams([txt], level=6, fmt=batch.FMT_ZLIB, engine=eng)[0]
