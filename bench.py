@@ -281,23 +281,41 @@ def run_c4(args, rank, local_rank, world):
     # collectives left are the index broadcast and one barrier that closes the step
     peer = world > 1 and args.c4_transport == "peer"
     if peer:
-        handles = [None, None]
+        # (the member index is part of the file: it sits in rank 0's memory too and is read through the same mapping)
+        handles = [None, None, None, None]
         if rank == 0:
-            handles = [blob.untyped_storage()._share_cuda_(), out_full.untyped_storage()._share_cuda_()]
+            index_dev = torch.from_numpy(np.ascontiguousarray(index, dtype=np.int64)).to(dev).view(torch.uint8).reshape(-1)
+            handles = [blob.untyped_storage()._share_cuda_(), out_full.untyped_storage()._share_cuda_(),
+                       index_dev.untyped_storage()._share_cuda_(), tuple(index.shape)]
         dist.broadcast_object_list(handles, src=0)
         if rank != 0:
             def _open(h):
                 st_ = torch.UntypedStorage._new_shared_cuda(*h)
                 return torch.empty(0, dtype=torch.uint8, device=st_.device).set_(st_)
-            blob, out_full = _open(handles[0]), _open(handles[1])
+            blob, out_full, index_dev = _open(handles[0]), _open(handles[1]), _open(handles[2])
+        idx_shape = handles[3]
+        idx_bytes = int(idx_shape[0]) * int(idx_shape[1]) * 8
+        idx_local = torch.empty(idx_bytes, dtype=torch.uint8, device=dev)
+        idx_pinned = torch.empty(idx_bytes, dtype=torch.uint8).pin_memory()
         s_in, s_out = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
         token = torch.zeros(1, device=dev)
+
+    def fetch_index():
+        """The member index on this rank's host: NCCL broadcast, or — peer transport — a copy out of rank 0's mapped memory."""
+        if world == 1:
+            return index
+        if not peer:
+            return shard.broadcast_index(index, 0, dev)
+        idx_local.copy_(index_dev[:idx_bytes], non_blocking=True)      # NVLink (rank 0: a local copy)
+        idx_pinned.copy_(idx_local, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return idx_pinned.numpy().view(np.int64).reshape(idx_shape)
 
     def one_step(timers=None):
         ev = lambda: torch.cuda.Event(enable_timing=True)
         marks = [ev() for _ in range(4)]
         marks[0].record()
-        idx = shard.broadcast_index(index, 0, dev) if world > 1 else index
+        idx = fetch_index()
         n = idx.shape[0]
         parts = shard.partition(idx[:, 1] + idx[:, 2], world)
         ends_c = np.concatenate([[0], np.cumsum(idx[:, 1])])
@@ -314,9 +332,14 @@ def run_c4(args, rank, local_rank, world):
                 return []
             ps = shard.partition(idx[ra:rb, 2], min(pieces_per_rank, rb - ra))
             return [(x, y) for x, y in ps if y > x]
-        all_cuts = [cuts_of(r) for r in range(world)]
-        my_cuts = all_cuts[rank]
-        npieces = max(len(c) for c in all_cuts) if all_cuts else 0
+        if peer:   # (every rank moves its own pieces: nobody needs the others' cuts)
+            all_cuts = None
+            my_cuts = cuts_of(rank)
+            npieces = len(my_cuts)
+        else:
+            all_cuts = [cuts_of(r) for r in range(world)]
+            my_cuts = all_cuts[rank]
+            npieces = max(len(c) for c in all_cuts) if all_cuts else 0
         scatter_works = [[] for _ in range(npieces)]
         in_events = [None] * npieces
         if peer:
@@ -353,11 +376,9 @@ def run_c4(args, rank, local_rank, world):
         else:
             local = blob[ranges_c[0][0]:ranges_c[0][1]]
         marks[1].record()
-        so = torch.from_numpy((idx[a:b, 0] - ends_c[a]).astype(np.int64)).to(dev)
-        sl = torch.from_numpy(idx[a:b, 1].astype(np.int64)).to(dev)
         do_h = (ends_o[a:b] - ends_o[a]).astype(np.int64)
-        do = torch.from_numpy(do_h).to(dev)
-        dc = torch.from_numpy(idx[a:b, 2].astype(np.int64)).to(dev)
+        tabs = torch.from_numpy(np.stack([idx[a:b, 0] - ends_c[a], idx[a:b, 1], do_h, idx[a:b, 2]]).astype(np.int64)).to(dev)  # one upload
+        so, sl, do, dc = tabs[0], tabs[1], tabs[2], tabs[3]
         my_out = out_full[ranges_o[0][0]:ranges_o[0][1]] if rank == 0 else torch.empty(ranges_o[rank][1] - ranges_o[rank][0] + 64, dtype=torch.uint8, device=dev)
         cons = torch.zeros(max(m, 1), dtype=torch.int64, device=dev)
         prod = torch.zeros(max(m, 1), dtype=torch.int64, device=dev)

@@ -28,7 +28,7 @@ def main():
     ap.add_argument("--c4-mib", type=int, default=512)
     ap.add_argument("--c3-mib", type=int, default=1024)
     ap.add_argument("--c3-level", type=int, default=6)
-    ap.add_argument("--c5-blocks", type=int, default=256)
+    ap.add_argument("--c5-blocks", type=int, default=1024)
     ap.add_argument("--steps", type=int, default=5)
     args = ap.parse_args()
     import torch

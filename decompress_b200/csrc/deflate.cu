@@ -1058,7 +1058,7 @@ __device__ __forceinline__ DcLevel dc_level(int level, int WAYS) {
   c.ways = chain < WAYS ? chain : WAYS;
   c.nice = level <= 1 ? 8 : level == 2 ? 16 : level == 3 ? 32 : level == 4 ? 16 : level == 5 ? 32 : level <= 7 ? 128 : 258;
   c.lazy = level <= 3 ? 0 : level == 4 ? 4 : level <= 6 ? 16 : level == 7 ? 32 : level == 8 ? 128 : 258;
-  c.maxlong = level <= 6 ? 2 : 32;
+  c.maxlong = level <= 6 ? 2 : 3;
   return c;
 }
 
@@ -1155,9 +1155,11 @@ deflate_cta_kernel(int level, int want_adler, int64_t nchunks, const uint8_t *sr
             }
             __syncthreads();
             // -- match.  Pass 1: every bucket entry that lies in the window before p and shares its first four bytes is
-            // measured over the next four; the ones equal over all eight wait in `longm` for pass 2.
+            // measured over the next four; of the ones equal over all eight, the nearest (up to three) wait for pass 2.
+            // Everything below depends on the SET of entries in the bucket, not on their slots (which thread of a step
+            // got which slot is a race).
             int mlen = 0, mdist = 0;
-            uint32_t longm = 0;
+            uint32_t lg1 = 0x10000u, lg2 = 0x10000u, lg3 = 0x10000u; // distances of the long candidates, ascending
             const int maxlen = avail < 258 ? avail : 258;
             if (can) {
               const uint32_t maxdist = (uint32_t)min(32768, j + hist);
@@ -1174,8 +1176,11 @@ deflate_cta_kernel(int level, int want_adler, int64_t nchunks, const uint8_t *sr
                     const uint32_t dist = (p - q) & 0xffffu;
                     if (dist - 1u < maxdist && rg32(r32, q) == P4) {
                       const uint32_t x = rg32(r32, q + 4u) ^ P4b;
-                      if (x == 0u && maxlen > 8) longm |= 1u << (g * 8 + k);
-                      else {
+                      if (x == 0u && maxlen > 8) {
+                        if (dist < lg1) { lg3 = lg2; lg2 = lg1; lg1 = dist; }
+                        else if (dist < lg2) { if (dist != lg1) { lg3 = lg2; lg2 = dist; } }
+                        else if (dist < lg3 && dist != lg2) lg3 = dist;
+                      } else {
                         const int l = x ? 4 + ((__ffs((int)x) - 1) >> 3) : 8; // (capped to maxlen below)
                         if (l > mlen || (l == mlen && (int)dist < mdist)) { mlen = l; mdist = (int)dist; }
                       }
@@ -1183,21 +1188,20 @@ deflate_cta_kernel(int level, int want_adler, int64_t nchunks, const uint8_t *sr
                   }
                 }
               }
+              // (measuring more than two candidates that share eight bytes buys 0.15 % of output at level 6: the deep levels take three)
+              if (L.maxlong < 3) lg3 = 0x10000u;
             }
-            // (measuring more than two candidates that share eight bytes buys 0.15 % of output at level 6: the deep levels do)
-            while (__popc(longm) > L.maxlong) longm &= ~(0x80000000u >> __clz((int)longm));
             // Pass 2: the long candidates, eight bytes per step; the lanes of a warp step together (a lane takes its next
             // candidate when one ends), so the loop runs as long as the warp's longest chain of them, not their sum
             {
               uint32_t q = 0, dist = 0;
               int l = 0;
               bool busy = false;
-              while (__any_sync(0xffffffffu, busy || longm != 0u)) {
-                if (!busy && longm != 0u) {
-                  const int k = __ffs((int)longm) - 1;
-                  longm &= longm - 1u;
-                  q = S.tab[hsh * WAYS + k];
-                  dist = (p - q) & 0xffffu;
+              while (__any_sync(0xffffffffu, busy || lg1 != 0x10000u)) {
+                if (!busy && lg1 != 0x10000u) {
+                  dist = lg1;
+                  lg1 = lg2; lg2 = lg3; lg3 = 0x10000u;
+                  q = (p - dist) & 0xffffu;
                   l = 8;
                   busy = true;
                 }
@@ -1212,7 +1216,7 @@ deflate_cta_kernel(int level, int want_adler, int64_t nchunks, const uint8_t *sr
                     if (l > maxlen) l = maxlen;
                     if (l > mlen || (l == mlen && (int)dist < mdist)) { mlen = l; mdist = (int)dist; }
                     busy = false;
-                    if (mlen >= L.nice) longm = 0; // nice_length: good enough, stop searching (de.ml:4158)
+                    if (mlen >= L.nice) lg1 = 0x10000u; // nice_length: good enough, stop searching (de.ml:4158)
                   }
                 }
               }

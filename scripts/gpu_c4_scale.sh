@@ -3,7 +3,7 @@
 # Usage (from the build box): gpurun --gpus 8 --timeout 1200 -- scripts/gpu_c4_scale.sh [MiB]
 MIB=${1:-8192}
 mkdir -p gpurun_out
-for n in 8 4 2 1; do
+for n in ${2:-8 4 2 1}; do
   if [ $n = 1 ]; then
     timeout 600 python bench.py --workload c4 --c4-mib $MIB --steps 3 --warmup 3 2> gpurun_out/c4_n$n.err | grep "^{" > gpurun_out/c4_n$n.json
   else
