@@ -315,70 +315,101 @@ def run_c4(args, rank, local_rank, world):
         ev = lambda: torch.cuda.Event(enable_timing=True)
         marks = [ev() for _ in range(4)]
         marks[0].record()
-        idx = fetch_index()
-        n = idx.shape[0]
-        parts = shard.partition(idx[:, 1] + idx[:, 2], world)
-        ends_c = np.concatenate([[0], np.cumsum(idx[:, 1])])
-        ends_o = np.concatenate([[0], np.cumsum(idx[:, 2])])
-        ranges_c = [(int(ends_c[a]), int(ends_c[b])) for a, b in parts]
-        ranges_o = [(int(ends_o[a]), int(ends_o[b])) for a, b in parts]
-        a, b = parts[rank]
-        m = b - a
-        # pieces: contiguous member ranges of about equal output.  Compressed slabs arrive piece by piece and a piece is
-        # decoded as soon as it is there; its output leaves for rank 0 while the next piece is being decoded.
-        def cuts_of(r):
-            ra, rb = parts[r]
-            if rb == ra:
-                return []
-            ps = shard.partition(idx[ra:rb, 2], min(pieces_per_rank, rb - ra))
-            return [(x, y) for x, y in ps if y > x]
-        if peer:   # (every rank moves its own pieces: nobody needs the others' cuts)
-            all_cuts = None
-            my_cuts = cuts_of(rank)
-            npieces = len(my_cuts)
-        else:
-            all_cuts = [cuts_of(r) for r in range(world)]
-            my_cuts = all_cuts[rank]
-            npieces = max(len(c) for c in all_cuts) if all_cuts else 0
-        scatter_works = [[] for _ in range(npieces)]
-        in_events = [None] * npieces
         if peer:
+            # Plan on the device: the index comes over NVLink out of rank 0's mapping, prefix sums and the two levels of cuts
+            # (ranks, then this rank's pieces) are a handful of small kernels, and only 3 x (world + 1) + 3 x (pieces + 1)
+            # integers ever reach the host (round 2, first version: the whole 2.3 MB index went to the host and numpy
+            # planned there, 5.1 ms of a 17.4 ms step at 8 GPUs).
+            idx_local.copy_(index_dev[:idx_bytes], non_blocking=True)
+            I = idx_local.view(torch.int64).view(int(idx_shape[0]), int(idx_shape[1]))
+            n = I.shape[0]
+            z1 = torch.zeros(1, dtype=torch.int64, device=dev)
+            ends_c_d = torch.cat([z1, torch.cumsum(I[:, 1], 0)])
+            ends_o_d = torch.cat([z1, torch.cumsum(I[:, 2], 0)])
+            cuts_d = shard.partition_cuts(I[:, 1] + I[:, 2], world)
+            head = torch.stack([cuts_d, ends_c_d[cuts_d], ends_o_d[cuts_d]]).cpu().numpy()
+            parts = [(int(head[0][r]), int(head[0][r + 1])) for r in range(world)]
+            ranges_c = [(int(head[1][r]), int(head[1][r + 1])) for r in range(world)]
+            ranges_o = [(int(head[2][r]), int(head[2][r + 1])) for r in range(world)]
+            job_src, job_out = int(head[1][world]), int(head[2][world])
+            a, b = parts[rank]
+            m = b - a
+            my_cuts, pc_c, pc_o = [], {}, {}
+            if m > 0:
+                pc_d = shard.partition_cuts(I[a:b, 2], min(pieces_per_rank, m))
+                pinfo = torch.stack([pc_d, ends_c_d[a + pc_d], ends_o_d[a + pc_d]]).cpu().numpy()
+                for i in range(pinfo.shape[1] - 1):
+                    x, y = int(pinfo[0][i]), int(pinfo[0][i + 1])
+                    if y > x:
+                        my_cuts.append((x, y))
+                        pc_c[x], pc_c[y], pc_o[x], pc_o[y] = int(pinfo[1][i]), int(pinfo[1][i + 1]), int(pinfo[2][i]), int(pinfo[2][i + 1])
+            npieces = len(my_cuts)
+            scatter_works = [[] for _ in range(npieces)]
+            in_events = [None] * npieces
             if rank == 0:
                 local = blob[ranges_c[0][0]:ranges_c[0][1]]
             else:
                 local = torch.empty(ranges_c[rank][1] - ranges_c[rank][0] + 64, dtype=torch.uint8, device=dev)
                 s_in.wait_stream(torch.cuda.current_stream())
                 with torch.cuda.stream(s_in):
-                    for p in range(len(my_cuts)):       # pull this rank's compressed slab out of rank 0's memory, piece by piece
+                    for p in range(npieces):            # pull this rank's compressed slab out of rank 0's memory, piece by piece
                         x, y = my_cuts[p]
-                        lo, hi = int(ends_c[a + x]), int(ends_c[a + y])
-                        local[lo - int(ends_c[a]):hi - int(ends_c[a])].copy_(blob[lo:hi], non_blocking=True)
+                        local[pc_c[x] - ranges_c[rank][0]:pc_c[y] - ranges_c[rank][0]].copy_(blob[pc_c[x]:pc_c[y]], non_blocking=True)
                         in_events[p] = torch.cuda.Event()
                         in_events[p].record(s_in)
-        elif world > 1:
-            if rank == 0:
-                local = blob[ranges_c[0][0]:ranges_c[0][1]]
-            else:
-                local = torch.empty(ranges_c[rank][1] - ranges_c[rank][0] + 64, dtype=torch.uint8, device=dev)
-            for p in range(npieces):
-                ops = []
-                if rank == 0:
-                    for r in range(1, world):
-                        if p < len(all_cuts[r]):
-                            x, y = all_cuts[r][p]
-                            ra = parts[r][0]
-                            ops.append(dist.P2POp(dist.isend, blob[int(ends_c[ra + x]):int(ends_c[ra + y])], r))
-                elif p < len(my_cuts):
-                    x, y = my_cuts[p]
-                    ops.append(dist.P2POp(dist.irecv, local[int(ends_c[a + x] - ends_c[a]):int(ends_c[a + y] - ends_c[a])], 0))
-                if ops:
-                    scatter_works[p] = dist.batch_isend_irecv(ops)
+            marks[1].record()
+            so = (I[a:b, 0] - ends_c_d[a]).contiguous()
+            sl = I[a:b, 1].contiguous()
+            do = (ends_o_d[a:b] - ends_o_d[a]).contiguous()
+            dc = I[a:b, 2].contiguous()
         else:
-            local = blob[ranges_c[0][0]:ranges_c[0][1]]
-        marks[1].record()
-        do_h = (ends_o[a:b] - ends_o[a]).astype(np.int64)
-        tabs = torch.from_numpy(np.stack([idx[a:b, 0] - ends_c[a], idx[a:b, 1], do_h, idx[a:b, 2]]).astype(np.int64)).to(dev)  # one upload
-        so, sl, do, dc = tabs[0], tabs[1], tabs[2], tabs[3]
+          idx = fetch_index()
+          n = idx.shape[0]
+          parts = shard.partition(idx[:, 1] + idx[:, 2], world)
+          ends_c = np.concatenate([[0], np.cumsum(idx[:, 1])])
+          ends_o = np.concatenate([[0], np.cumsum(idx[:, 2])])
+          ranges_c = [(int(ends_c[a]), int(ends_c[b])) for a, b in parts]
+          ranges_o = [(int(ends_o[a]), int(ends_o[b])) for a, b in parts]
+          a, b = parts[rank]
+          m = b - a
+          # pieces: contiguous member ranges of about equal output.  Compressed slabs arrive piece by piece and a piece is
+          # decoded as soon as it is there; its output leaves for rank 0 while the next piece is being decoded.
+          def cuts_of(r):
+              ra, rb = parts[r]
+              if rb == ra:
+                  return []
+              ps = shard.partition(idx[ra:rb, 2], min(pieces_per_rank, rb - ra))
+              return [(x, y) for x, y in ps if y > x]
+          all_cuts = [cuts_of(r) for r in range(world)]
+          my_cuts = all_cuts[rank]
+          npieces = max(len(c) for c in all_cuts) if all_cuts else 0
+          scatter_works = [[] for _ in range(npieces)]
+          in_events = [None] * npieces
+          if world > 1:
+              if rank == 0:
+                  local = blob[ranges_c[0][0]:ranges_c[0][1]]
+              else:
+                  local = torch.empty(ranges_c[rank][1] - ranges_c[rank][0] + 64, dtype=torch.uint8, device=dev)
+              for p in range(npieces):
+                  ops = []
+                  if rank == 0:
+                      for r in range(1, world):
+                          if p < len(all_cuts[r]):
+                              x, y = all_cuts[r][p]
+                              ra = parts[r][0]
+                              ops.append(dist.P2POp(dist.isend, blob[int(ends_c[ra + x]):int(ends_c[ra + y])], r))
+                  elif p < len(my_cuts):
+                      x, y = my_cuts[p]
+                      ops.append(dist.P2POp(dist.irecv, local[int(ends_c[a + x] - ends_c[a]):int(ends_c[a + y] - ends_c[a])], 0))
+                  if ops:
+                      scatter_works[p] = dist.batch_isend_irecv(ops)
+          else:
+              local = blob[ranges_c[0][0]:ranges_c[0][1]]
+          marks[1].record()
+          do_h = (ends_o[a:b] - ends_o[a]).astype(np.int64)
+          tabs = torch.from_numpy(np.stack([idx[a:b, 0] - ends_c[a], idx[a:b, 1], do_h, idx[a:b, 2]]).astype(np.int64)).to(dev)  # one upload
+          so, sl, do, dc = tabs[0], tabs[1], tabs[2], tabs[3]
+          job_src, job_out = int(ends_c[-1]), int(ends_o[-1])
         my_out = out_full[ranges_o[0][0]:ranges_o[0][1]] if rank == 0 else torch.empty(ranges_o[rank][1] - ranges_o[rank][0] + 64, dtype=torch.uint8, device=dev)
         cons = torch.zeros(max(m, 1), dtype=torch.int64, device=dev)
         prod = torch.zeros(max(m, 1), dtype=torch.int64, device=dev)
@@ -397,7 +428,7 @@ def run_c4(args, rank, local_rank, world):
                     evd = torch.cuda.Event()
                     evd.record()
                     s_out.wait_event(evd)
-                    lo, hi = int(do_h[x]), int(do_h[y - 1] + idx[a + y - 1, 2])
+                    lo, hi = pc_o[x] - ranges_o[rank][0], pc_o[y] - ranges_o[rank][0]
                     with torch.cuda.stream(s_out):
                         out_full[ranges_o[rank][0] + lo:ranges_o[rank][0] + hi].copy_(my_out[lo:hi], non_blocking=True)
             if world > 1 and not peer:
@@ -428,7 +459,7 @@ def run_c4(args, rank, local_rank, world):
         if timers is not None:
             torch.cuda.synchronize()
             timers.append([marks[k].elapsed_time(marks[k + 1]) for k in range(3)])
-        return st, prod, m, n, int(ends_c[-1]), int(ends_o[-1])
+        return st, prod, m, n, job_src, job_out
 
     W = max(3, args.warmup)
     for _ in range(W):

@@ -314,7 +314,8 @@ __device__ int df_build_code(SM &S, const uint32_t *freq, int n, int max_bits, u
 struct DfFastTree {
   uint32_t sortbuf[512];           // (frequency << 9) | symbol, ascending; unused slots 0xffffffff
   uint32_t weight[2 * 286];        // two-queue merge: leaves [0, m), internal nodes [m, 2m - 1)
-  uint32_t info[2 * 286];          // (distance to an ancestor << 16) | that ancestor: the parent at first, the root in the end
+  uint32_t info[2][2 * 286];       // (distance to an ancestor << 16) | that ancestor: the parent at first, the root in the end
+                                   // (two copies: a doubling round reads one and writes the other)
   uint32_t bl_count[16];
   uint32_t next_code[16];
   int m;
@@ -367,28 +368,29 @@ __device__ int df_build_code_fast(SM &S, const uint32_t *freq, int n, int max_bi
       uint32_t w = 0;
 #pragma unroll
       for (int k = 0; k < 2; k++) {
-        if (li < m && (ii >= nn || wl <= wi)) { w += wl; T.info[li] = (1u << 16) | (uint32_t)nn; li++; wl = li < m ? T.weight[li] : 0xffffffffu; }
-        else { w += wi; T.info[ii] = (1u << 16) | (uint32_t)nn; ii++; wi = ii < nn ? T.weight[ii] : 0xffffffffu; }
+        if (li < m && (ii >= nn || wl <= wi)) { w += wl; T.info[0][li] = (1u << 16) | (uint32_t)nn; li++; wl = li < m ? T.weight[li] : 0xffffffffu; }
+        else { w += wi; T.info[0][ii] = (1u << 16) | (uint32_t)nn; ii++; wi = ii < nn ? T.weight[ii] : 0xffffffffu; }
       }
       T.weight[nn] = w;
       if (ii == nn) wi = w; // (the queue of internal nodes was empty: the new one is its head)
       nn++;
     }
-    T.info[2 * m - 2] = (uint32_t)(2 * m - 2); // the root: distance 0 to itself
+    T.info[0][2 * m - 2] = (uint32_t)(2 * m - 2); // the root: distance 0 to itself
   }
   __syncwarp();
-  // depths by pointer jumping (a code of a 64 KiB chunk is at most 24 deep: six doublings reach 64).  In place: a
-  // word is a consistent (distance, ancestor) pair whenever it is read, older or newer, and either doubles the reach
+  // depths by pointer jumping (a code of a 64 KiB chunk is at most 24 deep: six doublings reach 64)
   const int nodes = 2 * m - 1;
   for (int r = 0; r < 6; r++) {
+    const uint32_t *src = T.info[r & 1];
+    uint32_t *dst = T.info[(r + 1) & 1];
     for (int i = lane; i < nodes; i += 32) {
-      const uint32_t a = T.info[i], b = T.info[a & 0xffffu];
-      T.info[i] = ((a >> 16) + (b >> 16)) << 16 | (b & 0xffffu);
+      const uint32_t a = src[i], b = src[a & 0xffffu];
+      dst[i] = ((a >> 16) + (b >> 16)) << 16 | (b & 0xffffu);
     }
     __syncwarp();
   }
   for (int i = lane; i < m; i += 32) {
-    uint32_t d = T.info[i] >> 16;
+    uint32_t d = T.info[0][i] >> 16; // (six rounds: back in the first copy)
     if ((int)d > max_bits) d = (uint32_t)max_bits;
     atomicAdd(&T.bl_count[d], 1u);
   }

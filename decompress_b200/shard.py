@@ -26,6 +26,20 @@ def partition(weights, world):
     return [(cuts[r], cuts[r + 1]) for r in range(world)]
 
 
+def partition_cuts(weights, world):
+    """`partition` for a weight tensor that lives on a device (or any torch tensor): the world + 1 cut indices as an int64
+    tensor on the same device, no host round trip — the same cuts as `partition` (same prefix sums, same left-most search)."""
+    import torch
+
+    n = weights.shape[0]
+    cum = torch.cat([torch.zeros(1, dtype=torch.float64, device=weights.device), torch.cumsum(weights.to(torch.float64), 0)])
+    targets = cum[-1] * torch.arange(1, world, dtype=torch.float64, device=weights.device) / world
+    k = torch.searchsorted(cum, targets, right=False).clamp_(max=n)
+    k = torch.cummax(k, 0).values if world > 1 and k.numel() else k
+    return torch.cat([torch.zeros(1, dtype=torch.int64, device=weights.device), k.to(torch.int64),
+                      torch.full((1,), n, dtype=torch.int64, device=weights.device)])
+
+
 def my_range(weights, rank, world):
     return partition(weights, world)[rank]
 

@@ -27,6 +27,10 @@ def test_partition_properties():
             if n >= 16 * world:
                 loads = [w[a:b].sum() for a, b in parts]
                 assert max(loads) <= 1.2 * (w.sum() / world) + w.max()
+            # the tensor form (what the C4 driver runs on the device) makes the same cuts
+            import torch
+            cuts = shard.partition_cuts(torch.from_numpy(np.asarray(w, dtype=np.int64)), world).tolist()
+            assert cuts == [parts[0][0]] + [b for _, b in parts], (n, world)
 
 
 def _worker(rank, world, port, n, q):
