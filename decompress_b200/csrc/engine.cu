@@ -37,7 +37,7 @@ void launch_lzo_decode(int mode, int64_t n, const uint8_t *src_base, const int64
                        uint8_t *dst_base, const int64_t *dst_off, const int64_t *dst_cap, int64_t *consumed,
                        int64_t *produced, int32_t *status, int only_status, unsigned long long *redo_count,
                        cudaStream_t stream);
-int launch_lzo_parallel(int mode, int64_t n, const uint8_t *src_base, const int64_t *src_off, const int64_t *src_len,
+int launch_lzo_parallel(int mode, int64_t n, int sms, const uint8_t *src_base, const int64_t *src_off, const int64_t *src_len,
                         uint8_t *dst_base, const int64_t *dst_off, const int64_t *dst_cap, int64_t *consumed,
                         int64_t *produced, int32_t *status, cudaStream_t stream);
 int launch_deflate(int level, int fmt, int64_t nstreams, int64_t nchunks, int64_t nsmall, const uint8_t *src_base, const void *chunks,
@@ -421,7 +421,7 @@ int dcmp_lzo_uncompress_batch_device(dcmp_engine *e, int mode, int64_t n, const 
   if (e->mode == 0) {
     // stage 1: one CTA per block (serial opcode parse, CTA-wide copies); stage 2: the one-warp-per-block
     // kernel on exactly the blocks stage 1 gave up (malformed input, short output window, ...)
-    int rc = dcmp::launch_lzo_parallel(mode, n, d_src_base, d_src_off, d_src_len, d_dst_base, d_dst_off, d_dst_cap, d_consumed,
+    int rc = dcmp::launch_lzo_parallel(mode, n, e->sm_count > 0 ? e->sm_count : 148, d_src_base, d_src_off, d_src_len, d_dst_base, d_dst_off, d_dst_cap, d_consumed,
                                        d_produced, d_status, (cudaStream_t)cuda_stream);
     if (rc != 0) { set_err("launch_lzo_parallel", (cudaError_t)rc); return DCMP_API_CUDA_ERROR; }
     static const bool no_fallback = getenv("DCMP_LZO_NO_FALLBACK") != nullptr; // debugging aid: given-up blocks keep status 0x7f

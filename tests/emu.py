@@ -14,7 +14,7 @@ _lib = None
 def build():
     srcs = [os.path.join(ROOT, "tests", "simt_emu", f) for f in ("emu_inflate.cc", "simt_emu.cc", "simt_emu.h")]
     srcs += [os.path.join(ROOT, "decompress_b200", "csrc", f) for f in os.listdir(os.path.join(ROOT, "decompress_b200", "csrc"))
-             if f.endswith((".cu", ".cuh"))]
+             if f.endswith((".cu", ".cuh", ".inc", ".h"))]
     if os.path.exists(_SO) and all(os.path.getmtime(s) <= os.path.getmtime(_SO) for s in srcs):
         return
     os.makedirs(os.path.dirname(_SO), exist_ok=True)
@@ -54,7 +54,8 @@ def inflate_streams(streams, caps, fmt=0, mode=0, ctas=2):
 
 def lzo_blocks(blocks, caps, mode=0, which=0):
     """LZO kernels on the emulator: list of (status, consumed, produced, bytes).  which=0: CTA-per-block kernel, then the
-    general one on the blocks it gave up (like engine.cu); which=2: the general kernel alone."""
+    general one on the blocks it gave up (like engine.cu), small-round shape; which=3: the same with the large-round shape;
+    which=2: the general kernel alone."""
     from decompress_b200 import batch
 
     src, so, sl, dst, do, dc = batch.pack(blocks, caps)

@@ -51,8 +51,12 @@ int emu_lzo_batch2(int lzo_mode, int which, int64_t n, const uint8_t *src, const
   using namespace dcmp;
   int retried = 0;
   if (which != 2) {
-    simt::launch(simt::dim3((unsigned)n), simt::dim3(LZP_PT), lzo_parallel_smem_bytes(), [&]() {
-      lzo_parallel_kernel(lzo_mode, n, src, soff, slen, dst, doff, dcap, cons, prod, status);
+    // which: 0 = the CTA-per-block kernel in its small-round shape (+ the general kernel for what it gives up), 3 = in its
+    // large-round shape, 2 = the general kernel alone
+    const int shape = which == 3 ? 1 : 0;
+    simt::launch(simt::dim3((unsigned)n), simt::dim3(LZP_PT), lzo_parallel_smem_bytes(shape), [&]() {
+      if (shape) lzp_large::lzo_parallel_kernel(lzo_mode, n, src, soff, slen, dst, doff, dcap, cons, prod, status);
+      else lzp_small::lzo_parallel_kernel(lzo_mode, n, src, soff, slen, dst, doff, dcap, cons, prod, status);
     });
     for (int64_t k = 0; k < n; k++) retried += status[k] == LZP_RETRY;
     if (!retried) return 0;

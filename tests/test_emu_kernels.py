@@ -73,19 +73,22 @@ def test_lzo_goldens_and_blocks(emu):
         return bytes.fromhex(pre) * times + bytes.fromhex(post)
 
     blocks = [src(v) for v in vec]
-    for mode, fn in ((0, oracle.lzo_uncompress), (1, oracle.lzo_uncompress_with_buffer)):
-        res = emu.lzo_blocks(blocks, [1 << 16] * len(blocks), mode=mode)
-        for v, b, r in zip(vec, blocks, res):
-            rc, cons, prod, out = fn(b, 1 << 16)
-            if mode == 1 and rc == 1 and r[0] == 2:
-                continue  # a full dst is reported distinctly in mode 1 (the reference's Buffer.t is unbounded)
-            assert r[0] == _ST[rc] and r[2] == prod and r[3] == out, v["name"]
+    # (which = 0 / 3: the CTA-per-block kernel in its small-round / large-round shape, the one a batch's size picks)
+    for which in (0, 3):
+        for mode, fn in ((0, oracle.lzo_uncompress), (1, oracle.lzo_uncompress_with_buffer)):
+            res = emu.lzo_blocks(blocks, [1 << 16] * len(blocks), mode=mode, which=which)
+            for v, b, r in zip(vec, blocks, res):
+                rc, cons, prod, out = fn(b, 1 << 16)
+                if mode == 1 and rc == 1 and r[0] == 2:
+                    continue  # a full dst is reported distinctly in mode 1 (the reference's Buffer.t is unbounded)
+                assert r[0] == _ST[rc] and r[2] == prod and r[3] == out, (v["name"], which)
     txt = workloads.text(120000, 4)
     plains = [txt, bytes(40000), os.urandom(30000), txt[:2000] + os.urandom(20000) + txt[2000:3000], b""]
     comps = [workloads.lzo1x_1_compress(p) for p in plains]
-    res = emu.lzo_blocks(comps, [len(p) for p in plains])
-    for r, c, p in zip(res, comps, plains):
-        assert r == (0, len(c), len(p), p)
+    for which in (0, 3):
+        res = emu.lzo_blocks(comps, [len(p) for p in plains], which=which)
+        for r, c, p in zip(res, comps, plains):
+            assert r == (0, len(c), len(p), p), which
 
 
 def test_lzo_long_overlapping_copy_general_kernel(emu):
@@ -95,7 +98,7 @@ def test_lzo_long_overlapping_copy_general_kernel(emu):
     blocks = [cases.lzo_block(lit[:max(off, 4 + off % 60)], off, ln) for off, ln in
               ((3, 70000), (5, 200000), (30000, 40000), (30000, 100000), (7, 65536 - 7 + 1), (4, 65536))]
     caps = [300000] * len(blocks)
-    for which in (2, 0):
+    for which in (2, 0, 3):
         res = emu.lzo_blocks(blocks, caps, mode=1, which=which)
         for b, r in zip(blocks, res):
             rc, cons, prod, out = oracle.lzo_uncompress_with_buffer(b, 300000)
