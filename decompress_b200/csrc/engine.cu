@@ -102,6 +102,22 @@ struct dcmp_engine {
   uint8_t *d_def_scratch = nullptr;  // [work counters (256 B) | token scratch of every CTA of the two kernels]
   uint8_t *d_def_arena = nullptr;
   size_t def_arena_cap = 0;
+  // the chunk table and the per-stream tables of a deflate call are built in pinned host memory the engine owns and
+  // uploaded asynchronously: the call does not wait for the stream; the next call waits for the uploads of this one
+  // (ev_tab) before it overwrites them
+  uint8_t *h_def_tab = nullptr;
+  size_t def_tab_cap = 0;
+  cudaEvent_t ev_tab = nullptr;
+  bool tab_in_flight = false;
+  int reserve_tab(size_t bytes) {
+    if (!ev_tab) CU(cudaEventCreateWithFlags(&ev_tab, cudaEventDisableTiming));
+    if (tab_in_flight) { CU(cudaEventSynchronize(ev_tab)); tab_in_flight = false; }
+    if (bytes <= def_tab_cap) return DCMP_API_OK;
+    if (h_def_tab) { CU(cudaFreeHost(h_def_tab)); h_def_tab = nullptr; def_tab_cap = 0; }
+    CU(cudaMallocHost((void **)&h_def_tab, bytes + (bytes >> 2) + 4096));
+    def_tab_cap = bytes + (bytes >> 2) + 4096;
+    return DCMP_API_OK;
+  }
   // host-facing calls: three-stage pipeline (H2D | kernels | D2H) over slices of the batch
   static const int MAX_SLICES = 16;
   cudaStream_t s_kernel = nullptr, s_out = nullptr, s_meta = nullptr;
@@ -129,6 +145,17 @@ struct dcmp_engine {
     return DCMP_API_OK;
   }
 };
+
+// The outputs of a batch packed back to back (one CTA per stream): what the host-facing deflate call copies to the host in
+// ONE transfer when the batch is many small streams, instead of one cudaMemcpyAsync per stream.
+__global__ void __launch_bounds__(128)
+dcmp_pack_outputs_kernel(const uint8_t *base, const int64_t *off, const int64_t *len, const int64_t *packed_off, uint8_t *packed) {
+  const int64_t k = blockIdx.x;
+  const int64_t n = len[k];
+  const uint8_t *s = base + off[k];
+  uint8_t *d = packed + packed_off[k];
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) d[i] = s[i];
+}
 
 extern "C" {
 
@@ -191,6 +218,8 @@ void dcmp_engine_destroy(dcmp_engine *e) {
   if (e->ev_last) cudaEventDestroy(e->ev_last);
   if (e->d_def_scratch) cudaFree(e->d_def_scratch);
   if (e->d_def_arena) cudaFree(e->d_def_arena);
+  if (e->h_def_tab) cudaFreeHost(e->h_def_tab);
+  if (e->ev_tab) cudaEventDestroy(e->ev_tab);
   if (e->pipeline_ready) {
     for (int i = 0; i < dcmp_engine::MAX_SLICES; i++) { cudaEventDestroy(e->ev_in[i]); cudaEventDestroy(e->ev_k[i]); cudaEventDestroy(e->ev_meta[i]); }
     cudaStreamDestroy(e->s_kernel);
@@ -555,15 +584,26 @@ int dcmp_deflate_batch_device(dcmp_engine *e, int level, int fmt, int64_t n, con
     e->def_arena_cap = need + (need >> 3);
   }
   uint8_t *A = e->d_def_arena;
-  CU(cudaMemcpyAsync(A + o_chunks, chunks.data(), (size_t)nc * sizeof(dcmp::DfChunkHost), cudaMemcpyHostToDevice, st));
-  CU(cudaMemcpyAsync(A + o_first, first.data(), (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, st));
-  CU(cudaMemcpyAsync(A + o_doff, body_off, (size_t)n * 8, cudaMemcpyHostToDevice, st));
-  CU(cudaMemcpyAsync(A + o_dcap, body_cap, (size_t)n * 8, cudaMemcpyHostToDevice, st));
-  if (gz) {
-    CU(cudaMemcpyAsync(A + o_soff, h_src_off, (size_t)n * 8, cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(A + o_slen, h_src_len, (size_t)n * 8, cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(A + o_goff, h_dst_off, (size_t)n * 8, cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(A + o_gcap, h_dst_cap, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+  // one pinned image of [chunks .. slots) and one upload: the tables sit in the arena exactly as in the image
+  {
+    const int rt = e->reserve_tab(o_slots);
+    if (rt != DCMP_API_OK) return rt;
+    uint8_t *H = e->h_def_tab;
+    memcpy(H + o_chunks, chunks.data(), (size_t)nc * sizeof(dcmp::DfChunkHost));
+    memcpy(H + o_first, first.data(), (size_t)(n + 1) * 8);
+    memcpy(H + o_doff, body_off, (size_t)n * 8);
+    memcpy(H + o_dcap, body_cap, (size_t)n * 8);
+    if (gz) {
+      memcpy(H + o_soff, h_src_off, (size_t)n * 8);
+      memcpy(H + o_slen, h_src_len, (size_t)n * 8);
+      memcpy(H + o_goff, h_dst_off, (size_t)n * 8);
+      memcpy(H + o_gcap, h_dst_cap, (size_t)n * 8);
+    }
+    // (the outs / chunk_dst regions in between are written by the kernels: they are skipped)
+    CU(cudaMemcpyAsync(A + o_chunks, H + o_chunks, o_outs - o_chunks, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(A + o_first, H + o_first, o_slots - o_first, cudaMemcpyHostToDevice, st));
+    CU(cudaEventRecord(e->ev_tab, st));
+    e->tab_in_flight = true;
   }
   int rc = dcmp::launch_deflate(level, fmt, n, nc, nsmall, d_src_base, A + o_chunks, (const int64_t *)(A + o_first), A + o_outs,
                                 A + o_slots, (int64_t *)(A + o_cdst), e->d_def_scratch,
@@ -578,9 +618,7 @@ int dcmp_deflate_batch_device(dcmp_engine *e, int level, int fmt, int64_t n, con
   }
   CU(cudaGetLastError());
   { const int rc1 = e->chain_end(st); if (rc1 != DCMP_API_OK) return rc1; }
-  // the uploads above read host vectors that die with this frame
-  CU(cudaStreamSynchronize(st));
-  return DCMP_API_OK;
+  return DCMP_API_OK; // (nothing here waits for the stream: the tables were uploaded from the engine's pinned staging)
 }
 
 int dcmp_deflate_batch(dcmp_engine *e, int level, int fmt, int64_t n, const uint8_t *src_base, const int64_t *src_off,
@@ -598,9 +636,13 @@ int dcmp_deflate_batch(dcmp_engine *e, int level, int fmt, int64_t n, const uint
   }
   size_t s_bytes = (size_t)(s_hi - s_lo), d_bytes = (size_t)(d_hi - d_lo);
   if ((s_bytes && !src_base) || (d_bytes && !dst_base)) return DCMP_API_INVALID_ARGUMENT;
+  // many small streams: their outputs are packed on the device and come back in one transfer (below)
+  const bool pack = n >= 64 && d_bytes / (size_t)n < (256u << 10);
   size_t o_dst = align_up(s_bytes + 16, 256);
   size_t o_res = align_up(o_dst + d_bytes + 16, 256);
-  int rc = e->reserve(o_res + (size_t)n * 12 + 256);
+  size_t o_tab = align_up(o_res + (size_t)n * 12 + 16, 256);            // pack: offsets in the window, packed offsets
+  size_t o_pack = align_up(o_tab + (pack ? (size_t)n * 16 : 0), 256);
+  int rc = e->reserve(o_pack + (pack ? d_bytes : 0) + 256);
   if (rc != DCMP_API_OK) return rc;
   uint8_t *d_src = e->d_buf, *d_dst = e->d_buf + o_dst;
   int64_t *d_written = (int64_t *)(e->d_buf + o_res);
@@ -615,6 +657,29 @@ int dcmp_deflate_batch(dcmp_engine *e, int level, int fmt, int64_t n, const uint
   CU(cudaMemcpyAsync(written, d_written, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
   CU(cudaMemcpyAsync(status, d_status, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
+  if (pack) {
+    std::vector<int64_t> tab((size_t)n * 2);
+    int64_t total = 0;
+    for (int64_t k = 0; k < n; k++) {
+      tab[k] = dof[k];
+      tab[n + k] = total;
+      if (status[k] == DCMP_OK && written[k] > 0) total += written[k];
+    }
+    if (total > 0) {
+      int64_t *d_tab = (int64_t *)(e->d_buf + o_tab);
+      uint8_t *d_pack = e->d_buf + o_pack;
+      CU(cudaMemcpyAsync(d_tab, tab.data(), (size_t)n * 16, cudaMemcpyHostToDevice, st));
+      dcmp_pack_outputs_kernel<<<(unsigned)n, 128, 0, st>>>(d_dst, d_tab, d_written, d_tab + n, d_pack);
+      CU(cudaGetLastError());
+      e->launches += 1;
+      std::vector<uint8_t> host((size_t)total);
+      CU(cudaMemcpyAsync(host.data(), d_pack, (size_t)total, cudaMemcpyDeviceToHost, st));
+      CU(cudaStreamSynchronize(st));
+      for (int64_t k = 0; k < n; k++)
+        if (status[k] == DCMP_OK && written[k] > 0) memcpy(dst_base + dst_off[k], host.data() + tab[n + k], (size_t)written[k]);
+    }
+    return DCMP_API_OK;
+  }
   for (int64_t k = 0; k < n; k++)
     if (status[k] == DCMP_OK && written[k] > 0)
       CU(cudaMemcpyAsync(dst_base + dst_off[k], d_dst + dof[k], (size_t)written[k], cudaMemcpyDeviceToHost, st));

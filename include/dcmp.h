@@ -180,8 +180,9 @@ int dcmp_deflate_batch(dcmp_engine *e, int level, int fmt, int64_t n,
                        uint8_t *dst_base, const int64_t *dst_off, const int64_t *dst_cap,
                        int64_t *written, int32_t *status);
 /* Data pointers are DEVICE pointers, the four offset tables are HOST arrays (the call cuts the inputs
- * into chunks on the host); d_written / d_status are device arrays.  Synchronises `cuda_stream` once,
- * after the kernels are enqueued. */
+ * into chunks on the host and uploads the chunk table from pinned staging the engine owns); d_written / d_status are
+ * device arrays.  Does not wait for `cuda_stream`: synchronise it (or order later work behind it) before reading them.
+ * The host tables may be reused as soon as the call returns. */
 int dcmp_deflate_batch_device(dcmp_engine *e, int level, int fmt, int64_t n,
                               const uint8_t *d_src_base, const int64_t *h_src_off, const int64_t *h_src_len,
                               uint8_t *d_dst_base, const int64_t *h_dst_off, const int64_t *h_dst_cap,
