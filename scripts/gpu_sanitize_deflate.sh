@@ -14,7 +14,7 @@ ins=[txt, b"", txt[:100], bytes(140000), b"abc", edge, noise, txt[:65537], (b"ab
 for lv in (0,1,6,9):
     d=batch.deflate_streams(ins,level=lv,fmt=batch.FMT_ZLIB,engine=eng)
     assert all(r[0]==0 and zlib.decompress(r[2])==x for r,x in zip(d,ins)), lv
-d=batch.deflate_streams(ins,level=6,fmt=batch.FMT_GZIP,engine=eng); assert all(r[0]==0 for r in d)
+d=batch.deflate_streams(ins,level=6,fmt=_lib.FMT_GZIP,engine=eng); assert all(r[0]==0 for r in d)
 print("sanitizer workload ok")
 PY
 timeout 1200 compute-sanitizer --tool memcheck --error-exitcode 9 python /tmp/sand.py 2>&1 | tail -6 | tee gpurun_out/r2_memcheck_deflate.log
