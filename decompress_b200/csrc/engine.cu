@@ -359,8 +359,16 @@ static int host_batch(dcmp_engine *e, device_batch_fn launch, int fmt, int64_t n
   // bytes, the kernels, device->host copy of the inflated bytes — in slices of consecutive streams, so
   // that PCIe in both directions and the SMs work at the same time.  A slice's input is the byte span
   // its streams reference; if the caller's layout is not monotonic the batch runs as one slice.
-  static const int64_t slice_mb = getenv("DCMP_SLICE_MB") ? std::max(1, atoi(getenv("DCMP_SLICE_MB"))) : 48; // tuning knob
-  int nslice = (int)std::min<int64_t>(dcmp_engine::MAX_SLICES, std::max<int64_t>(1, work / (slice_mb << 20)));
+  // The slices DOUBLE in size: the first one is small, so that its output starts down the link a fraction of a
+  // millisecond into the call, and every later one is as big as everything before it, so that its kernel is done long before
+  // the copy engine is through with its predecessors (C2, end to end against a 52 GB/s ceiling of the link: even slices of
+  // 48 MB 42.8 GB/s — the first device-to-host byte left 0.7 ms into a 6.2 ms call — doubling slices from 2 / 4 / 8 / 16 / 32 MB
+  // 42.7 / 43.8 / 44.5 / 45.2 / 43.6; gpurun_out/r2_e2e_slices.txt).
+  static const int64_t first_mb = getenv("DCMP_SLICE_MB") ? std::max(1, atoi(getenv("DCMP_SLICE_MB"))) : 16; // tuning knobs
+  static const bool even = getenv("DCMP_SLICE_EVEN") != nullptr;   // round 1's even slices of DCMP_SLICE_MB (A/B)
+  int nslice = 1;
+  if (even) nslice = (int)std::min<int64_t>(dcmp_engine::MAX_SLICES, std::max<int64_t>(1, work / (first_mb << 20)));
+  else while (nslice < 8 && work / ((1ll << (nslice + 1)) - 1) >= (first_mb << 20)) nslice++;
   if (n < 4 * nslice) nslice = 1;
   bool monotonic = true;
   for (int64_t k = 1; k < n && monotonic; k++)
@@ -370,9 +378,11 @@ static int host_batch(dcmp_engine *e, device_batch_fn launch, int fmt, int64_t n
   {
     int64_t acc = 0;
     int c = 1;
+    const long double whole = even ? (long double)nslice : (long double)((1ll << nslice) - 1);
     for (int64_t k = 0; k < n && c < nslice; k++) {
       acc += src_len[k] + dst_cap[k];
-      if (acc >= work * c / nslice) cut[c++] = k + 1;
+      const long double part = even ? (long double)c : (long double)((1ll << c) - 1);
+      if ((long double)acc >= (long double)work * part / whole) cut[c++] = k + 1;
     }
     while (c < nslice) cut[c++] = n;
     cut[nslice] = n;
