@@ -1118,7 +1118,7 @@ deflate_cta_kernel(int level, int want_adler, int64_t nchunks, const uint8_t *sr
             const uint32_t h = (rg32(r32, p) * 0x9e3779b1u) >> (32 - DC_HB);
             const uint32_t sh = 8u * (h & 3u);
             const uint32_t slot_i = (atomicAdd(&S.cnt[h >> 2], 1u << sh) >> sh) & (uint32_t)(WAYS - 1);
-            S.tab[h * WAYS + slot_i] = (uint16_t)p;
+            st_relaxed_u16(&S.tab[h * WAYS + slot_i], (uint16_t)p);
           }
         }
         // ------------------------------------------------------------ 1 tokenise, half by half
@@ -1153,7 +1153,7 @@ deflate_cta_kernel(int level, int want_adler, int64_t nchunks, const uint8_t *sr
               hsh = (rg32(r32, p) * 0x9e3779b1u) >> (32 - DC_HB);
               const uint32_t sh = 8u * (hsh & 3u);
               const uint32_t slot_i = (atomicAdd(&S.cnt[hsh >> 2], 1u << sh) >> sh) & (uint32_t)(WAYS - 1);
-              S.tab[hsh * WAYS + slot_i] = (uint16_t)p;
+              st_relaxed_u16(&S.tab[hsh * WAYS + slot_i], (uint16_t)p); // (more than WAYS positions of a step in one bucket share slots: any of them is a valid entry)
             }
             __syncthreads();
             // -- match.  Pass 1: every bucket entry that lies in the window before p and shares its first four bytes is

@@ -15,6 +15,8 @@ for lv in (0,1,6,9):
     d=batch.deflate_streams(ins,level=lv,fmt=batch.FMT_ZLIB,engine=eng)
     assert all(r[0]==0 and zlib.decompress(r[2])==x for r,x in zip(d,ins)), lv
 d=batch.deflate_streams(ins,level=6,fmt=_lib.FMT_GZIP,engine=eng); assert all(r[0]==0 for r in d)
+small=[txt[k*37:k*37+20+k*11] for k in range(100)]   # many small streams: the warp-per-chunk kernel, outputs packed for one transfer
+d=batch.deflate_streams(small,level=6,fmt=batch.FMT_ZLIB,engine=eng); assert all(r[0]==0 and zlib.decompress(r[2])==x for r,x in zip(d,small))
 print("sanitizer workload ok")
 PY
 timeout 1200 compute-sanitizer --tool memcheck --error-exitcode 9 python /tmp/sand.py 2>&1 | tail -6 | tee gpurun_out/r2_memcheck_deflate.log
