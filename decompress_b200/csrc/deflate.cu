@@ -1545,7 +1545,8 @@ size_t deflate_cta_smem_bytes(int level) { return (level >= 7 ? sizeof(DcSmemT<1
 static_assert(sizeof(DcSmemT<8>) + 128 + 1024 <= 227 * 1024 / 2, "two compressor CTAs per SM");
 #ifndef DCMP_EMU
 // DCMP_DEF_KERNEL=warp: every chunk goes to the warp-per-chunk kernel (the round-1 path; A/B measurements)
-static bool deflate_force_warp() { const char *v = getenv("DCMP_DEF_KERNEL"); return v && v[0] == 'w'; }
+// (latched at the first call: the scratch of the warp-per-chunk kernel is sized by it)
+static bool deflate_force_warp() { static const bool f = [] { const char *v = getenv("DCMP_DEF_KERNEL"); return v && v[0] == 'w'; }(); return f; }
 // resident CTAs per SM of the two kernels (the persistent grids and their scratch are sized with them)
 int deflate_ctas_per_sm() {
   int n = 0;

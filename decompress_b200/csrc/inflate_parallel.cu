@@ -77,6 +77,11 @@ constexpr int WARMUP_BITS = DCMP_WARMUP_BITS; // a lane's speculative pass start
 #ifndef DCMP_CKPT_SHIFT
 #define DCMP_CKPT_SHIFT 4
 #endif
+#ifndef DCMP_D_PAIRS
+#define DCMP_D_PAIRS 0                    // phase D: 1 = two consecutive literals of a lane are replayed in one step: a fifth fewer
+                                          // warp-steps on text, but 150.4 vs 154.6 GB/s on C2 (the two token loads of a pair
+                                          // have one step of lead instead of three)
+#endif
 constexpr int CKPT_SHIFT = DCMP_CKPT_SHIFT; // one checkpoint per 2^CKPT_SHIFT-bit window of the sub-chunk
 constexpr uint32_t CKPT_NONE = 0x80000000u; // no token of the speculative pass starts in this window (a long match can skip one)
 static_assert(CKPT_SHIFT >= 3 && CKPT_SHIFT <= 5, "");
@@ -1233,13 +1238,23 @@ inflate_parallel_kernel(int fmt, int64_t nstreams, const uint8_t *src_base, cons
           // -- next token, for the lanes that finished the previous one
           bool fetch = active && rem == 0;
           if (fetch && ti == total_tok) { active = false; fetch = false; }
-          uint32_t t = 0;
+          uint32_t t = 0, t2 = 0;
+          bool pair = false; // (DCMP_D_PAIRS) two literals in a row leave in one step
           if (fetch) {
             t = q0;
-            q0 = q1;
-            q1 = q2;
-            if (ti + 3 < total_tok) q2 = tok_at(ti + 3);
-            ti++;
+            pair = DCMP_D_PAIRS && ti + 1 < total_tok && !tok_is_match(t) && !tok_is_match(q1);
+            if (pair) {
+              t2 = q1;
+              q0 = q2;
+              if (ti + 3 < total_tok) q1 = tok_at(ti + 3);
+              if (ti + 4 < total_tok) q2 = tok_at(ti + 4);
+              ti += 2;
+            } else {
+              q0 = q1;
+              q1 = q2;
+              if (ti + 3 < total_tok) q2 = tok_at(ti + 3);
+              ti++;
+            }
           }
           const bool new_match = fetch && tok_is_match(t);
           if (new_match) {
@@ -1254,7 +1269,7 @@ inflate_parallel_kernel(int fmt, int64_t nstreams, const uint8_t *src_base, cons
           }
           // -- this step's symbols (branch-free for the three common cases)
           const bool lit = fetch && !new_match;
-          const uint32_t n = lit ? 1u : (rem < 8u ? rem : 8u);  // 0 for idle lanes
+          const uint32_t n = lit ? (pair ? 2u : 1u) : (rem < 8u ? rem : 8u);  // 0 for idle lanes
           const bool in_round = s >= (int32_t)bias;
           const bool in_hist = s + (int32_t)n <= (int32_t)bias;
           const bool slow = rem > 0u && (in_round ? dist < n : !in_hist);
@@ -1285,7 +1300,7 @@ inflate_parallel_kernel(int fmt, int64_t nstreams, const uint8_t *src_base, cons
           const uint32_t p1 = in_round ? m0 + 0x00020002u : __byte_perm(ha, 0u, 0x4342);
           const uint32_t p2 = in_round ? m0 + 0x00040004u : __byte_perm(hb, 0u, 0x4140);
           const uint32_t p3 = in_round ? m0 + 0x00060006u : __byte_perm(hb, 0u, 0x4342);
-          if (lit) p0 = t & 0xffu;
+          if (lit) p0 = (t & 0xffu) | ((t2 & 0xffu) << 16);
           STAT(if (!slow && rem > 0) { if (in_round) g_stats.markers += n; else g_stats.hist_bytes += n; })
           if (slow) {
             // straddles the start of the round, or overlaps itself inside the group (point at the first period)
