@@ -79,8 +79,8 @@ constexpr int WARMUP_BITS = DCMP_WARMUP_BITS; // a lane's speculative pass start
 #endif
 #ifndef DCMP_D_PAIRS
 #define DCMP_D_PAIRS 0                    // phase D: 1 = two consecutive literals of a lane are replayed in one step: a fifth fewer
-                                          // warp-steps on text, but 150.4 vs 154.6 GB/s on C2 (the two token loads of a pair
-                                          // have one step of lead instead of three)
+                                          // warp-steps on text, but 151.0 vs 154.6 GB/s on C2 (150.4 with a three-deep token
+                                          // queue): the two fetch paths diverge inside the warp
 #endif
 constexpr int CKPT_SHIFT = DCMP_CKPT_SHIFT; // one checkpoint per 2^CKPT_SHIFT-bit window of the sub-chunk
 constexpr uint32_t CKPT_NONE = 0x80000000u; // no token of the speculative pass starts in this window (a long match can skip one)
@@ -1232,6 +1232,10 @@ inflate_parallel_kernel(int fmt, int64_t nstreams, const uint8_t *src_base, cons
         if (0 < total_tok) q0 = tok_at(0);
         if (1 < total_tok) q1 = tok_at(1);
         if (2 < total_tok) q2 = tok_at(2);
+#if DCMP_D_PAIRS
+        uint32_t q3 = 0; // (a pair consumes two tokens: one more in flight keeps the lead of the loads)
+        if (3 < total_tok) q3 = tok_at(3);
+#endif
         bool active = total_tok > 0;
         while (__any_sync(0xffffffffu, active)) {
           STAT(if (active) iters++;)
@@ -1242,19 +1246,28 @@ inflate_parallel_kernel(int fmt, int64_t nstreams, const uint8_t *src_base, cons
           bool pair = false; // (DCMP_D_PAIRS) two literals in a row leave in one step
           if (fetch) {
             t = q0;
-            pair = DCMP_D_PAIRS && ti + 1 < total_tok && !tok_is_match(t) && !tok_is_match(q1);
+#if DCMP_D_PAIRS
+            pair = ti + 1 < total_tok && !tok_is_match(t) && !tok_is_match(q1);
             if (pair) {
               t2 = q1;
               q0 = q2;
-              if (ti + 3 < total_tok) q1 = tok_at(ti + 3);
+              q1 = q3;
               if (ti + 4 < total_tok) q2 = tok_at(ti + 4);
+              if (ti + 5 < total_tok) q3 = tok_at(ti + 5);
               ti += 2;
             } else {
               q0 = q1;
               q1 = q2;
-              if (ti + 3 < total_tok) q2 = tok_at(ti + 3);
+              q2 = q3;
+              if (ti + 4 < total_tok) q3 = tok_at(ti + 4);
               ti++;
             }
+#else
+            q0 = q1;
+            q1 = q2;
+            if (ti + 3 < total_tok) q2 = tok_at(ti + 3);
+            ti++;
+#endif
           }
           const bool new_match = fetch && tok_is_match(t);
           if (new_match) {
