@@ -860,6 +860,7 @@ deflate_tmake_kernel(const int32_t *freqs, int length, int max_bits, int32_t *le
   if (lane == 0) *max_code_out = mc;
 }
 
+#ifdef DCMP_EMU
 // (tests: the CTA-per-chunk compressor's builder on its own)
 __global__ void __launch_bounds__(32)
 deflate_tmake_fast_kernel(const int32_t *freqs, int length, int max_bits, int32_t *lens_out, int32_t *codes_out, int32_t *max_code_out) {
@@ -874,6 +875,7 @@ deflate_tmake_fast_kernel(const int32_t *freqs, int length, int max_bits, int32_
   for (int i = lane; i < length; i += 32) { lens_out[i] = S.len[i]; codes_out[i] = S.code[i]; }
   if (lane == 0) *max_code_out = mc;
 }
+#endif
 
 template <int HB>
 __global__ void __launch_bounds__(DF_WARPS * 32)
