@@ -13,7 +13,7 @@
 //
 // Layout.  Every input stream is cut into 64 KiB chunks, one DEFLATE block each (Dynamic, Fixed or Stored, whichever is
 // smallest).  Two kernels share a batch:
-//   deflate_cta_kernel    one CTA of 512 threads per run of consecutive chunks: input staged in shared memory by TMA,
+//   deflate_cta_kernel    one CTA of 512 (1024) threads per run of consecutive chunks: input staged in shared memory by TMA,
 //                         the 32 KiB window and its hash buckets carried from chunk to chunk, per-level chain / nice /
 //                         lazy (de.ml:4030-4049), block-wide histogram, parallel Huffman build, all warps packing
 //                         bits at scanned offsets — described where it is defined, further down;
@@ -906,14 +906,14 @@ deflate_chunk_kernel(int level, int want_adler, int64_t nchunks, const uint8_t *
 // read through L1/L2) stays for the small inputs of a batch — thousands of few-hundred-byte streams keep every warp of the
 // GPU busy there — this one takes everything longer than DF_SMALL.
 //
-// One CTA of 512 threads owns a RUN of consecutive 64 KiB chunks of one stream and keeps De.Lz77's state on chip
+// One CTA of 512 threads (1024 with the 16-way table) owns a RUN of consecutive 64 KiB chunks of one stream and keeps De.Lz77's state on chip
 // across them (de.ml:4076-4100: the window, its hash heads and chains):
 //   ring   64 KiB of shared memory = the last 64 KiB of the input, indexed by (global address & 0xffff): the 32 KiB window
 //          plus the 32 KiB half that is being tokenised (loaded with 128-bit copies; a chunk is two halves);
 //   table  2048 hash buckets of WAYS 16-bit ring positions, replaced round-robin: the `max_chain` most recent
 //          positions with the same hash4 (de.ml:4067-4071).  What zlib keeps as head[] + prev[] chains; WAYS = 8 for
 //          levels 1..6, 16 for 7..9, of which a level examines min(max_chain, WAYS) (level table de.ml:4030-4049).
-// A step = 512 consecutive positions, one per thread:
+// A step = as many consecutive positions as the CTA has threads, one per thread:
 //   insert   every position enters its bucket (an atomic counter per bucket hands out the slot)          -- barrier
 //   match    every position compares itself with the bucket's entries that lie before it (positions of the same
 //            step included), eight bytes at a time out of the ring; longest wins, nearest on ties; the search stops
@@ -927,8 +927,9 @@ deflate_chunk_kernel(int level, int want_adler, int64_t nchunks, const uint8_t *
 // and the bits, packed by all sixteen warps at once — per-warp bit totals, a scan, every warp into its own bit window
 // that drains to the chunk's slot with plain 32-bit stores (an atomicOr for the two words a warp shares with its
 // neighbours).  Matches do not cross a half (the bytes behind it are not in the ring yet): one match per 32 KiB is cut.
-constexpr int DC_T = 512;
-constexpr int DC_NW = DC_T / 32;
+// threads of a CTA: 512 with the 8-way table (two CTAs per SM), 1024 with the 16-way table (its 146 KiB of shared memory
+// leave room for one CTA per SM only: twice the warps keep the SM as busy)
+__host__ __device__ constexpr int dc_threads(int ways) { return ways == 16 ? 1024 : 512; }
 constexpr int DC_HB = 11;
 constexpr int DC_HALF = 32768;
 constexpr int DC_RING = 65536;
@@ -943,6 +944,7 @@ constexpr uint32_t DC_EXIT_END = 1000;   // transfer function: ran into the end 
 template <int WAYS>
 struct DcSmemT {
   static constexpr int HASH_BITS = DC_HB;
+  static constexpr int DC_NW = dc_threads(WAYS) / 32;
   __align__(16) uint8_t ring[DC_RING + DC_MIRROR]; // + a copy of its first bytes: a read that starts inside the ring never wraps
   __align__(16) uint16_t tab[(1 << DC_HB) * WAYS];
   uint32_t cnt[(1 << DC_HB) / 4];          // four 8-bit insertion counters per word
@@ -1067,11 +1069,12 @@ __device__ __forceinline__ DcLevel dc_level(int level, int WAYS) {
 }
 
 template <int WAYS>
-__global__ void __launch_bounds__(DC_T, WAYS == 8 ? 2 : 1)
+__global__ void __launch_bounds__(dc_threads(WAYS), WAYS == 8 ? 2 : 1)
 deflate_cta_kernel(int level, int want_adler, int64_t nchunks, const uint8_t *src_base, const DfChunk *chunks,
                    DfChunkOut *outs, uint8_t *slots, uint32_t *tok_scratch, unsigned long long *work_counter, int tune_ways) {
   DCMP_DYN_SMEM(smem_raw);
   typedef DcSmemT<WAYS> Smem;
+  constexpr int DC_T = dc_threads(WAYS), DC_NW = DC_T / 32;
   Smem &S = *reinterpret_cast<Smem *>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   uint32_t *tok = tok_scratch + (size_t)blockIdx.x * DF_CHUNK;
@@ -1606,12 +1609,12 @@ int launch_deflate(int level, int fmt, int64_t nstreams, int64_t nchunks, int64_
     if (level >= 7) {
       int ctas = sm_count; // 1 per SM: 146 KiB of shared memory each
       if (ctas > want) ctas = (int)want;
-      deflate_cta_kernel<16><<<(unsigned)ctas, DC_T, deflate_cta_smem_bytes(level), stream>>>(
+      deflate_cta_kernel<16><<<(unsigned)ctas, dc_threads(16), deflate_cta_smem_bytes(level), stream>>>(
           level, want_adler, nchunks, src_base, (const DfChunk *)chunks, (DfChunkOut *)outs, slots, tok_cta, counters, tune_ways);
     } else {
       int ctas = DC_CTAS_PER_SM * sm_count;
       if (ctas > want) ctas = (int)want;
-      deflate_cta_kernel<8><<<(unsigned)ctas, DC_T, deflate_cta_smem_bytes(level), stream>>>(
+      deflate_cta_kernel<8><<<(unsigned)ctas, dc_threads(8), deflate_cta_smem_bytes(level), stream>>>(
           level, want_adler, nchunks, src_base, (const DfChunk *)chunks, (DfChunkOut *)outs, slots, tok_cta, counters, tune_ways);
     }
   }

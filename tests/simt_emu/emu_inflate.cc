@@ -103,7 +103,7 @@ int emu_deflate_batch(int level, int fmt, int64_t n, const uint8_t *src, const i
   unsigned long long counters[2] = {0, 0};
   if (nc - nsmall > 0) {
     std::vector<uint32_t> tokc((size_t)ctas * DF_CHUNK);
-    simt::launch(simt::dim3(ctas), simt::dim3(DC_T), deflate_cta_smem_bytes(level), [&]() {
+    simt::launch(simt::dim3(ctas), simt::dim3(dc_threads(level >= 7 ? 16 : 8)), deflate_cta_smem_bytes(level), [&]() {
       if (level >= 7) deflate_cta_kernel<16>(level, fmt == DCMP_FMT_ZLIB, nc, src, chunks.data(), outs.data(), slots.data(), tokc.data(), &counters[0], 0);
       else deflate_cta_kernel<8>(level, fmt == DCMP_FMT_ZLIB, nc, src, chunks.data(), outs.data(), slots.data(), tokc.data(), &counters[0], 0);
     });
