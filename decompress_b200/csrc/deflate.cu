@@ -1054,7 +1054,7 @@ struct DcBits {
   }
 };
 
-struct DcLevel { int ways, nice, lazy, maxlong; };
+struct DcLevel { int ways, nice, lazy; };
 __device__ __forceinline__ DcLevel dc_level(int level, int WAYS) {
   // {good_length; max_lazy; nice_length; max_chain} of de.ml:4030-4049; levels 1..3 are zlib's deflate_fast (no lazy
   // evaluation); good_length shortens the chain of the LAZY search after a good match: there is no "previous match"
@@ -1064,7 +1064,6 @@ __device__ __forceinline__ DcLevel dc_level(int level, int WAYS) {
   c.ways = chain < WAYS ? chain : WAYS;
   c.nice = level <= 1 ? 8 : level == 2 ? 16 : level == 3 ? 32 : level == 4 ? 16 : level == 5 ? 32 : level <= 7 ? 128 : 258;
   c.lazy = level <= 3 ? 0 : level == 4 ? 4 : level <= 6 ? 16 : level == 7 ? 32 : level == 8 ? 128 : 258;
-  c.maxlong = level <= 6 ? 2 : 3;
   return c;
 }
 
@@ -1184,9 +1183,14 @@ deflate_cta_kernel(int level, int want_adler, int64_t nchunks, const uint8_t *sr
                     if (dist - 1u < maxdist && rg32(r32, q) == P4) {
                       const uint32_t x = rg32(r32, q + 4u) ^ P4b;
                       if (x == 0u && maxlen > 8) {
-                        if (dist < lg1) { lg3 = lg2; lg2 = lg1; lg1 = dist; }
-                        else if (dist < lg2) { if (dist != lg1) { lg3 = lg2; lg2 = dist; } }
-                        else if (dist < lg3 && dist != lg2) lg3 = dist;
+                        if constexpr (WAYS == 16) { // (three long candidates with the deep table, two otherwise)
+                          if (dist < lg1) { lg3 = lg2; lg2 = lg1; lg1 = dist; }
+                          else if (dist < lg2) { if (dist != lg1) { lg3 = lg2; lg2 = dist; } }
+                          else if (dist < lg3 && dist != lg2) lg3 = dist;
+                        } else {
+                          if (dist < lg1) { lg2 = lg1; lg1 = dist; }
+                          else if (dist < lg2 && dist != lg1) lg2 = dist;
+                        }
                       } else {
                         const int l = x ? 4 + ((__ffs((int)x) - 1) >> 3) : 8; // (capped to maxlen below)
                         if (l > mlen || (l == mlen && (int)dist < mdist)) { mlen = l; mdist = (int)dist; }
@@ -1196,7 +1200,6 @@ deflate_cta_kernel(int level, int want_adler, int64_t nchunks, const uint8_t *sr
                 }
               }
               // (measuring more than two candidates that share eight bytes buys 0.15 % of output at level 6: the deep levels take three)
-              if (L.maxlong < 3) lg3 = 0x10000u;
             }
             // Pass 2: the long candidates, eight bytes per step; the lanes of a warp step together (a lane takes its next
             // candidate when one ends), so the loop runs as long as the warp's longest chain of them, not their sum
