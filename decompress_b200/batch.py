@@ -81,12 +81,13 @@ def inflate_device(fmt, d_src, d_src_off, d_src_len, d_dst, d_dst_off, d_dst_cap
     _lib.check(rc, "dcmp_inflate_batch_device")
 
 
-def deflate_streams(inputs, caps=None, level=6, fmt=FMT_RAW, engine=None):
-    """dcmp_deflate_batch on a list of byte strings: list of (status, written, compressed bytes)."""
+def deflate_streams(inputs, caps=None, level=6, fmt=FMT_RAW, engine=None, align=16):
+    """dcmp_deflate_batch on a list of byte strings: list of (status, written, compressed bytes).  `align`: alignment of
+    every input and output window inside the two slabs (the C ABI takes any)."""
     eng = engine or _lib.default_engine()
     if caps is None:
         caps = [int(_lib.lib().dcmp_deflate_bound(len(x), fmt)) for x in inputs]
-    src, so, sl, dst, do, dc = pack(inputs, caps)
+    src, so, sl, dst, do, dc = pack(inputs, caps, align=align)
     n = len(inputs)
     wr = np.zeros(n, dtype=np.int64)
     st = np.zeros(n, dtype=np.int32)

@@ -71,11 +71,12 @@ def lzo_blocks(blocks, caps, mode=0, which=0):
     return [(int(st[k]), int(cons[k]), int(prod[k]), dst[do[k]:do[k] + int(min(max(prod[k], 0), dc[k]))].tobytes()) for k in range(n)]
 
 
-def deflate_streams(inputs, caps, level=6, fmt=0):
-    """Deflate kernels on the emulator: list of (status, written, bytes)."""
+def deflate_streams(inputs, caps, level=6, fmt=0, align=16):
+    """Deflate kernels on the emulator: list of (status, written, bytes).  `align`: alignment of every stream inside the
+    batch's slab (1: the streams follow each other byte for byte)."""
     from decompress_b200 import batch
 
-    src, so, sl, dst, do, dc = batch.pack(inputs, caps)
+    src, so, sl, dst, do, dc = batch.pack(inputs, caps, align=align)
     n = len(inputs)
     wr = np.zeros(n, dtype=np.int64)
     st = np.full(n, -1, dtype=np.int32)

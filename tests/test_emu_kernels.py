@@ -130,8 +130,8 @@ def test_deflate_window_edge_at_distance_32768_in_an_unaligned_batch(emu):
     and the bytes around a half are window, not padding (tests/cases.py: deflate_window_edge_stream)."""
     edge = cases.deflate_window_edge_stream()
     ins = [b"abc", edge, b"z" * 7, edge[5:], edge]
-    for level in (1, 6, 9):
-        res = emu.deflate_streams(ins, [len(x) + len(x) // 8 + 64 for x in ins], level=level, fmt=batch.FMT_ZLIB)
+    for level, align in ((1, 1), (6, 1), (9, 1), (6, 16)):   # (align = 1: streams at odd addresses of the slab)
+        res = emu.deflate_streams(ins, [len(x) + len(x) // 8 + 64 for x in ins], level=level, fmt=batch.FMT_ZLIB, align=align)
         for (st, written, comp), x in zip(res, ins):
             assert st == 0 and zlib.decompress(comp) == x
             assert oracle.zl_inflate_ns(comp, len(x))[:3] == (0, written, len(x))

@@ -60,9 +60,9 @@ def test_window_edge_at_distance_32768_in_an_unaligned_batch(eng):
     (tests/cases.py: deflate_window_edge_stream)."""
     from tests import cases
     edge = cases.deflate_window_edge_stream()
-    ins = [b"abc", edge, b"z" * 7, edge[5:], edge, bytes(9) + edge]
-    for level in (1, 6, 9):
-        _roundtrip(ins, batch.deflate_streams(ins, level=level, fmt=batch.FMT_ZLIB, engine=eng), batch.FMT_ZLIB, eng)
+    ins = [b"abc", edge, b"z" * 7, edge[5:], edge, bytes(9) + edge, workloads.text(200001, 9)]
+    for level, align in ((1, 1), (6, 1), (9, 1), (6, 16)):   # (align = 1: the streams follow each other byte for byte)
+        _roundtrip(ins, batch.deflate_streams(ins, level=level, fmt=batch.FMT_ZLIB, engine=eng, align=align), batch.FMT_ZLIB, eng)
 
 
 def test_compresses_text(eng):
