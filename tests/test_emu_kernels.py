@@ -137,6 +137,33 @@ def test_deflate_window_edge_at_distance_32768_in_an_unaligned_batch(emu):
             assert oracle.zl_inflate_ns(comp, len(x))[:3] == (0, written, len(x))
 
 
+def test_deflate_random_batches_round_trip(emu):
+    """Seeded random batches through both compressors: sizes around the 4 KiB / 32 KiB / 64 KiB boundaries, text, runs,
+    noise, short periods, every level class, both slab alignments; zlib and the oracle's Inf must give the input back and
+    consume exactly `written` bytes (fuzz/fuzz.ml:169-194)."""
+    import random
+    rng = random.Random(3)
+    txt = bytes(workloads.text(150000, 77))
+
+    def gen():
+        k = rng.randrange(6)
+        n = rng.choice([0, 1, 4, 5, 100, 4096, 4097, 32767, 32768, 32769, 65535, 65536, 65537, rng.randrange(1, 140000)])
+        if k == 0: return txt[rng.randrange(1000):][:n]
+        if k == 1: return bytes(n)
+        if k == 2: return bytes(rng.randrange(256) for _ in range(min(n, 40000)))
+        if k == 3: return (bytes(rng.randrange(256) for _ in range(rng.randrange(1, 300))) * (n // 2 + 1))[:n]
+        if k == 4: return (txt[:rng.randrange(1, 40000)] * 8)[:n]
+        return txt[:n // 2] + bytes(n - n // 2)
+
+    for _ in range(12):
+        ins = [gen() for _ in range(rng.randrange(1, 4))]
+        level, align = rng.choice([1, 4, 6, 9]), rng.choice([1, 16])
+        res = emu.deflate_streams(ins, [len(x) + len(x) // 8 + 128 for x in ins], level=level, fmt=batch.FMT_ZLIB, align=align)
+        for (st, written, comp), x in zip(res, ins):
+            assert st == 0 and zlib.decompress(comp) == x, (level, align, len(x))
+            assert oracle.zl_inflate_ns(comp, len(x))[:3] == (0, written, len(x)), (level, align, len(x))
+
+
 def test_fast_code_builder_is_complete_limited_and_as_cheap_as_t_make(emu):
     """df_build_code_fast (the CTA-per-chunk compressor's Huffman builder: sort, two-queue merge, pointer jumping, gen_bitlen's
     repair) against De.T.make as the oracle restates it: every used symbol has a code, no code is longer than the limit, the
