@@ -11,7 +11,7 @@
 // valid DEFLATE stream — parity for this path is "the reference's Inf and system zlib both
 // inflate it back byte-identically" (SURVEY.md §8c), which tests/test_gpu_deflate.py checks.
 //
-// Layout.  Every input stream is cut into 64 KiB chunks, one DEFLATE block each (Dynamic, Fixed or Stored, whichever is
+// Layout.  Every input stream is cut into 128 KiB chunks, one DEFLATE block each (Dynamic, Fixed or Stored, whichever is
 // smallest).  Two kernels share a batch:
 //   deflate_cta_kernel    one CTA of 512 (1024) threads per run of consecutive chunks: input staged in shared memory by TMA,
 //                         the 32 KiB window and its hash buckets carried from chunk to chunk, per-level chain / nice /
@@ -40,7 +40,7 @@
 
 namespace dcmp {
 
-constexpr int DF_CHUNK = 65536;
+constexpr int DF_CHUNK = 131072;          // input bytes per DEFLATE block (four 32 KiB halves of the ring)
 #ifndef DCMP_DF_WARPS
 #define DCMP_DF_WARPS 4
 #endif
@@ -71,7 +71,7 @@ constexpr int DF_HEAP = 2 * 286 + 1;   // zlib's HEAP_SIZE (de.ml:233)
 // De.T.make's state (de.ml:2013-2026); only alive after tokenising, so it overlays the hash table.  A heap slot carries
 // its ordering key — frequency and subtree depth, what zlib's `smaller` compares (de.ml:1879-1885) — next to the node,
 // so a step down the heap is one round of loads, not a chain through freq[heap[j]] and depth[heap[j]].
-// KEY: 32 bits hold frequencies below 2^23 (a 64 KiB chunk), the command-level entry points use 64.
+// KEY: 32 bits hold frequencies below 2^23 (a 128 KiB chunk has at most 2^17 tokens), the command-level entry points use 64.
 template <class KEY>
 struct DfTreeT {
   static constexpr int SHIFT = 9;   // depth < 2^9 (at most 285)
@@ -378,7 +378,7 @@ __device__ int df_build_code_fast(SM &S, const uint32_t *freq, int n, int max_bi
     T.info[0][2 * m - 2] = (uint32_t)(2 * m - 2); // the root: distance 0 to itself
   }
   __syncwarp();
-  // depths by pointer jumping (a code of a 64 KiB chunk is at most 24 deep: six doublings reach 64)
+  // depths by pointer jumping (a code over at most 2^17 + 1 tokens is at most 26 deep: six doublings reach 64)
   const int nodes = 2 * m - 1;
   for (int r = 0; r < 6; r++) {
     const uint32_t *src = T.info[r & 1];
@@ -906,10 +906,10 @@ deflate_chunk_kernel(int level, int want_adler, int64_t nchunks, const uint8_t *
 // read through L1/L2) stays for the small inputs of a batch — thousands of few-hundred-byte streams keep every warp of the
 // GPU busy there — this one takes everything longer than DF_SMALL.
 //
-// One CTA of 512 threads (1024 with the 16-way table) owns a RUN of consecutive 64 KiB chunks of one stream and keeps De.Lz77's state on chip
+// One CTA of 512 threads (1024 with the 16-way table) owns a RUN of consecutive 128 KiB chunks of one stream and keeps De.Lz77's state on chip
 // across them (de.ml:4076-4100: the window, its hash heads and chains):
 //   ring   64 KiB of shared memory = the last 64 KiB of the input, indexed by (global address & 0xffff): the 32 KiB window
-//          plus the 32 KiB half that is being tokenised (loaded with 128-bit copies; a chunk is two halves);
+//          plus the 32 KiB half that is being tokenised (staged by TMA; a chunk is four halves);
 //   table  2048 hash buckets of WAYS 16-bit ring positions, replaced round-robin: the `max_chain` most recent
 //          positions with the same hash4 (de.ml:4067-4071).  What zlib keeps as head[] + prev[] chains; WAYS = 8 for
 //          levels 1..6, 16 for 7..9, of which a level examines min(max_chain, WAYS) (level table de.ml:4030-4049).
@@ -935,7 +935,7 @@ constexpr int DC_HALF = 32768;
 constexpr int DC_RING = 65536;
 constexpr int DC_MIRROR = 288;           // >= 258 + 8 + 16: the longest match plus the footprint of the word loads
 constexpr int DC_WIN = 64;               // words of a warp's output bit window
-constexpr int DC_RUN = 4;                // consecutive chunks a CTA claims at once (the window carries over inside a run)
+constexpr int DC_RUN = 2;                // consecutive chunks a CTA claims at once (the window carries over inside a run)
 #ifndef DCMP_DC_EXACT_TREE
 #define DCMP_DC_EXACT_TREE 0             // 1: De.T.make's heap in this kernel too (its tie-breaks), ~15 % slower on C3
 #endif
