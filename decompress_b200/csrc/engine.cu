@@ -647,7 +647,7 @@ int dcmp_deflate_batch(dcmp_engine *e, int level, int fmt, int64_t n, const uint
   size_t s_bytes = (size_t)(s_hi - s_lo), d_bytes = (size_t)(d_hi - d_lo);
   if ((s_bytes && !src_base) || (d_bytes && !dst_base)) return DCMP_API_INVALID_ARGUMENT;
   // many small streams: their outputs are packed on the device and come back in one transfer (below)
-  const bool pack = n >= 64 && d_bytes / (size_t)n < (256u << 10);
+  const bool pack = n >= 64 && d_bytes / (size_t)n < (256u << 10) && d_bytes <= ((size_t)1 << 30); // (the packed copy is staged in host memory once more)
   size_t o_dst = align_up(s_bytes + 16, 256);
   size_t o_res = align_up(o_dst + d_bytes + 16, 256);
   size_t o_tab = align_up(o_res + (size_t)n * 12 + 16, 256);            // pack: offsets in the window, packed offsets
